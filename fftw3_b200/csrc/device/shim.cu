@@ -1,0 +1,211 @@
+// shim.cu -- implementation of the C-ABI in include/b200fft_device.h on CUDA.
+// Everything the C host layer needs from the device goes through here.
+// There is NO CPU fallback: without a usable device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "fft_generic.cuh"
+#include "real_ops.cuh"
+#include "fft_fast.cuh"
+
+namespace {
+char g_err[512] = "";
+cudaStream_t g_stream = 0;
+int g_init = 0, g_ndev = 0, g_sms = 0;
+size_t g_max_smem = 0;
+char g_name[256] = "";
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return -1;
+}
+
+int ensure_init()
+{
+    if (g_init) return g_ndev > 0 ? 0 : -1;
+    g_init = 1;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_err, sizeof g_err, "no CUDA device: %s", cudaGetErrorString(e));
+        g_ndev = 0;
+        return -1;
+    }
+    g_ndev = n;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    strncpy(g_name, prop.name, sizeof g_name - 1);
+    g_sms = prop.multiProcessorCount;
+    g_max_smem = prop.sharedMemPerBlockOptin;
+    cudaFuncSetAttribute(b2::fft_generic_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)g_max_smem);
+    cudaFuncSetAttribute(b2::fft_generic_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)g_max_smem);
+    b2fast::init((int)g_max_smem);
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int b2d_device_count(void) { ensure_init(); return g_ndev; }
+const char *b2d_device_name(void) { ensure_init(); return g_name; }
+int b2d_sm_count(void) { ensure_init(); return g_sms; }
+const char *b2d_last_error(void) { return g_err; }
+size_t b2d_max_smem_per_block(void) { ensure_init(); return g_max_smem; }
+uint64_t b2d_launch_count(void) { return g_launches.load(); }
+
+int b2d_pointer_is_device(const void *p)
+{
+    if (ensure_init()) return -1;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+void *b2d_malloc(size_t bytes)
+{
+    if (ensure_init()) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(e, "cudaMalloc"); return nullptr; }
+    return p;
+}
+void b2d_free(void *p) { if (p) cudaFree(p); }
+
+void *b2d_malloc_host(size_t bytes)
+{
+    if (ensure_init()) return nullptr;
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(e, "cudaMallocHost"); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b2d_free_host(void *p) { if (p) cudaFreeHost(p); }
+
+int b2d_memcpy_h2d(void *d, const void *s, size_t n)
+{
+    cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "memcpy h2d");
+}
+int b2d_memcpy_d2h(void *d, const void *s, size_t n)
+{
+    cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g_stream);
+    if (e != cudaSuccess) return fail(e, "memcpy d2h");
+    e = cudaStreamSynchronize(g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "memcpy d2h sync");
+}
+int b2d_memcpy_d2d(void *d, const void *s, size_t n)
+{
+    cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "memcpy d2d");
+}
+int b2d_memset(void *d, int byte, size_t n)
+{
+    cudaError_t e = cudaMemsetAsync(d, byte, n, g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "memset");
+}
+int b2d_sync(void)
+{
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) return fail(e, "sync");
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail(e, "kernel");
+}
+void b2d_set_stream(void *s) { g_stream = (cudaStream_t)s; }
+void *b2d_get_stream(void) { return (void *)g_stream; }
+
+int b2d_timer_start(void)
+{
+    if (ensure_init()) return -1;
+    if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+    cudaError_t e = cudaEventRecord(g_ev0, g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "event record");
+}
+int b2d_timer_stop(float *ms)
+{
+    cudaError_t e = cudaEventRecord(g_ev1, g_stream);
+    if (e != cudaSuccess) return fail(e, "event record");
+    e = cudaEventSynchronize(g_ev1);
+    if (e != cudaSuccess) return fail(e, "event sync");
+    cudaEventElapsedTime(ms, g_ev0, g_ev1);
+    return 0;
+}
+
+size_t b2d_fft_pass_smem(const b2d_fft_pass *p)
+{
+    size_t fast = b2fast::smem_bytes(*p);
+    if (fast) return fast;
+    return p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
+}
+
+int b2d_launch_fft_pass(const b2d_fft_pass *p)
+{
+    if (ensure_init()) return -1;
+    int64_t blocks = b2::grid_blocks(*p);
+    if (blocks <= 0) return 0;
+    if (blocks > 2147483647LL) { snprintf(g_err, sizeof g_err, "grid too large"); return -1; }
+    int rc = b2fast::try_launch(*p, g_stream);
+    if (rc == 0) { g_launches++; return 0; }
+    if (rc < 0) { snprintf(g_err, sizeof g_err, "fast kernel launch failed"); return -1; }
+    size_t smem = b2d_fft_pass_smem(p);
+    if (smem > g_max_smem) { snprintf(g_err, sizeof g_err, "pass needs %zu B smem", smem); return -1; }
+    int threads = p->tpb * p->tpx;
+    if (threads < 32) threads = 32;
+    if (threads > 1024) threads = 1024;
+    if (p->prec == B2D_F32)
+        b2::fft_generic_kernel<float><<<(unsigned)blocks, threads, smem, g_stream>>>(*p);
+    else
+        b2::fft_generic_kernel<double><<<(unsigned)blocks, threads, smem, g_stream>>>(*p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "fft_generic_kernel launch");
+    g_launches++;
+    return 0;
+}
+
+int b2d_launch_copy(const b2d_copy *c)
+{
+    if (ensure_init()) return -1;
+    int64_t total = c->n[0] * c->n[1] * c->n[2] * c->n[3];
+    if (total <= 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 2147483647LL) { snprintf(g_err, sizeof g_err, "copy grid too large"); return -1; }
+    if (c->prec == B2D_F32) b2::copy_kernel<float><<<(unsigned)blocks, 256, 0, g_stream>>>(*c, total);
+    else b2::copy_kernel<double><<<(unsigned)blocks, 256, 0, g_stream>>>(*c, total);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "copy_kernel launch");
+    g_launches++;
+    return 0;
+}
+
+int b2d_launch_realop(const b2d_realop *r)
+{
+    if (ensure_init()) return -1;
+    int len;
+    int kind = r->op & 15;
+    if (r->op == B2D_ROP_R2C_POST) len = r->m / 2 + 1;
+    else if (r->op == B2D_ROP_C2R_PRE) len = r->m;
+    else if (r->op & B2D_ROP_R2R_POST) len = r->n;
+    else len = b2::r2r_work_len(kind, r->n);
+    int64_t nb = r->bn[0] * r->bn[1] * r->bn[2];
+    if (nb <= 0 || len <= 0) return 0;
+    int chunks = (len + 127) / 128;
+    int64_t blocks = (int64_t)chunks * nb;
+    if (blocks > 2147483647LL) { snprintf(g_err, sizeof g_err, "realop grid too large"); return -1; }
+    if (r->prec == B2D_F32) b2::realop_kernel<float><<<(unsigned)blocks, 128, 0, g_stream>>>(*r, len, chunks);
+    else b2::realop_kernel<double><<<(unsigned)blocks, 128, 0, g_stream>>>(*r, len, chunks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "realop_kernel launch");
+    g_launches++;
+    return 0;
+}
+
+}  // extern "C"

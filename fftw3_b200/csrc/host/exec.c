@@ -1,0 +1,192 @@
+/* exec.c -- run a plan: bind buffers, launch the recorded passes.
+ *
+ * Reference counterpart: api/execute.c:23-27 and the new-array variants
+ * api/execute-dft.c:25-32, execute-dft-r2c.c, execute-dft-c2r.c, execute-r2r.c,
+ * which call the root plan's apply() with (possibly new) pointers.
+ *
+ * Pointers may be device pointers (zero-copy: the passes run directly on them)
+ * or host pointers (FFTW's classic contract): then the touched byte ranges are
+ * staged to the GPU, transformed there and copied back, synchronously.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b2_internal.h"
+
+int b2_async_mode = 0;
+
+static size_t real_size(int prec) { return prec == B2D_F32 ? 4 : 8; }
+
+static void *resolve(const b2_plan *p, b2_ref r, void *const user[4], size_t rs)
+{
+    switch (r.buf) {
+    case BUF_IN0: case BUF_IN1: case BUF_OUT0: case BUF_OUT1:
+        return user[r.buf - BUF_IN0] ? (char *)user[r.buf - BUF_IN0] + r.off * (int64_t)rs : NULL;
+    case BUF_SCRATCH0: case BUF_SCRATCH1: case BUF_SCRATCH2:
+        return (char *)p->scratch[r.buf - BUF_SCRATCH0] + r.off * (int64_t)rs;
+    default:
+        return NULL;
+    }
+}
+
+static int run_steps(const b2_plan *p, void *const user[4])
+{
+    int i;
+    size_t rs = real_size(p->prob.prec);
+    for (i = 0; i < p->nsteps; ++i) {
+        const b2_step *s = &p->steps[i];
+        int rc = 0;
+        if (s->kind == STEP_FFT) {
+            b2d_fft_pass f = s->u.fft;
+            f.in_re = resolve(p, s->r[0], user, rs);
+            f.in_im = resolve(p, s->r[1], user, rs);
+            f.out_re = resolve(p, s->r[2], user, rs);
+            f.out_im = resolve(p, s->r[3], user, rs);
+            rc = b2d_launch_fft_pass(&f);
+        } else if (s->kind == STEP_COPY) {
+            b2d_copy c = s->u.copy;
+            c.in = resolve(p, s->r[0], user, rs);
+            c.out = resolve(p, s->r[1], user, rs);
+            rc = b2d_launch_copy(&c);
+        } else {
+            b2d_realop r = s->u.rop;
+            r.x_re = resolve(p, s->r[0], user, rs);
+            r.x_im = resolve(p, s->r[1], user, rs);
+            r.y_re = resolve(p, s->r[2], user, rs);
+            r.y_im = resolve(p, s->r[3], user, rs);
+            r.work = resolve(p, s->r[4], user, rs);
+            rc = b2d_launch_realop(&r);
+        }
+        if (rc) {
+            fprintf(stderr, "fftw3_b200: pass %d failed: %s\n", i, b2d_last_error());
+            return rc;
+        }
+    }
+    return 0;
+}
+
+/* ---- host staging ---- */
+typedef struct { char *lo, *hi; int has_in, has_out; } region;
+
+/* tensor of everything one user pointer touches */
+static void touched_span(const b2_problem *q, int which /*0..3*/, int64_t *lo, int64_t *hi)
+{
+    int is_out = which >= 2;
+    b2_tensor t = q->sz;
+    int i;
+    /* half-complex side of r2c / c2r: last dim has n/2+1 entries */
+    if (t.rnk > 0 && ((q->kind == B2_R2C && is_out) || (q->kind == B2_C2R && !is_out)))
+        t.d[t.rnk - 1].n = t.d[t.rnk - 1].n / 2 + 1;
+    for (i = 0; i < q->vecsz.rnk && t.rnk < B2_MAXRANK; ++i) t.d[t.rnk++] = q->vecsz.d[i];
+    b2_tensor_span(&t, is_out, lo, hi);
+}
+
+static int64_t touched_count(const b2_problem *q, int which)
+{
+    int is_out = which >= 2;
+    b2_tensor t = q->sz;
+    if (t.rnk > 0 && ((q->kind == B2_R2C && is_out) || (q->kind == B2_C2R && !is_out)))
+        t.d[t.rnk - 1].n = t.d[t.rnk - 1].n / 2 + 1;
+    return b2_tensor_count(&t) * b2_tensor_count(&q->vecsz);
+}
+
+static int execute_host(b2_plan *p, void *const user[4])
+{
+    const b2_problem *q = &p->prob;
+    size_t rs = real_size(q->prec);
+    region reg[4];
+    int nreg = 0, map[4], i, j, rc = 0;
+    void *dev_user[4];
+    int64_t written_reals = 0;
+
+    for (i = 0; i < 4; ++i) {
+        int64_t lo, hi;
+        char *a, *b;
+        map[i] = -1;
+        if (!user[i]) continue;
+        touched_span(q, i, &lo, &hi);
+        a = (char *)user[i] + lo * (int64_t)rs;
+        b = (char *)user[i] + (hi + 1) * (int64_t)rs;
+        if (i >= 2) written_reals += touched_count(q, i);
+        /* merge with an existing region if overlapping / adjacent */
+        for (j = 0; j < nreg; ++j) {
+            if (a <= reg[j].hi + 64 && b + 64 >= reg[j].lo) {
+                if (a < reg[j].lo) reg[j].lo = a;
+                if (b > reg[j].hi) reg[j].hi = b;
+                break;
+            }
+        }
+        if (j == nreg) { reg[nreg].lo = a; reg[nreg].hi = b; reg[nreg].has_in = reg[nreg].has_out = 0; ++nreg; }
+        map[i] = j;
+        if (i < 2) reg[j].has_in = 1; else reg[j].has_out = 1;
+    }
+    /* regions may have become overlapping after growth: merge again */
+    for (i = 0; i < nreg; ++i)
+        for (j = i + 1; j < nreg; ++j)
+            if (reg[j].lo <= reg[i].hi + 64 && reg[j].hi + 64 >= reg[i].lo) {
+                int k;
+                if (reg[j].lo < reg[i].lo) reg[i].lo = reg[j].lo;
+                if (reg[j].hi > reg[i].hi) reg[i].hi = reg[j].hi;
+                reg[i].has_in |= reg[j].has_in; reg[i].has_out |= reg[j].has_out;
+                for (k = 0; k < 4; ++k) { if (map[k] == j) map[k] = i; else if (map[k] > j) map[k]--; }
+                for (k = j; k + 1 < nreg; ++k) reg[k] = reg[k + 1];
+                --nreg; j = i;
+            }
+    {
+        /* is the output dense?  then output-only regions need no upload */
+        size_t out_bytes = 0;
+        int dense;
+        for (i = 0; i < nreg; ++i) if (reg[i].has_out && !reg[i].has_in) out_bytes += (size_t)(reg[i].hi - reg[i].lo);
+        dense = (out_bytes == (size_t)written_reals * rs);
+        for (i = 0; i < nreg; ++i) {
+            size_t bytes = (size_t)(reg[i].hi - reg[i].lo);
+            if (p->stage_cap[i] < bytes) {
+                b2d_free(p->stage_dev[i]);
+                p->stage_dev[i] = b2d_malloc(bytes);
+                p->stage_cap[i] = p->stage_dev[i] ? bytes : 0;
+                if (!p->stage_dev[i]) { fprintf(stderr, "fftw3_b200: staging alloc failed: %s\n", b2d_last_error()); return -1; }
+            }
+            if (reg[i].has_in || !dense)
+                rc |= b2d_memcpy_h2d(p->stage_dev[i], reg[i].lo, bytes);
+        }
+    }
+    for (i = 0; i < 4; ++i)
+        dev_user[i] = (map[i] >= 0) ? (char *)p->stage_dev[map[i]] + ((char *)user[i] - reg[map[i]].lo) : NULL;
+    if (!rc) rc = run_steps(p, dev_user);
+    for (i = 0; i < nreg && !rc; ++i)
+        if (reg[i].has_out) rc |= b2d_memcpy_d2h(reg[i].lo, p->stage_dev[i], (size_t)(reg[i].hi - reg[i].lo));
+    if (!rc) rc = b2d_sync();
+    if (rc) fprintf(stderr, "fftw3_b200: execute failed: %s\n", b2d_last_error());
+    return rc;
+}
+
+void b2_execute(b2_plan *p, void *in0, void *in1, void *out0, void *out1)
+{
+    void *user[4];
+    int dev;
+    if (!p || p->is_nop) return;
+    user[0] = in0; user[1] = in1; user[2] = out0; user[3] = out1;
+    dev = b2d_pointer_is_device(in0 ? in0 : out0);
+    if (dev < 0) { fprintf(stderr, "fftw3_b200: no CUDA device: %s\n", b2d_last_error()); abort(); }
+    if (dev == 1) {
+        if (run_steps(p, user)) abort();
+        if (!b2_async_mode && b2d_sync()) { fprintf(stderr, "fftw3_b200: %s\n", b2d_last_error()); abort(); }
+    } else {
+        pthread_mutex_t *m = (pthread_mutex_t *)p->lock;
+        if (m) pthread_mutex_lock(m);
+        if (execute_host(p, user)) { if (m) pthread_mutex_unlock(m); abort(); }
+        if (m) pthread_mutex_unlock(m);
+    }
+}
+
+void b2_plan_lock_init(b2_plan *p)
+{
+    pthread_mutex_t *m = (pthread_mutex_t *)malloc(sizeof *m);
+    if (m) pthread_mutex_init(m, NULL);
+    p->lock = m;
+}
+
+void b2_plan_lock_destroy(b2_plan *p)
+{
+    if (p->lock) { pthread_mutex_destroy((pthread_mutex_t *)p->lock); free(p->lock); p->lock = NULL; }
+}

@@ -1,0 +1,989 @@
+/* planner.c -- the GPU plan builder.
+ *
+ * Turns a canonical problem into a flat list of device passes.  It plays the
+ * role of the reference's planner + solvers (kernel/planner.c:518-747,
+ * dft/ct.c, dft/rank-geq2.c:42-52, dft/vrank-geq1.c:54-65, dft/bluestein.c,
+ * rdft/rank-geq2-rdft2.c:40-66, rdft/ct-hc2c.c:59-82, reodft/*.c) but the
+ * search space is the GPU one: per pass, the radix factorisation, how many
+ * transforms a CTA stages, threads per transform and the specialised-vs-generic
+ * kernel; candidates are timed with CUDA events (FFTW_MEASURE and above) or
+ * chosen by a closed-form heuristic (FFTW_ESTIMATE), and the winner is
+ * remembered as wisdom keyed on the pass signature.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b2_internal.h"
+
+double b2_timelimit = -1.0;
+
+/* ------------------------------------------------------------------ helpers */
+typedef struct {           /* where a complex (or real) line lives */
+    b2_ref re, im;
+    int64_t stride;        /* element stride, reals */
+} b2_view;
+
+static size_t real_size(int prec) { return prec == B2D_F32 ? 4 : 8; }
+
+static b2_step *new_step(b2_plan *p, b2_step_kind kind)
+{
+    b2_step *s;
+    if (p->nsteps == p->cap) {
+        int ncap = p->cap ? 2 * p->cap : 8;
+        b2_step *ns = (b2_step *)realloc(p->steps, (size_t)ncap * sizeof(b2_step));
+        if (!ns) return NULL;
+        p->steps = ns; p->cap = ncap;
+    }
+    s = &p->steps[p->nsteps++];
+    memset(s, 0, sizeof *s);
+    s->kind = kind;
+    return s;
+}
+
+static const void *plan_table(b2_plan *p, int prec, int kind, int64_t n, int64_t aux)
+{
+    b2_table *t = b2_table_get(prec, kind, n, aux);
+    if (!t) return NULL;
+    if (p->ntables == p->tcap) {
+        int ncap = p->tcap ? 2 * p->tcap : 8;
+        b2_table **nt = (b2_table **)realloc(p->tables, (size_t)ncap * sizeof(b2_table *));
+        if (!nt) { b2_table_release(t); return NULL; }
+        p->tables = nt; p->tcap = ncap;
+    }
+    p->tables[p->ntables++] = t;
+    return t->dev;
+}
+
+static void need_scratch(b2_plan *p, int slot, size_t bytes)
+{
+    if (bytes > p->scratch_bytes[slot]) p->scratch_bytes[slot] = bytes;
+}
+
+static b2_ref mkref(int buf, int64_t off) { b2_ref r; r.buf = buf; r.off = off; return r; }
+
+/* --------------------------------------------------------- radix selection */
+int64_t b2_max_single_pass(int prec)
+{
+    return prec == B2D_F32 ? 8192 : 4096;
+}
+
+static int single_pass_fits(int64_t n, int prec)
+{
+    /* generic kernel: two padded rows of n complex + offsets must fit 227 KB */
+    int64_t pitch = n + (n >> 4) + 9;
+    size_t esz = 2 * real_size(prec);
+    return (size_t)(2 * pitch) * esz + 256 <= (size_t)232448;
+}
+
+/* Factor n into supported radices.  variant selects among orderings/groupings;
+   returns the number of stages, 0 if n has a prime factor > 13 or variant is
+   out of range. */
+int b2_factorize(int64_t n, int prec, int variant, int *radix)
+{
+    static const int odd[] = { 13, 11, 7, 5, 3 };
+    int cnt = 0, i, a = 0, n3 = 0;
+    int tmp[64];
+    int64_t m = n;
+    (void)prec;
+    if (n < 1) return 0;
+    if (n == 1) return (variant == 0) ? -1 : 0;   /* -1: zero stages, valid */
+    while (m % 2 == 0) { m /= 2; ++a; }
+    for (i = 0; i < 5; ++i)
+        while (m % odd[i] == 0) {
+            m /= odd[i];
+            if (odd[i] == 3) ++n3; else tmp[cnt++] = odd[i];
+            if (cnt > 40) return 0;
+        }
+    if (m != 1) return 0;
+    while (n3 >= 2) { tmp[cnt++] = 9; n3 -= 2; }
+    if (n3) tmp[cnt++] = 3;
+    /* power-of-two part 2^a */
+    {
+        int q = a / 4, r = a % 4;
+        switch (variant) {
+        case 0:    /* as many radix-16 as possible, remainder as one stage */
+            for (i = 0; i < q; ++i) tmp[cnt++] = 16;
+            if (r == 1) {
+                if (q > 0) { tmp[cnt - 1] = 8; tmp[cnt++] = 4; } else tmp[cnt++] = 2;
+            } else if (r == 2) tmp[cnt++] = 4;
+            else if (r == 3) tmp[cnt++] = 8;
+            break;
+        case 1:    /* radix-8 flavoured */
+            q = a / 3; r = a % 3;
+            for (i = 0; i < q; ++i) tmp[cnt++] = 8;
+            if (r == 1) { if (q > 0) tmp[cnt - 1] = 16; else tmp[cnt++] = 2; }
+            else if (r == 2) tmp[cnt++] = 4;
+            break;
+        case 2:    /* radix-4 flavoured */
+            for (i = 0; i < a / 2; ++i) tmp[cnt++] = 4;
+            if (a % 2) tmp[cnt++] = 2;
+            break;
+        default:
+            return 0;
+        }
+    }
+    if (cnt > B2D_MAX_STAGES) return 0;
+    /* descending: the first (twiddle-free) stage gets the largest radix */
+    {
+        int j;
+        for (i = 0; i < cnt; ++i)
+            for (j = i + 1; j < cnt; ++j)
+                if (tmp[j] > tmp[i]) { int t = tmp[i]; tmp[i] = tmp[j]; tmp[j] = t; }
+    }
+    for (i = 0; i < cnt; ++i) radix[i] = tmp[i];
+    return cnt;
+}
+
+static int64_t next_pow2(int64_t n) { int64_t m = 1; while (m < n) m <<= 1; return m; }
+
+/* ------------------------------------------------ single shared-memory pass */
+typedef struct {
+    int pre_op, post_op;
+    int n_in, n_out;          /* 0 = n */
+    int64_t big_n, tw4_split; /* STORE_TWIDDLE4: enclosing size and lo-table length */
+} b2_ops;
+
+static void fill_geometry(b2d_fft_pass *f, int variant)
+{
+    /* heuristic CTA shape; `variant` perturbs it for the measuring planner:
+       variant = fvar + 3 * tvar  (fvar: factorisation, tvar: tile size class) */
+    int tvar = variant / 3;
+    int rmax = 1, i, tpx, tpb;
+    int col = f->load_col || f->store_col;
+    size_t esz = 2 * real_size(f->prec);
+    int64_t pitch = f->n + (f->n >> 4) + 9;
+    size_t per_xform = (size_t)(2 * pitch) * esz + 24;
+    size_t budget = 110 * 1024;            /* aim for two CTAs per SM */
+    for (i = 0; i < f->nstages; ++i) if (f->radix[i] > rmax) rmax = f->radix[i];
+    tpx = f->n / rmax;
+    if (tpx < 1) tpx = 1;
+    if (tpx > 256) tpx = 256;
+    if (col) tpb = (f->prec == B2D_F32) ? 16 : 8;
+    else { tpb = 128 / tpx; if (tpb < 1) tpb = 1; }
+    if (tvar == 1) tpb *= 2;
+    else if (tvar == 2) { tpb /= 2; if (tpb < 1) tpb = 1; }
+    else if (tvar == 3) { tpb *= 4; budget = 220 * 1024; }
+    while (tpb > 1 && (size_t)tpb * per_xform > budget) tpb /= 2;
+    if ((size_t)tpb * per_xform > (size_t)232448 - 64) tpb = 1;
+    if (f->bn[0] < tpb) tpb = (int)(f->bn[0] > 0 ? f->bn[0] : 1);
+    while (tpb * tpx > 1024 && tpx > 1) tpx /= 2;
+    while (tpb * tpx > 1024 && tpb > 1) tpb /= 2;
+    while (tpb * tpx < 64 && tpx < f->n && tpx < 256) tpx *= 2;
+    f->tpb = tpb;
+    f->tpx = tpx;
+}
+
+#define NVARIANTS 12
+
+static int configure_variant(b2d_fft_pass *f, int variant)
+{
+    int ns = b2_factorize(f->n, f->prec, variant % 3, f->radix);
+    if (ns == 0) return -1;
+    f->nstages = ns < 0 ? 0 : ns;
+    fill_geometry(f, variant);
+    if (b2d_fft_pass_smem(f) > b2d_max_smem_per_block()) return -1;
+    return 0;
+}
+
+/* offsets reached by a pass on its input / output side (reals) */
+static void pass_span(const b2d_fft_pass *f, int out, int64_t *lo, int64_t *hi)
+{
+    int i;
+    int64_t mn = 0, mx = 0, s = out ? f->os : f->is;
+    int64_t len = out ? (f->n_out ? f->n_out : f->n) : (f->n_in ? f->n_in : f->n);
+    int64_t e = (len - 1) * s;
+    if (e < 0) mn += e; else mx += e;
+    for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) {
+        int64_t bs = out ? f->bos[i] : f->bis[i];
+        e = (f->bn[i] - 1) * bs;
+        if (e < 0) mn += e; else mx += e;
+    }
+    *lo = mn; *hi = mx;
+}
+
+/* time one configured pass on scratch buffers; returns ms or <0 */
+static double time_pass(b2d_fft_pass *f, int inplace, int64_t im_minus_re_in, int64_t im_minus_re_out)
+{
+    int64_t ilo, ihi, olo, ohi;
+    size_t rs = real_size(f->prec);
+    size_t ibytes, obytes;
+    void *ibuf, *obuf;
+    float ms = 0, best = 1e30f;
+    int rep, reps;
+    b2d_fft_pass g = *f;
+    pass_span(f, 0, &ilo, &ihi);
+    pass_span(f, 1, &olo, &ohi);
+    ibytes = (size_t)(ihi - ilo + 4 + llabs(im_minus_re_in)) * rs;
+    obytes = (size_t)(ohi - olo + 4 + llabs(im_minus_re_out)) * rs;
+    ibuf = b2d_malloc(ibytes);
+    if (!ibuf) return -1;
+    if (inplace) { obuf = ibuf; if (obytes > ibytes) { b2d_free(ibuf); return -1; } }
+    else { obuf = b2d_malloc(obytes); if (!obuf) { b2d_free(ibuf); return -1; } }
+    b2d_memset(ibuf, 0, ibytes);
+    if (!inplace) b2d_memset(obuf, 0, obytes);
+    {
+        char *ib = (char *)ibuf + (size_t)(-ilo + (im_minus_re_in < 0 ? -im_minus_re_in : 0)) * rs;
+        char *ob = (char *)obuf + (size_t)(-olo + (im_minus_re_out < 0 ? -im_minus_re_out : 0)) * rs;
+        g.in_re = ib; g.in_im = ib + im_minus_re_in * (int64_t)rs;
+        g.out_re = ob; g.out_im = ob + im_minus_re_out * (int64_t)rs;
+    }
+    if (b2d_launch_fft_pass(&g) || b2d_sync()) { best = -1; goto done; }
+    reps = 3;
+    for (rep = 0; rep < reps; ++rep) {
+        b2d_timer_start();
+        if (b2d_launch_fft_pass(&g)) { best = -1; goto done; }
+        if (b2d_timer_stop(&ms)) { best = -1; goto done; }
+        if (ms < best) best = ms;
+    }
+done:
+    if (!inplace) b2d_free(obuf);
+    b2d_free(ibuf);
+    return best;
+}
+
+static unsigned patience_of(unsigned flags)
+{
+    if (flags & B2F_ESTIMATE) return 0;
+    if (flags & B2F_EXHAUSTIVE) return 3;
+    if (flags & B2F_PATIENT) return 2;
+    return 1;
+}
+
+/* Emit one single-pass FFT step (n fits shared memory, smooth).  Batch dims
+   already canonical (<= 3). */
+static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
+                       const b2_dim *bd, int brank, b2_ops ops, int bluestein_m, const char *note)
+{
+    b2_step *s = new_step(p, STEP_FFT);
+    b2d_fft_pass *f;
+    int i, variant = 0, have = 0;
+    unsigned pat = patience_of(p->prob.flags);
+    int inplace;
+    if (!s) return -1;
+    f = &s->u.fft;
+    f->prec = prec;
+    f->n = (int)(bluestein_m ? bluestein_m : n);
+    f->pre_op = ops.pre_op; f->post_op = ops.post_op;
+    f->n_in = ops.n_in ? ops.n_in : (int)n;
+    f->n_out = ops.n_out ? ops.n_out : (int)n;
+    f->is = in.stride; f->os = out.stride;
+    for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) { f->bn[i] = 1; f->bis[i] = 0; f->bos[i] = 0; }
+    for (i = 0; i < brank; ++i) { f->bn[i] = bd[i].n; f->bis[i] = bd[i].is; f->bos[i] = bd[i].os; }
+    f->load_col = (brank > 0 && llabs(bd[0].is) < llabs(in.stride)) ? 1 : 0;
+    f->store_col = (brank > 0 && llabs(bd[0].os) < llabs(out.stride)) ? 1 : 0;
+    f->scale = 1.0;
+    f->tw = plan_table(p, prec, TAB_TWIDDLE, f->n, 0);
+    if (!f->tw) return -1;
+    if (bluestein_m) {
+        f->bluestein = 1;
+        f->pre_op |= B2D_LOAD_PAD | B2D_LOAD_CHIRP;
+        f->post_op |= B2D_STORE_TRUNC | B2D_STORE_CHIRP_SCALE;
+        f->scale = 1.0 / (double)bluestein_m;
+        f->aux0 = plan_table(p, prec, TAB_CHIRP, n, 0);
+        f->aux1 = plan_table(p, prec, TAB_BLUE_B, n, bluestein_m);
+        if (!f->aux0 || !f->aux1) return -1;
+    }
+    if (f->post_op & B2D_STORE_TWIDDLE4) {
+        f->big_n = ops.big_n; f->aux_split = ops.tw4_split;
+        f->aux0 = plan_table(p, prec, TAB_TW4_LO, ops.big_n, ops.tw4_split);
+        f->aux1 = plan_table(p, prec, TAB_TW4_HI, ops.big_n, ops.tw4_split);
+        if (!f->aux0 || !f->aux1) return -1;
+    }
+    s->r[0] = in.re; s->r[1] = in.im; s->r[2] = out.re; s->r[3] = out.im;
+    snprintf(s->note, sizeof s->note, "%s", note);
+    inplace = (in.re.buf == out.re.buf && in.re.off == out.re.off) ||
+              (in.re.buf == BUF_IN0 && out.re.buf == BUF_OUT0 && p->inplace);
+
+    /* choose the variant: wisdom -> measure -> heuristic */
+    {
+        b2_sig sig = b2_sig_of_pass(f, inplace);
+        if (b2_wisdom_lookup(sig, pat, &variant)) have = 1;
+        if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
+        if (!have && pat >= 1) {
+            int v, nv = (pat >= 2) ? NVARIANTS : 6, bestv = -1;
+            double bestt = 1e30;
+            int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
+            int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
+            if (f->pre_op & B2D_LOAD_REAL) dri = 0;
+            if (f->post_op & B2D_STORE_REALPART) dro = 0;
+            /* split arrays living in different buffers: time as interleaved-adjacent */
+            if (llabs(dri) > 64) dri = 1;
+            if (llabs(dro) > 64) dro = 1;
+            for (v = 0; v < nv; ++v) {
+                double t;
+                b2d_fft_pass trial = *f;
+                if (configure_variant(&trial, v)) continue;
+                /* skip duplicates of an earlier geometry */
+                t = time_pass(&trial, inplace, dri, dro);
+                if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
+            }
+            if (bestv >= 0) { variant = bestv; have = 1; p->cost += bestt; }
+        }
+        if (!have) variant = 0;
+        if (configure_variant(f, variant)) {
+            if (configure_variant(f, 0)) return -1;
+            variant = 0;
+        }
+        b2_wisdom_store(sig, pat, variant);
+    }
+    /* op count estimate (reference convention is per-plan add/mul/fma) */
+    {
+        double nb = (double)(f->bn[0] * f->bn[1] * f->bn[2]);
+        double lg = log2((double)(f->n > 1 ? f->n : 2));
+        double reps = bluestein_m ? 2.0 : 1.0;
+        p->est_flops_add += reps * nb * 3.0 * f->n * lg;
+        p->est_flops_mul += reps * nb * 0.5 * f->n * lg;
+        p->est_flops_fma += reps * nb * 1.0 * f->n * lg;
+    }
+    return 0;
+}
+
+/* iterate a canonical batch tensor of arbitrary rank: the 3 innermost dims go
+   into the kernel, outer dims are looped here (rare) */
+typedef int (*emit_fn)(b2_plan *p, void *ctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff);
+
+static int for_outer_dims(b2_plan *p, const b2_tensor *batch, emit_fn fn, void *ctx)
+{
+    int inner = batch->rnk < B2D_MAX_BATCH_DIMS ? batch->rnk : B2D_MAX_BATCH_DIMS;
+    int64_t idx[B2_MAXRANK];
+    int d, rc;
+    if (batch->rnk <= B2D_MAX_BATCH_DIMS) return fn(p, ctx, batch->d, inner, 0, 0);
+    for (d = 0; d < B2_MAXRANK; ++d) idx[d] = 0;
+    for (;;) {
+        int64_t io = 0, oo = 0;
+        for (d = inner; d < batch->rnk; ++d) { io += idx[d] * batch->d[d].is; oo += idx[d] * batch->d[d].os; }
+        rc = fn(p, ctx, batch->d, inner, io, oo);
+        if (rc) return rc;
+        for (d = inner; d < batch->rnk; ++d) {
+            if (++idx[d] < batch->d[d].n) break;
+            idx[d] = 0;
+        }
+        if (d == batch->rnk) break;
+    }
+    return 0;
+}
+
+static b2_view view_shift(b2_view v, int64_t off)
+{
+    v.re.off += off; v.im.off += off;
+    return v;
+}
+
+/* ----------------------------------------------------- batched 1-D complex FFT */
+typedef struct {
+    int prec; int64_t n; b2_view in, out; b2_ops ops; int scratch_slot; const char *note;
+} fft1d_ctx;
+
+static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
+                      const b2_tensor *batch_in, b2_ops ops, int scratch_slot, const char *note);
+
+static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff)
+{
+    fft1d_ctx *c = (fft1d_ctx *)vctx;
+    b2_view in = view_shift(c->in, ioff), out = view_shift(c->out, ooff);
+    int64_t n = c->n;
+    int radix[64];
+    int smooth = b2_factorize(n, c->prec, 0, radix) != 0;
+
+    if (smooth && single_pass_fits(n, c->prec))
+        return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, 0, c->note);
+
+    if (!smooth) {
+        /* Bluestein (dft/bluestein.c:82-128): one CTA does chirp, FFT_M, x B, IFFT_M, chirp */
+        int64_t m = next_pow2(2 * n - 1);
+        if (single_pass_fits(m, c->prec))
+            return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, (int)m, "bluestein");
+        return -1;   /* large non-smooth sizes: not yet supported */
+    }
+
+    /* four-step: n = n1 * n2, pass A strided length-n1 FFTs + twiddle into
+       scratch, pass B contiguous length-n2 FFTs with transposed store */
+    if (c->ops.pre_op & (B2D_LOAD_HERMCONJ | B2D_LOAD_PAD | B2D_LOAD_CHIRP)) return -1;
+    if (c->ops.post_op) return -1;
+    if (brank > 2) {
+        int64_t k;
+        for (k = 0; k < bd[brank - 1].n; ++k) {
+            int rc2 = fft1d_inner(p, vctx, bd, brank - 1, ioff + k * bd[brank - 1].is, ooff + k * bd[brank - 1].os);
+            if (rc2) return rc2;
+        }
+        return 0;
+    }
+    {
+        int64_t n1 = 0, n2 = 0, d, best = -1;
+        int64_t lines = 1, L;
+        b2_dim ba[3], bb[3];
+        b2_view sv;
+        b2_ops oa, ob;
+        int i, rc, tmp[64];
+        size_t rs = real_size(c->prec);
+        for (d = 2; d * d <= n; ++d) {
+            if (n % d) continue;
+            if (!single_pass_fits(n / d, c->prec) || !single_pass_fits(d, c->prec)) continue;
+            if (!b2_factorize(d, c->prec, 0, tmp) || !b2_factorize(n / d, c->prec, 0, tmp)) continue;
+            if (d > best) best = d;      /* closest to sqrt(n) from below */
+        }
+        if (best < 0) return -1;
+        n1 = best; n2 = n / best;        /* n1 <= n2: rows of pass B are the long contiguous ones */
+        for (i = 0; i < brank; ++i) lines *= bd[i].n;
+        need_scratch(p, c->scratch_slot, (size_t)lines * (size_t)n * 2 * rs);
+        /* scratch layout [line][k1][j2], interleaved complex */
+        sv.re = mkref(BUF_SCRATCH0 + c->scratch_slot, 0);
+        sv.im = mkref(BUF_SCRATCH0 + c->scratch_slot, 1);
+        /* pass A */
+        ba[0].n = n2; ba[0].is = in.stride; ba[0].os = 2;
+        {
+            int64_t ld = 2 * n;
+            for (i = 0; i < brank; ++i) { ba[i + 1].n = bd[i].n; ba[i + 1].is = bd[i].is; ba[i + 1].os = ld; ld *= bd[i].n; }
+        }
+        {
+            b2_view ia = in, oa_v = sv;
+            ia.stride = n2 * in.stride;
+            oa_v.stride = 2 * n2;
+            L = 1; while (L * L < n) L <<= 1;
+            oa = c->ops; oa.post_op = B2D_STORE_TWIDDLE4; oa.n_in = 0; oa.n_out = 0;
+            oa.big_n = n; oa.tw4_split = L;
+            rc = emit_single(p, c->prec, n1, ia, oa_v, ba, brank + 1, oa, 0, "four-step A");
+            if (rc) return rc;
+        }
+        /* pass B */
+        bb[0].n = n1; bb[0].is = 2 * n2; bb[0].os = out.stride;
+        {
+            int64_t ld = 2 * n;
+            for (i = 0; i < brank; ++i) { bb[i + 1].n = bd[i].n; bb[i + 1].is = ld; bb[i + 1].os = bd[i].os; ld *= bd[i].n; }
+        }
+        {
+            b2_view ib = sv, ob_v = out;
+            ib.stride = 2;
+            ob_v.stride = n1 * out.stride;
+            memset(&ob, 0, sizeof ob);
+            rc = emit_single(p, c->prec, n2, ib, ob_v, bb, brank + 1, ob, 0, "four-step B");
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
+                      const b2_tensor *batch_in, b2_ops ops, int scratch_slot, const char *note)
+{
+    b2_tensor batch = *batch_in;
+    fft1d_ctx c;
+    if (batch.rnk == B2_RNK_MINFTY) return 0;
+    b2_tensor_drop_unit(&batch);
+    b2_tensor_sort_merge(&batch);
+    if (b2_tensor_count(&batch) == 0) return 0;
+    c.prec = prec; c.n = n; c.in = in; c.out = out; c.ops = ops; c.scratch_slot = scratch_slot; c.note = note;
+    return for_outer_dims(p, &batch, fft1d_inner, &c);
+}
+
+/* every b2_ref offset, user buffer or scratch, is in units of the real scalar type */
+
+/* plain contiguous in-place FFT on a device buffer (used to build Bluestein's B table) */
+int b2_run_contig_fft(int prec, int64_t n, void *dev)
+{
+    b2d_fft_pass f;
+    b2_table *tw;
+    int rc;
+    memset(&f, 0, sizeof f);
+    f.prec = prec; f.n = (int)n;
+    f.n_in = f.n_out = (int)n;
+    f.is = f.os = 2;
+    f.bn[0] = f.bn[1] = f.bn[2] = 1;
+    f.scale = 1.0;
+    if (configure_variant(&f, 0)) return -1;
+    tw = b2_table_get(prec, TAB_TWIDDLE, n, 0);
+    if (!tw) return -1;
+    f.tw = tw->dev;
+    f.in_re = dev; f.in_im = (char *)dev + real_size(prec);
+    f.out_re = dev; f.out_im = (char *)dev + real_size(prec);
+    rc = b2d_launch_fft_pass(&f);
+    if (!rc) rc = b2d_sync();
+    b2_table_release(tw);
+    return rc;
+}
+
+/* ------------------------------------------------------------ copy (rank 0) */
+typedef struct { int prec; b2_ref in, out; int elem; } copy_ctx;
+
+static int copy_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff)
+{
+    copy_ctx *c = (copy_ctx *)vctx;
+    b2_step *s = new_step(p, STEP_COPY);
+    int i;
+    if (!s) return -1;
+    s->u.copy.prec = c->prec;
+    s->u.copy.elem_reals = c->elem;
+    s->u.copy.rank = brank;
+    for (i = 0; i < 4; ++i) { s->u.copy.n[i] = 1; s->u.copy.is[i] = 0; s->u.copy.os[i] = 0; }
+    for (i = 0; i < brank; ++i) { s->u.copy.n[i] = bd[i].n; s->u.copy.is[i] = bd[i].is; s->u.copy.os[i] = bd[i].os; }
+    s->r[0] = c->in; s->r[0].off += ioff;
+    s->r[1] = c->out; s->r[1].off += ooff;
+    snprintf(s->note, sizeof s->note, "copy");
+    return 0;
+}
+
+static int emit_copy(b2_plan *p, int prec, b2_ref in, b2_ref out, const b2_tensor *t, int elem)
+{
+    b2_tensor c = *t;
+    copy_ctx ctx;
+    if (c.rnk == B2_RNK_MINFTY) return 0;
+    b2_tensor_drop_unit(&c);
+    b2_tensor_sort_merge(&c);
+    if (b2_tensor_count(&c) == 0) return 0;
+    ctx.prec = prec; ctx.in = in; ctx.out = out; ctx.elem = elem;
+    return for_outer_dims(p, &c, copy_inner, &ctx);
+}
+
+/* --------------------------------------------------------------- real ops */
+typedef struct {
+    int prec, op, n, m; int64_t xs; b2_ref x_re, x_im, y_re, y_im; int work_slot;
+    int64_t wdist; const void *tw; int user_is_out; int64_t *line_base;
+} rop_ctx;
+
+static int rop_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff)
+{
+    rop_ctx *c = (rop_ctx *)vctx;
+    b2_step *s = new_step(p, STEP_REALOP);
+    b2d_realop *r;
+    int i;
+    int64_t lines = 1;
+    if (!s) return -1;
+    r = &s->u.rop;
+    r->prec = c->prec; r->op = c->op; r->n = c->n; r->m = c->m; r->xs = c->xs;
+    for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) { r->bn[i] = 1; r->bxs[i] = 0; }
+    /* the tensor handed to us has user strides in .is and dense work strides in .os */
+    for (i = 0; i < brank; ++i) { r->bn[i] = bd[i].n; r->bxs[i] = bd[i].is; lines *= bd[i].n; }
+    r->wdist = c->wdist;
+    r->tw = c->tw;
+    s->r[0] = c->x_re; s->r[1] = c->x_im; s->r[2] = c->y_re; s->r[3] = c->y_im;
+    if (c->user_is_out) { s->r[2].off += ioff; s->r[3].off += ioff; }
+    else { s->r[0].off += ioff; s->r[1].off += ioff; }
+    s->r[4] = mkref(BUF_SCRATCH0 + c->work_slot, ooff);   /* dense work strides are in reals */
+    snprintf(s->note, sizeof s->note, "realop %d", c->op);
+    (void)lines;
+    return 0;
+}
+
+/* user-side batch `ub` (strides in .is) gets dense work strides in .os (reals,
+   2*wdist per line) in ascending order of the sorted user strides */
+static void dense_work_strides(b2_tensor *t, int64_t wdist)
+{
+    int i;
+    int64_t ld = 2 * wdist;
+    for (i = 0; i < t->rnk; ++i) { t->d[i].os = ld; ld *= t->d[i].n; }
+}
+
+static int cmp_is(const void *a, const void *b)
+{
+    int64_t x = llabs(((const b2_dim *)a)->is), y = llabs(((const b2_dim *)b)->is);
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* Build the canonical user batch (sorted by user stride, unit dims dropped)
+   with dense work strides.  Both the FFT passes and the real ops that share a
+   work buffer use this same tensor so their line numbering agrees. */
+static void make_work_batch(b2_tensor *t, int64_t wdist)
+{
+    b2_tensor_drop_unit(t);
+    if (t->rnk > 1) qsort(t->d, (size_t)t->rnk, sizeof(b2_dim), cmp_is);
+    dense_work_strides(t, wdist);
+}
+
+static int emit_realop(b2_plan *p, rop_ctx *c, const b2_tensor *wb)
+{
+    /* no merging here: the dense strides already make merged == unmerged numbering,
+       but sort_merge orders by .os which is ascending by construction */
+    b2_tensor t = *wb;
+    if (t.rnk == B2_RNK_MINFTY || b2_tensor_count(&t) == 0) return 0;
+    b2_tensor_sort_merge(&t);
+    return for_outer_dims(p, &t, rop_inner, c);
+}
+
+/* ------------------------------------------------------------------ c2c */
+static void other_dims(const b2_problem *q, int skip, int use_out_for_in, b2_tensor *t)
+{
+    /* batch = vecsz + all sz dims except `skip`; when use_out_for_in, the pass
+       runs in place on the output so both sides use .os */
+    int i;
+    b2_tensor_init(t, 0);
+    for (i = 0; i < q->sz.rnk; ++i) {
+        if (i == skip) continue;
+        t->d[t->rnk] = q->sz.d[i];
+        if (use_out_for_in) t->d[t->rnk].is = q->sz.d[i].os;
+        t->rnk++;
+    }
+    for (i = 0; i < q->vecsz.rnk; ++i) {
+        t->d[t->rnk] = q->vecsz.d[i];
+        if (use_out_for_in) t->d[t->rnk].is = q->vecsz.d[i].os;
+        t->rnk++;
+    }
+}
+
+static int plan_c2c(b2_plan *p)
+{
+    const b2_problem *q = &p->prob;
+    b2_ops none;
+    int d, first = 1, rc;
+    memset(&none, 0, sizeof none);
+    if (q->sz.rnk == 0) {
+        /* rank-0: copy (rdft/rank0.c); re and im planes separately */
+        if (p->inplace) return 0;
+        rc = emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_OUT0, 0), &q->vecsz, 1);
+        if (rc) return rc;
+        return emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_OUT1, 0), &q->vecsz, 1);
+    }
+    for (d = q->sz.rnk - 1; d >= 0; --d) {
+        b2_tensor batch;
+        b2_view in, out;
+        other_dims(q, d, !first, &batch);
+        out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = q->sz.d[d].os;
+        if (first) { in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN1, 0); in.stride = q->sz.d[d].is; }
+        else in = out;
+        rc = emit_fft1d(p, q->prec, q->sz.d[d].n, in, out, &batch, none, 1, first ? "dft" : "dft(in place)");
+        if (rc) return rc;
+        first = 0;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ r2c */
+static int plan_r2c(b2_plan *p)
+{
+    const b2_problem *q = &p->prob;
+    int last = q->sz.rnk - 1, d, rc;
+    int64_t n, is, os;
+    b2_tensor batch;
+    b2_ops ops;
+    b2_view in, out;
+    if (q->sz.rnk < 1) {
+        /* rank 0 r2c: copy real part, zero imaginary: express as n=1 transform */
+        return -1;
+    }
+    n = q->sz.d[last].n; is = q->sz.d[last].is; os = q->sz.d[last].os;
+    other_dims(q, last, 0, &batch);
+    memset(&ops, 0, sizeof ops);
+    out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = os;
+    if (n % 2 == 0 && n >= 2) {
+        int64_t m = n / 2;
+        b2_tensor wb = batch, fb;
+        rop_ctx c;
+        b2_view wv;
+        size_t esz = 2 * real_size(q->prec);
+        int i;
+        /* FFT_m of (even, odd) samples as (re, im): user -> work */
+        make_work_batch(&wb, m);      /* .is = user real strides, .os = dense work */
+        need_scratch(p, 0, (size_t)(b2_tensor_count(&wb) > 0 ? b2_tensor_count(&wb) : 1) * (size_t)m * esz);
+        in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN0, is); in.stride = 2 * is;
+        wv.re = mkref(BUF_SCRATCH0, 0); wv.im = mkref(BUF_SCRATCH0, 1); wv.stride = 2;
+        rc = emit_fft1d(p, q->prec, m, in, wv, &wb, ops, 1, "r2c half-size dft");
+        if (rc) return rc;
+        /* split: work -> user complex; user strides are now the OUTPUT strides */
+        fb = wb;
+        {
+            /* replace .is by output strides of the same dims, keeping order */
+            b2_tensor ob;
+            other_dims(q, last, 1, &ob);   /* .is == .os == output strides */
+            b2_tensor_drop_unit(&ob);
+            /* wb was sorted by input stride; re-create in the same order: match by position
+               is fragile, so rebuild: sort a copy of (in,out) pairs by input stride */
+            {
+                b2_tensor pair;
+                other_dims(q, last, 0, &pair);
+                b2_tensor_drop_unit(&pair);
+                if (pair.rnk > 1) qsort(pair.d, (size_t)pair.rnk, sizeof(b2_dim), cmp_is);
+                for (i = 0; i < pair.rnk; ++i) { fb.d[i].n = pair.d[i].n; fb.d[i].is = pair.d[i].os; }
+                fb.rnk = pair.rnk;
+                dense_work_strides(&fb, m);
+            }
+        }
+        memset(&c, 0, sizeof c);
+        c.prec = q->prec; c.op = B2D_ROP_R2C_POST; c.n = (int)n; c.m = (int)m; c.xs = os;
+        c.y_re = mkref(BUF_OUT0, 0); c.y_im = mkref(BUF_OUT1, 0);
+        c.work_slot = 0; c.wdist = m; c.user_is_out = 1;
+        c.tw = plan_table(p, q->prec, TAB_R2C, n, 0);
+        if (!c.tw) return -1;
+        rc = emit_realop(p, &c, &fb);
+        if (rc) return rc;
+    } else {
+        in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN0, 0); in.stride = is;
+        ops.pre_op = B2D_LOAD_REAL; ops.post_op = B2D_STORE_TRUNC; ops.n_out = (int)(n / 2 + 1);
+        rc = emit_fft1d(p, q->prec, n, in, out, &batch, ops, 1, "r2c odd");
+        if (rc) return rc;
+    }
+    /* remaining dims: complex, in place on the output, last dim now n/2+1 long */
+    memset(&ops, 0, sizeof ops);
+    for (d = last - 1; d >= 0; --d) {
+        b2_tensor b2;
+        int i, k = 0;
+        other_dims(q, d, 1, &b2);
+        /* the entry that came from the last dim has n -> n/2+1 */
+        for (i = 0; i < q->sz.rnk; ++i) {
+            if (i == d) continue;
+            if (i == last) b2.d[k].n = n / 2 + 1;
+            ++k;
+        }
+        out.stride = q->sz.d[d].os;
+        rc = emit_fft1d(p, q->prec, q->sz.d[d].n, out, out, &b2, ops, 1, "r2c outer dft");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ c2r */
+static int plan_c2r(b2_plan *p)
+{
+    const b2_problem *q = &p->prob;
+    int last = q->sz.rnk - 1, d, rc;
+    int64_t n, is, os;
+    b2_tensor batch;
+    b2_ops ops;
+    b2_view in, out;
+    int src_re = BUF_IN0, src_im = BUF_IN1;
+    if (q->sz.rnk < 1) return -1;
+    n = q->sz.d[last].n; is = q->sz.d[last].is; os = q->sz.d[last].os;
+    memset(&ops, 0, sizeof ops);
+
+    if (q->sz.rnk > 1) {
+        /* leading dims: backward complex passes in place on the INPUT (this is why
+           multi-dimensional c2r destroys its input: api/plan-many-dft-c2r.c:41-42) */
+        if (!p->inplace) p->destroys_input = 1;
+        for (d = 0; d < last; ++d) {
+            b2_tensor b2;
+            int i, k = 0;
+            /* in place on input: both sides use .is */
+            b2_tensor_init(&b2, 0);
+            for (i = 0; i < q->sz.rnk; ++i) {
+                if (i == d) continue;
+                b2.d[k] = q->sz.d[i];
+                b2.d[k].os = q->sz.d[i].is;
+                if (i == last) b2.d[k].n = n / 2 + 1;
+                ++k;
+            }
+            for (i = 0; i < q->vecsz.rnk; ++i) { b2.d[k] = q->vecsz.d[i]; b2.d[k].os = q->vecsz.d[i].is; ++k; }
+            b2.rnk = k;
+            /* backward = forward with re/im swapped */
+            in.re = mkref(src_im, 0); in.im = mkref(src_re, 0); in.stride = q->sz.d[d].is;
+            rc = emit_fft1d(p, q->prec, q->sz.d[d].n, in, in, &b2, ops, 1, "c2r outer dft");
+            if (rc) return rc;
+        }
+    }
+    other_dims(q, last, 0, &batch);
+    out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT0, 0); out.stride = os;
+    if (n % 2 == 0 && n >= 2) {
+        int64_t m = n / 2;
+        b2_tensor wb = batch, fb;
+        rop_ctx c;
+        b2_view wv;
+        size_t esz = 2 * real_size(q->prec);
+        int i;
+        make_work_batch(&wb, m);       /* sorted by INPUT (complex) strides */
+        need_scratch(p, 0, (size_t)(b2_tensor_count(&wb) > 0 ? b2_tensor_count(&wb) : 1) * (size_t)m * esz);
+        memset(&c, 0, sizeof c);
+        c.prec = q->prec; c.op = B2D_ROP_C2R_PRE; c.n = (int)n; c.m = (int)m; c.xs = is;
+        c.x_re = mkref(src_re, 0); c.x_im = mkref(src_im, 0);
+        c.work_slot = 0; c.wdist = m; c.user_is_out = 0;
+        c.tw = plan_table(p, q->prec, TAB_R2C, n, 0);
+        if (!c.tw) return -1;
+        rc = emit_realop(p, &c, &wb);
+        if (rc) return rc;
+        /* forward FFT_m on the swapped work, scattered as (odd, even) reals */
+        fb = wb;
+        for (i = 0; i < fb.rnk; ++i) { int64_t t = fb.d[i].is; fb.d[i].is = fb.d[i].os; fb.d[i].os = t; }
+        /* fb: .is = dense work strides, .os = must be the user's OUTPUT strides of the same dims */
+        {
+            b2_tensor pair;
+            other_dims(q, last, 0, &pair);
+            b2_tensor_drop_unit(&pair);
+            if (pair.rnk > 1) qsort(pair.d, (size_t)pair.rnk, sizeof(b2_dim), cmp_is);
+            for (i = 0; i < pair.rnk; ++i) fb.d[i].os = pair.d[i].os;
+        }
+        wv.re = mkref(BUF_SCRATCH0, 0); wv.im = mkref(BUF_SCRATCH0, 1); wv.stride = 2;
+        out.re = mkref(BUF_OUT0, os); out.im = mkref(BUF_OUT0, 0); out.stride = 2 * os;
+        rc = emit_fft1d(p, q->prec, m, wv, out, &fb, ops, 1, "c2r half-size dft");
+        if (rc) return rc;
+    } else {
+        in.re = mkref(src_re, 0); in.im = mkref(src_im, 0); in.stride = is;
+        ops.pre_op = B2D_LOAD_HERMCONJ; ops.post_op = B2D_STORE_REALPART;
+        ops.n_in = (int)n; ops.n_out = (int)n;
+        rc = emit_fft1d(p, q->prec, n, in, out, &batch, ops, 1, "c2r odd");
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ r2r */
+static int r2r_work_len(int kind, int64_t n, int64_t *m)
+{
+    switch (kind) {
+    case 3: if (n < 2) return -1; *m = 2 * (n - 1); return 0;     /* REDFT00 */
+    case 7: *m = 2 * (n + 1); return 0;                           /* RODFT00 */
+    case 6: case 10: *m = 2 * n; return 0;                        /* REDFT11, RODFT11 */
+    default: *m = n; return 0;
+    }
+}
+
+static int plan_r2r(b2_plan *p)
+{
+    const b2_problem *q = &p->prob;
+    int d, first = 1, rc;
+    b2_ops none;
+    memset(&none, 0, sizeof none);
+    if (q->sz.rnk == 0) {
+        if (p->inplace) return 0;
+        return emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_OUT0, 0), &q->vecsz, 1);
+    }
+    for (d = q->sz.rnk - 1; d >= 0; --d) {
+        int kind = q->r2r_kind[d];
+        int64_t n = q->sz.d[d].n, m;
+        b2_tensor ub, wb_in, wb_out, fb;
+        rop_ctx c;
+        b2_view wv;
+        size_t esz = 2 * real_size(q->prec);
+        int i;
+        if (kind < 0 || kind > 10) return -1;
+        if (r2r_work_len(kind, n, &m)) return -1;
+        /* user batch for this dim: input side strides for PRE, output side for POST */
+        other_dims(q, d, !first, &ub);      /* .is = source strides, .os = out strides */
+        wb_in = ub;
+        make_work_batch(&wb_in, m);         /* sorted by source stride; .os := dense */
+        /* POST tensor: same dim order, user strides = output strides */
+        {
+            b2_tensor pair = ub;
+            b2_tensor_drop_unit(&pair);
+            if (pair.rnk > 1) qsort(pair.d, (size_t)pair.rnk, sizeof(b2_dim), cmp_is);
+            wb_out = wb_in;
+            for (i = 0; i < pair.rnk; ++i) wb_out.d[i].is = pair.d[i].os;
+        }
+        need_scratch(p, 0, (size_t)(b2_tensor_count(&wb_in) > 0 ? b2_tensor_count(&wb_in) : 1) * (size_t)m * esz);
+        memset(&c, 0, sizeof c);
+        c.prec = q->prec; c.n = (int)n; c.m = (int)m; c.work_slot = 0; c.wdist = m;
+        c.tw = NULL;
+        if (kind == 4 || kind == 5 || kind == 6 || kind == 8 || kind == 9 || kind == 10) {
+            c.tw = plan_table(p, q->prec, TAB_QUARTER, n, 0);
+            if (!c.tw) return -1;
+        }
+        /* PRE */
+        c.op = B2D_ROP_R2R_PRE | kind;
+        c.xs = first ? q->sz.d[d].is : q->sz.d[d].os;
+        c.x_re = first ? mkref(BUF_IN0, 0) : mkref(BUF_OUT0, 0);
+        c.user_is_out = 0;
+        rc = emit_realop(p, &c, &wb_in);
+        if (rc) return rc;
+        /* FFT_m in place on the work lines */
+        fb = wb_in;
+        for (i = 0; i < fb.rnk; ++i) fb.d[i].is = fb.d[i].os;
+        wv.re = mkref(BUF_SCRATCH0, 0); wv.im = mkref(BUF_SCRATCH0, 1); wv.stride = 2;
+        rc = emit_fft1d(p, q->prec, m, wv, wv, &fb, none, 1, "r2r core dft");
+        if (rc) return rc;
+        /* POST */
+        c.op = B2D_ROP_R2R_POST | kind;
+        c.xs = q->sz.d[d].os;
+        c.y_re = mkref(BUF_OUT0, 0);
+        c.user_is_out = 1;
+        rc = emit_realop(p, &c, &wb_out);
+        if (rc) return rc;
+        first = 0;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ entry */
+static int tensor_valid(const b2_tensor *t, int allow_minfty)
+{
+    int i;
+    if (t->rnk == B2_RNK_MINFTY) return allow_minfty;
+    if (t->rnk < 0 || t->rnk > B2_MAXRANK) return 0;
+    for (i = 0; i < t->rnk; ++i) if (t->d[i].n < (allow_minfty ? 0 : 1)) return 0;
+    return 1;
+}
+
+b2_plan *b2_mkplan(const b2_problem *prob)
+{
+    b2_plan *p;
+    int rc = 0, i;
+    if (!tensor_valid(&prob->sz, 0) || !tensor_valid(&prob->vecsz, 1)) return NULL;
+    if (b2d_device_count() <= 0) return NULL;      /* no GPU, no plan: there is no CPU fallback */
+    p = (b2_plan *)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->refcnt = 1;
+    p->prob = *prob;
+    b2_plan_lock_init(p);
+    b2_wisdom_set_prec(prob->prec);
+    b2_tensor_drop_unit(&p->prob.vecsz);
+    /* unit transform dims are identities; keep their r2r kinds aligned */
+    {
+        b2_tensor *t = &p->prob.sz;
+        int k = 0;
+        int keep_last = (prob->kind == B2_R2C || prob->kind == B2_C2R);
+        for (i = 0; i < t->rnk; ++i) {
+            int is_last = (i == t->rnk - 1);
+            if (t->d[i].n != 1 || (keep_last && is_last) || prob->kind == B2_R2R) {
+                p->prob.r2r_kind[k] = prob->r2r_kind[i];
+                t->d[k++] = t->d[i];
+            }
+        }
+        t->rnk = k;
+    }
+    p->inplace = (prob->in0 == prob->out0);
+    if (prob->kind == B2_C2C && prob->in0 == prob->out1 && prob->in1 == prob->out0) p->inplace = 0;
+    if (b2_tensor_count(&p->prob.vecsz) == 0) { p->is_nop = 1; return p; }
+    if (p->inplace && prob->kind != B2_R2C && prob->kind != B2_C2R) {
+        /* in-place needs identical input and output locations (dft/problem.c:95-99) */
+        if (!b2_tensor_inplace_ok(&p->prob.sz) || !b2_tensor_inplace_ok(&p->prob.vecsz)) {
+            b2_plan_destroy(p);
+            return NULL;
+        }
+    }
+    switch (prob->kind) {
+    case B2_C2C: rc = plan_c2c(p); break;
+    case B2_R2C: rc = plan_r2c(p); break;
+    case B2_C2R: rc = plan_c2r(p); break;
+    case B2_R2R: rc = plan_r2r(p); break;
+    }
+    if (rc) { b2_plan_destroy(p); return NULL; }
+    for (i = 0; i < 3; ++i) {
+        if (p->scratch_bytes[i]) {
+            p->scratch[i] = b2d_malloc(p->scratch_bytes[i]);
+            if (!p->scratch[i]) { b2_plan_destroy(p); return NULL; }
+        }
+    }
+    if (b2d_sync()) { b2_plan_destroy(p); return NULL; }
+    return p;
+}
+
+void b2_plan_destroy(b2_plan *p)
+{
+    int i;
+    if (!p) return;
+    b2_plan_lock_destroy(p);
+    for (i = 0; i < p->ntables; ++i) b2_table_release(p->tables[i]);
+    free(p->tables);
+    for (i = 0; i < 3; ++i) b2d_free(p->scratch[i]);
+    for (i = 0; i < 4; ++i) b2d_free(p->stage_dev[i]);
+    free(p->steps);
+    free(p);
+}
+
+void b2_plan_print(const b2_plan *p, FILE *f)
+{
+    int i, j;
+    if (p->is_nop) { fprintf(f, "(b200-nop)"); return; }
+    fprintf(f, "(b200-plan");
+    for (i = 0; i < p->nsteps; ++i) {
+        const b2_step *s = &p->steps[i];
+        if (s->kind == STEP_FFT) {
+            const b2d_fft_pass *q = &s->u.fft;
+            fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
+            for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
+            fprintf(f, " batch=%lldx%lldx%lld tpb=%d tpx=%d %s->%s%s)", (long long)q->bn[0], (long long)q->bn[1],
+                    (long long)q->bn[2], q->tpb, q->tpx, q->load_col ? "col" : "row",
+                    q->store_col ? "col" : "row", q->bluestein ? " bluestein" : "");
+        } else if (s->kind == STEP_COPY) {
+            fprintf(f, "\n  (copy %lldx%lldx%lldx%lld)", (long long)s->u.copy.n[0], (long long)s->u.copy.n[1],
+                    (long long)s->u.copy.n[2], (long long)s->u.copy.n[3]);
+        } else {
+            fprintf(f, "\n  (%s n=%d m=%d)", s->note, s->u.rop.n, s->u.rop.m);
+        }
+    }
+    fprintf(f, ")");
+}

@@ -1,0 +1,140 @@
+/* b200fft_device.h -- the thin C-ABI shim between the C host layer (api +
+ * plan builder, fftw3_b200/csrc/host) and the sm_100a CUDA kernels
+ * (fftw3_b200/csrc/device).  Plain pointers and sizes only; no CUDA or torch
+ * types in any signature, so the host layer is compiled by a C compiler.
+ *
+ * Reference counterpart: this seam sits where the reference's plan->apply
+ * closures call codelets (dft/direct.c:92-97, dft/dftw-direct.c:46-56,
+ * rdft/ct-hc2c-direct.c:45-60) and kernel copies (kernel/cpy2d.c, rdft/rank0.c).
+ * A "pass" below is one kernel launch that streams the array through HBM once.
+ */
+#ifndef B200FFT_DEVICE_H
+#define B200FFT_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_MAX_STAGES 12
+#define B2D_MAX_BATCH_DIMS 3
+
+enum { B2D_F64 = 0, B2D_F32 = 1 };
+
+/* element-wise operations fused into the load side of an FFT pass (bit mask) */
+enum {
+    B2D_LOAD_REAL = 1,      /* input is real (imag := 0), in_im unused               */
+    B2D_LOAD_HERMCONJ = 2,  /* loads conj(H), H = Hermitian sequence of logical length
+                               n_in given by its non-redundant half (c2r): k > n_in/2
+                               reads in[n_in-k]; imag of self-mirrored bins ignored   */
+    B2D_LOAD_PAD = 4,       /* k >= n_in reads as zero                               */
+    B2D_LOAD_CHIRP = 8      /* multiply by aux0[k] (Bluestein chirp)                 */
+};
+
+/* element-wise operations fused into the store side of an FFT pass (bit mask) */
+enum {
+    B2D_STORE_REALPART = 1,    /* store Re only (c2r)                                 */
+    B2D_STORE_TRUNC = 2,       /* store only k < n_out                                */
+    B2D_STORE_CHIRP_SCALE = 4, /* Bluestein: z * aux0[k] * scale                      */
+    B2D_STORE_TWIDDLE4 = 8     /* four-step: z *= W_big^(k * b0) (two-level tables)   */
+};
+
+/* One batched strided 1-D complex FFT pass.  All strides/offsets are in units
+ * of the REAL scalar type (like the reference's internal tensors, where a
+ * complex interleaved array has stride 2: api/plan-many-dft.c:43-46). */
+typedef struct b2d_fft_pass {
+    int prec;                 /* B2D_F64 / B2D_F32                                  */
+    int n;                    /* transform length computed in shared memory          */
+    int nstages;
+    int radix[B2D_MAX_STAGES];
+    int tpb;                  /* transforms per CTA (tile along batch dim 0)         */
+    int tpx;                  /* threads per transform                               */
+    int load_col, store_col;  /* 0: consecutive lanes walk the transform (ROW);
+                                 1: consecutive lanes walk batch dim 0 (COL)         */
+    int pre_op, post_op;
+    int bluestein;            /* 1: forward stages, x aux1[k], inverse stages        */
+    int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
+    int64_t is, os;           /* element stride along the transform                  */
+    int64_t bn[B2D_MAX_BATCH_DIMS], bis[B2D_MAX_BATCH_DIMS], bos[B2D_MAX_BATCH_DIMS];
+    /* buffers: re/im pointers (im == re +- 1 means interleaved; sign swap = -1)    */
+    const void *in_re, *in_im;
+    void *out_re, *out_im;
+    const void *tw;           /* n complex: exp(-2 pi i k / n)                       */
+    const void *aux0, *aux1;  /* op tables                                           */
+    int64_t aux_split;        /* TWIDDLE4: lo-table length L (e = hi*L + lo)          */
+    int64_t big_n;            /* TWIDDLE4: N of the enclosing transform               */
+    double scale;
+} b2d_fft_pass;
+
+/* strided N-d copy / rank-0 transform (kernel/cpy2d.c, rdft/rank0.c analogue);
+ * element = `elem_reals` consecutive reals (1: real scalar, 2: interleaved complex) */
+typedef struct b2d_copy {
+    int prec;
+    int elem_reals;
+    int rank;                       /* <= 4 */
+    int64_t n[4], is[4], os[4];     /* dim 0 fastest                                */
+    const void *in;
+    void *out;
+} b2d_copy;
+
+/* r2c / c2r even-length split (rdft/ct-hc2c-direct.c:45-60 analogue) and r2r
+ * pre/post element maps: see device/real_ops.cuh */
+typedef struct b2d_realop {
+    int prec;
+    int op;                    /* B2D_ROP_* */
+    int n;                     /* logical 1-D size                                   */
+    int m;                     /* complex work length                                */
+    int64_t xs;                /* stride of the user-side line (reals)               */
+    int64_t bn[B2D_MAX_BATCH_DIMS], bxs[B2D_MAX_BATCH_DIMS];  /* user-side batch     */
+    int64_t wdist;             /* work-buffer distance between lines (complex units) */
+    const void *x_re, *x_im;   /* user side (x_im used by split complex ops)          */
+    void *y_re, *y_im;
+    void *work;                /* interleaved complex work buffer                     */
+    const void *tw;            /* op-specific table                                   */
+} b2d_realop;
+
+enum {
+    B2D_ROP_R2C_POST = 1,   /* work[0..n/2) = FFT(z), write X[0..n/2] to user (cr,ci)  */
+    B2D_ROP_C2R_PRE = 2,    /* user X[0..n/2] -> work z-spectrum for backward FFT     */
+    B2D_ROP_R2R_PRE = 16,   /* + kind: user real line -> complex work sequence        */
+    B2D_ROP_R2R_POST = 32   /* + kind: complex work spectrum -> user real line        */
+};
+
+/* ---- runtime ---- */
+int  b2d_device_count(void);            /* 0 if no usable CUDA device                  */
+const char *b2d_device_name(void);
+int  b2d_sm_count(void);
+const char *b2d_last_error(void);
+int  b2d_pointer_is_device(const void *p);   /* 1 device/managed, 0 host, -1 error     */
+void *b2d_malloc(size_t bytes);
+void b2d_free(void *p);
+void *b2d_malloc_host(size_t bytes);     /* pinned */
+void b2d_free_host(void *p);
+int  b2d_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int  b2d_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int  b2d_memcpy_d2d(void *dst, const void *src, size_t bytes);
+int  b2d_memset(void *dst, int byte, size_t bytes);
+int  b2d_sync(void);
+void b2d_set_stream(void *cuda_stream);  /* NULL = legacy default stream              */
+void *b2d_get_stream(void);
+size_t b2d_max_smem_per_block(void);
+
+/* timing on the launch stream (planner measurements) */
+int  b2d_timer_start(void);
+int  b2d_timer_stop(float *ms);
+
+/* ---- kernels ---- */
+int  b2d_launch_fft_pass(const b2d_fft_pass *p);
+size_t b2d_fft_pass_smem(const b2d_fft_pass *p);  /* dynamic smem bytes it needs   */
+int  b2d_launch_copy(const b2d_copy *c);
+int  b2d_launch_realop(const b2d_realop *r);
+
+/* number of kernels launched since the library was loaded (bench `gpu_launches`) */
+uint64_t b2d_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_DEVICE_H */

@@ -1,0 +1,35 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """The REAL host layer linked against the unit-test double of the device shim
+    (tests/emu/emu_shim.cpp).  Test infrastructure only; never the product."""
+    from fftw3_b200 import binding
+    subprocess.run(["sh", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], check=True)
+    return binding.Lib(os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """The product library on a real GPU.  Fails loudly if the CUDA library is
+    missing or no device is usable -- there is no fallback to hide behind."""
+    from fftw3_b200 import binding
+    path = binding.default_library_path()
+    assert os.path.exists(path), "product library not built: run python -c 'import __graft_entry__ as g; g.build()'"
+    lib = binding.Lib(path)
+    name = lib.device_name()
+    assert name, "no CUDA device visible to libfftw3_b200.so"
+    return lib

@@ -1,0 +1,132 @@
+// tests/emu/emu_shim.cpp -- UNIT-TEST DOUBLE for include/b200fft_device.h.
+//
+// NOT part of the product.  It exists so that the C host layer (argument
+// checking, tensor canonicalisation, plan building, pass descriptors, wisdom)
+// and the kernels' index algebra can be unit-tested in `-m "not gpu"` runs on a
+// box without a GPU: "device memory" is malloc, and a kernel launch runs the
+// very same __host__ __device__ phase functions of fft_generic.cuh /
+// real_ops.cuh with CTAs and threads as plain loops.  It is built into
+// tests/_emu/ by tests/conftest.py and only ever loaded by tests.  The product
+// library (fftw3_b200/lib/libfftw3_b200.so) links shim.cu instead and has no
+// CPU path at all.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <chrono>
+#include <set>
+#include <vector>
+
+#include "../../fftw3_b200/csrc/device/fft_generic.cuh"
+#include "../../fftw3_b200/csrc/device/real_ops.cuh"
+
+static char g_err[256] = "";
+static uint64_t g_launches = 0;
+static std::set<void *> g_dev;
+static std::chrono::steady_clock::time_point g_t0;
+
+template <typename T>
+static void run_fft_pass(const b2d_fft_pass &p)
+{
+    using namespace b2;
+    int64_t blocks = grid_blocks(p);
+    int nthreads = p.tpb * p.tpx;
+    if (nthreads < 32) nthreads = 32;
+    if (nthreads > 1024) nthreads = 1024;
+    std::vector<unsigned char> raw(smem_bytes<T>(p) + 64);
+    unsigned char *base = raw.data();
+    base += (16 - ((uintptr_t)base & 15)) & 15;
+    for (int64_t blk = 0; blk < blocks; ++blk) {
+        Smem<T> s = carve<T>(p, base);
+        TileCtx c = decode_block(p, blk);
+        for (int t = 0; t < nthreads; ++t) phase_offsets<T>(p, s, c, t);
+        for (int t = 0; t < nthreads; ++t) phase_load<T>(p, s, t, nthreads);
+        cplx<T> *src = s.a, *dst = s.b;
+        int reps = p.bluestein ? 2 : 1;
+        for (int rep = 0; rep < reps; ++rep) {
+            int ns = 1;
+            for (int st = 0; st < p.nstages; ++st) {
+                for (int t = 0; t < nthreads; ++t) phase_stage<T>(p, st, ns, src, dst, s.pitch, t, nthreads);
+                ns *= p.radix[st];
+                cplx<T> *tmp = src; src = dst; dst = tmp;
+            }
+            if (p.bluestein && rep == 0)
+                for (int t = 0; t < nthreads; ++t) phase_pointwise<T>(p, src, s.pitch, t, nthreads);
+        }
+        for (int t = 0; t < nthreads; ++t) phase_store<T>(p, s, src, t, nthreads);
+    }
+}
+
+template <typename T>
+static void run_realop(const b2d_realop &r)
+{
+    using namespace b2;
+    int kind = r.op & 15, len;
+    if (r.op == B2D_ROP_R2C_POST) len = r.m / 2 + 1;
+    else if (r.op == B2D_ROP_C2R_PRE) len = r.m;
+    else if (r.op & B2D_ROP_R2R_POST) len = r.n;
+    else len = r2r_work_len(kind, r.n);
+    int64_t nb = r.bn[0] * r.bn[1] * r.bn[2];
+    for (int64_t b = 0; b < nb; ++b)
+        for (int i = 0; i < len; ++i) {
+            if (r.op == B2D_ROP_R2C_POST) r2c_post_pair<T>(r, b, i);
+            else if (r.op == B2D_ROP_C2R_PRE) c2r_pre_elem<T>(r, b, i);
+            else if (r.op & B2D_ROP_R2R_POST) r2r_post_elem<T>(r, kind, b, i);
+            else r2r_pre_elem<T>(r, kind, b, i);
+        }
+}
+
+extern "C" {
+int b2d_device_count(void) { return 1; }
+const char *b2d_device_name(void) { return "emulated-for-unit-tests"; }
+int b2d_sm_count(void) { return 148; }
+const char *b2d_last_error(void) { return g_err; }
+size_t b2d_max_smem_per_block(void) { return 232448; }
+uint64_t b2d_launch_count(void) { return g_launches; }
+int b2d_pointer_is_device(const void *p) { return g_dev.count((void *)p) ? 1 : 0; }
+void *b2d_malloc(size_t n) { void *p = malloc(n ? n : 1); g_dev.insert(p); return p; }
+void b2d_free(void *p) { if (p) { g_dev.erase(p); free(p); } }
+void *b2d_malloc_host(size_t n) { void *p = NULL; if (posix_memalign(&p, 64, n ? n : 1)) return NULL; return p; }
+void b2d_free_host(void *p) { free(p); }
+int b2d_memcpy_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int b2d_memcpy_d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int b2d_memcpy_d2d(void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }
+int b2d_memset(void *d, int b, size_t n) { memset(d, b, n); return 0; }
+int b2d_sync(void) { return 0; }
+void b2d_set_stream(void *) {}
+void *b2d_get_stream(void) { return NULL; }
+int b2d_timer_start(void) { g_t0 = std::chrono::steady_clock::now(); return 0; }
+int b2d_timer_stop(float *ms)
+{
+    *ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - g_t0).count();
+    return 0;
+}
+size_t b2d_fft_pass_smem(const b2d_fft_pass *p)
+{
+    return p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
+}
+int b2d_launch_fft_pass(const b2d_fft_pass *p)
+{
+    if (b2d_fft_pass_smem(p) > b2d_max_smem_per_block()) {
+        snprintf(g_err, sizeof g_err, "pass needs too much smem");
+        return -1;
+    }
+    if (p->prec == B2D_F32) run_fft_pass<float>(*p); else run_fft_pass<double>(*p);
+    ++g_launches;
+    return 0;
+}
+int b2d_launch_copy(const b2d_copy *c)
+{
+    int64_t total = c->n[0] * c->n[1] * c->n[2] * c->n[3];
+    for (int64_t i = 0; i < total; ++i) {
+        if (c->prec == B2D_F32) b2::copy_elem<float>(*c, i); else b2::copy_elem<double>(*c, i);
+    }
+    ++g_launches;
+    return 0;
+}
+int b2d_launch_realop(const b2d_realop *r)
+{
+    if (r->prec == B2D_F32) run_realop<float>(*r); else run_realop<double>(*r);
+    ++g_launches;
+    return 0;
+}
+}

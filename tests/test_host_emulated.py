@@ -1,0 +1,205 @@
+"""Host-layer logic (API validation, tensor canonicalisation, pass-list
+construction, wisdom) and the kernels' index algebra, exercised WITHOUT a GPU
+through the unit-test double of the device shim (tests/emu).  The same checks
+run against the real CUDA kernels in test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fftcheck as F
+from fftw3_b200 import binding as B
+from oracle import oracle as O
+
+PRECS = ["d", "f"]
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 12, 13, 16, 17, 25, 30, 31, 64, 100, 121, 128, 169, 243, 256, 1000, 1009, 1024])
+def test_c2c_1d(emu_lib, prec, n):
+    err, tol = F.c2c(emu_lib, prec, (n,), howmany=3)
+    assert err <= tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("shape,inplace,sign", [((16, 12), False, -1), ((8, 6, 10), True, -1), ((5, 7), True, 1),
+                                                ((4, 4, 4, 3), False, 1), ((1, 8), False, -1), ((8, 1, 3), False, -1)])
+def test_c2c_nd(emu_lib, prec, shape, inplace, sign):
+    err, tol = F.c2c(emu_lib, prec, shape, howmany=2, inplace=inplace, sign=sign)
+    assert err <= tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_c2c_four_step(emu_lib, prec):
+    err, tol = F.c2c(emu_lib, prec, (16384,), howmany=2)
+    assert err <= tol
+    err, tol = F.c2c(emu_lib, prec, (2 * 3 * 5 * 7 * 11 * 13,), howmany=1)   # 30030 mixed radix
+    assert err <= tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("shape", [(16,), (18,), (15,), (9,), (2,), (1,), (4, 6), (3, 5, 8), (6, 7), (1009,), (37,)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_r2c_c2r(emu_lib, prec, shape, inplace):
+    err, tol = F.r2c(emu_lib, prec, shape, howmany=2, inplace=inplace)
+    assert err <= tol
+    err, tol = F.c2r(emu_lib, prec, shape, howmany=2, inplace=inplace)
+    assert err <= tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("kind", list(B.R2R_KINDS))
+@pytest.mark.parametrize("n", [2, 3, 8, 9, 16, 37])
+def test_r2r_1d(emu_lib, prec, kind, n):
+    err, tol = F.r2r(emu_lib, prec, (n,), [kind], howmany=3)
+    assert err <= tol
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_r2r_nd(emu_lib, prec):
+    err, tol = F.r2r(emu_lib, prec, (8, 6), ["REDFT10", "RODFT11"], howmany=2)
+    assert err <= tol
+    err, tol = F.r2r(emu_lib, prec, (5, 12), ["R2HC", "DHT"], howmany=2, inplace=True)
+    assert err <= tol
+    err, tol = F.r2r(emu_lib, prec, (4, 3, 5), ["REDFT00", "RODFT00", "REDFT01"], howmany=1)
+    assert err <= tol
+
+
+def test_strided_advanced_interface(emu_lib):
+    """plan_many_dft with stride/dist/embed: element (j,k) at j*stride + k*dist
+    (doc/reference.texi:1061-1075)."""
+    rng = np.random.default_rng(3)
+    n, howmany, istride, idist, ostride, odist = 12, 5, 3, 40, 2, 30
+    xin = F.rand_complex(rng, (howmany * idist + n * istride,), "d")
+    out = np.full(howmany * odist + n * ostride, 7 + 7j, dtype=np.complex128)
+    p = emu_lib.plan_many_dft("d", [n], howmany, xin.ctypes.data, None, istride, idist, out.ctypes.data, None,
+                              ostride, odist, -1, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    touched = np.zeros(out.shape, bool)
+    for k in range(howmany):
+        ref = O.dft(xin[k * idist:k * idist + n * istride:istride])
+        got = out[k * odist:k * odist + n * ostride:ostride]
+        touched[k * odist:k * odist + n * ostride:ostride] = True
+        assert O.rel_l2(got, ref) < 1e-15
+    assert np.all(out[~touched] == 7 + 7j), "wrote outside the described output locations"
+
+
+def test_embedded_2d(emu_lib):
+    rng = np.random.default_rng(4)
+    n = (6, 10)
+    inembed, onembed = (8, 16), (6, 12)
+    big = F.rand_complex(rng, inembed, "d")
+    out = np.zeros(onembed, dtype=np.complex128)
+    p = emu_lib.plan_many_dft("d", n, 1, big.ctypes.data, inembed, 1, 0, out.ctypes.data, onembed, 1, 0, -1,
+                              B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(out[:6, :10], O.dft(big[:6, :10])) < 1e-15
+
+
+def test_guru_transposed_and_split(emu_lib):
+    """guru interface: arbitrary strides (here a transposed output) and split arrays
+    (api/plan-guru-dft.h:24-44, plan-guru-split-dft.h:24-39)."""
+    rng = np.random.default_rng(5)
+    n0, n1, hm = 8, 6, 3
+    x = F.rand_complex(rng, (hm, n0, n1), "d")
+    y = np.zeros((hm, n1, n0), dtype=np.complex128)        # transposed output
+    dims = [(n0, n1, 1), (n1, 1, n0)]
+    how = [(hm, n0 * n1, n0 * n1)]
+    p = emu_lib.plan_guru_dft("d", dims, how, x.ctypes.data, y.ctypes.data, -1, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    ref = O.dft(x, rank=2)
+    assert O.rel_l2(y.transpose(0, 2, 1), ref) < 1e-15
+    # guru64 + split arrays, backward obtained by swapping re/im arguments
+    ri, ii = np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag)
+    ro, io = np.zeros_like(ri), np.zeros_like(ii)
+    dims = [(n0, n1, n1), (n1, 1, 1)]
+    p = emu_lib.plan_guru_split_dft("d", dims, how, ii.ctypes.data, ri.ctypes.data, io.ctypes.data,
+                                    ro.ctypes.data, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(ro + 1j * io, O.dft(x, sign=+1, rank=2)) < 1e-15
+
+
+def test_new_array_execute(emu_lib):
+    rng = np.random.default_rng(6)
+    n = 48
+    a, b = F.rand_complex(rng, (n,), "d"), np.zeros(n, np.complex128)
+    p = emu_lib.fn("d", "plan_dft_1d")(n, a.ctypes.data, b.ctypes.data, 1, B.FFTW_ESTIMATE)
+    assert p
+    c, d = F.rand_complex(rng, (n,), "d"), np.zeros(n, np.complex128)
+    emu_lib.fn("d", "execute_dft")(p, c.ctypes.data, d.ctypes.data)
+    assert np.all(b == 0)
+    assert O.rel_l2(d, O.dft(c, sign=+1)) < 1e-15
+    p2 = emu_lib.fn("d", "copy_plan")(p)
+    emu_lib.destroy_plan("d", p)
+    emu_lib.execute("d", p2)                      # still alive through the copy
+    assert O.rel_l2(b, O.dft(a, sign=+1)) < 1e-15
+    emu_lib.destroy_plan("d", p2)
+
+
+def test_null_on_invalid(emu_lib):
+    x = np.zeros(64, np.complex128)
+    f = emu_lib.fn("d", "plan_dft_1d")
+    assert not f(0, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)        # n <= 0
+    assert not f(-3, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    assert not emu_lib.plan_many_dft("d", [8], -1, x.ctypes.data, None, 1, 8, x.ctypes.data, None, 1, 8, -1,
+                                     B.FFTW_ESTIMATE)                          # howmany < 0
+    # in place with different strides is unsolvable (dft/problem.c:95-99)
+    assert not emu_lib.plan_many_dft("d", [8], 2, x.ctypes.data, None, 1, 8, x.ctypes.data, None, 2, 16, -1,
+                                     B.FFTW_ESTIMATE)
+    # multi-dimensional out-of-place c2r cannot preserve its input
+    y = np.zeros(64, np.float64)
+    assert not emu_lib.plan_many_dft_c2r("d", [4, 6], 1, x.ctypes.data, None, 1, 16, y.ctypes.data, None, 1, 24,
+                                         B.FFTW_ESTIMATE | B.FFTW_PRESERVE_INPUT)
+    # REDFT00 of size 1 has logical size 0
+    assert not emu_lib.plan_many_r2r("d", [1], 1, y.ctypes.data, None, 1, 1, y.ctypes.data, None, 1, 1,
+                                     ["REDFT00"], B.FFTW_ESTIMATE)
+    # howmany == 0 is a valid no-op plan (dft/nop.c:35-52)
+    p = emu_lib.plan_many_dft("d", [8], 0, x.ctypes.data, None, 1, 8, x.ctypes.data, None, 1, 8, -1, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+
+
+def test_wisdom_roundtrip(emu_lib):
+    emu_lib.fn("d", "forget_wisdom")()
+    x = np.zeros((4, 64), np.complex128)
+    mk = lambda flags: emu_lib.plan_many_dft("d", [64], 4, x.ctypes.data, None, 1, 64, x.ctypes.data, None, 1, 64,
+                                             -1, flags)
+    assert not mk(B.FFTW_WISDOM_ONLY | B.FFTW_MEASURE)          # nothing known yet
+    p = mk(B.FFTW_MEASURE)
+    assert p
+    emu_lib.destroy_plan("d", p)
+    s = emu_lib.export_wisdom_to_string("d")
+    assert s.startswith("(fftw3_b200-") and "b200_fft_pass" in s
+    emu_lib.fn("d", "forget_wisdom")()
+    assert not mk(B.FFTW_WISDOM_ONLY | B.FFTW_MEASURE)
+    assert emu_lib.fn("d", "import_wisdom_from_string")(s.encode()) == 1
+    p = mk(B.FFTW_WISDOM_ONLY | B.FFTW_MEASURE)
+    assert p
+    emu_lib.destroy_plan("d", p)
+    # wrong precision / malformed input is rejected wholesale
+    assert emu_lib.fn("f", "import_wisdom_from_string")(s.encode()) == 0
+    assert emu_lib.fn("d", "import_wisdom_from_string")(b"(fftw-3.3.11 fftw_wisdom #x0)") == 0
+    assert emu_lib.fn("d", "import_wisdom_from_string")(s[:-10].encode()) == 0
+
+
+def test_plan_introspection(emu_lib):
+    x = np.zeros(1024, np.complex128)
+    p = emu_lib.fn("d", "plan_dft_1d")(1024, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    s = emu_lib.sprint_plan("d", p)
+    assert "fft-pass" in s and "n=1024" in s
+    a, m, f = C.c_double(), C.c_double(), C.c_double()
+    emu_lib.fn("d", "flops")(p, C.byref(a), C.byref(m), C.byref(f))
+    assert a.value > 0 and emu_lib.fn("d", "estimate_cost")(p) > 0
+    emu_lib.destroy_plan("d", p)
+    ptr = emu_lib.fn("d", "malloc")(1000)
+    assert ptr and emu_lib.fn("d", "alignment_of")(ptr) == 0
+    emu_lib.fn("d", "free")(ptr)
