@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of fftw3_b200 (contract: see the task brief).
+
+Workload (BASELINE.json `metric`): 3-D complex double c2c 1024^3, in place,
+one "step" = one forward transform of the whole 16 GiB array.
+  N = 1 : the whole array on one B200 (fftw_plan_dft_3d through the C-ABI).
+  N > 1 : slab decomposition over N GPUs, one process per GPU, exchange over
+          NVLink (fftw_mpi_plan_dft_3d equivalent, fftw3_b200/dist.py).
+Metric: GFLOP/s in FFTW's convention 5*N*log2(N)/t (libbench2/mflops.c:19-23).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 1024]
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GIB = 1 << 30
+
+
+def flops_c2c(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return 5.0 * n * math.log2(n)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------ CPU reference
+def cpu_reference_run(steps, warmup, sample_n=256):
+    """The reference's own CPU implementation (oracle/_ref = unmodified FFTW
+    sources compiled codelet-less here, with its OpenMP threads) on a bounded
+    sample of the workload: one in-place c2c double transform of sample_n^3."""
+    import ctypes as C
+    import numpy as np
+    path = os.path.join(ROOT, "oracle", "_ref", "libfftw3_ref.so")
+    kind = "reference"
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    cores = os.cpu_count() or 1
+    lib.fftw_init_threads()
+    lib.fftw_plan_with_nthreads(C.c_int(cores))
+    lib.fftw_plan_dft_3d.restype = C.c_void_p
+    lib.fftw_plan_dft_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
+    lib.fftw_execute.argtypes = [C.c_void_p]
+    lib.fftw_destroy_plan.argtypes = [C.c_void_p]
+    n = sample_n
+    rng = np.random.default_rng(0)
+    a = (rng.uniform(-0.5, 0.5, (n, n, n)) + 1j * rng.uniform(-0.5, 0.5, (n, n, n))).astype(np.complex128)
+    p = lib.fftw_plan_dft_3d(n, n, n, a.ctypes.data, a.ctypes.data, -1, 1 << 6)   # FFTW_ESTIMATE
+    assert p
+    for _ in range(warmup):
+        lib.fftw_execute(p)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.fftw_execute(p)
+    dt = (time.perf_counter() - t0) / steps
+    lib.fftw_destroy_plan(p)
+    return {"value": flops_c2c((n, n, n)) / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+            "sample": "%d^3 c2c double in place, FFTW_ESTIMATE, reference sources built without generated "
+                      "codelets (genfft needs OCaml), %d OpenMP threads" % (n, cores),
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), sample_n=256)
+    n = args.size
+    line = {
+        "impl": "reference", "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": r["value"], "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 c2c double in place (reference arm runs the bounded sample below)" % n},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------- ours
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from fftw3_b200 import binding as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = B.load()
+    n = args.size
+    shape = (n, n, n)
+    dev = torch.device("cuda", local_rank)
+
+    if world > 1:
+        from fftw3_b200 import dist as fdist
+        return fdist.bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run)
+
+    # ---- N = 1: whole array on one GPU, in place, device resident ----
+    a = torch.empty(shape, dtype=torch.complex128, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    ar = torch.view_as_real(a)
+    ar.copy_(torch.rand(ar.shape, dtype=torch.float64, device=dev, generator=g) - 0.5)
+    flags = B.FFTW_MEASURE if not args.estimate else B.FFTW_ESTIMATE
+    t0 = time.perf_counter()
+    plan = lib.fn("d", "plan_dft_3d")(n, n, n, a.data_ptr(), a.data_ptr(), B.FFTW_FORWARD, flags)
+    assert plan, "fftw_plan_dft_3d returned NULL"
+    plan_s = time.perf_counter() - t0
+    plan_txt = lib.sprint_plan("d", plan)
+    # data for the timed runs (planning may have scribbled on nothing: it times on scratch)
+    lib.lib.fftw_b200_set_async(1)
+    for _ in range(max(3, args.warmup)):
+        lib.execute("d", plan)
+        ar.mul_(1.0 / n ** 1.5)        # keep magnitudes bounded across repeated in-place transforms
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = lib.launch_count()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(args.steps):
+        lib.execute("d", plan)          # enqueued on the legacy default stream == torch's current stream
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    ms = total_ms / args.steps
+    gflops = flops_c2c(shape) / (ms * 1e-3) / 1e9
+    lib.lib.fftw_b200_set_async(0)
+
+    # roofline: every pass reads and writes the whole array once
+    array_bytes = 16 * n ** 3
+    passes = launches // args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = passes * 2 * array_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "passes": passes, "algorithmic_bytes_per_launch": 2 * array_bytes,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+
+    # ---- e2e: the same transform through the C-ABI on HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        del a, ar
+        torch.cuda.empty_cache()
+        e2e_steps = max(1, min(args.steps, 2))
+        nbytes = array_bytes
+        hp = lib.fn("d", "malloc")(nbytes)          # pinned when possible
+        assert hp
+        import ctypes as C
+        host = np.ctypeslib.as_array((C.c_double * (2 * n ** 3)).from_address(hp))
+        host[:] = 0.25
+        hplan = lib.fn("d", "plan_dft_3d")(n, n, n, hp, hp, B.FFTW_FORWARD, flags)   # wisdom hit: no re-measuring
+        assert hplan
+        lib.execute("d", hplan)                      # warm-up: allocates the staging buffer
+        host[:] = 0.25
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            lib.execute("d", hplan)                  # synchronous: H2D + 3 passes + D2H
+        dt = (time.perf_counter() - t0) / e2e_steps
+        lib.destroy_plan("d", hplan)
+        lib.fn("d", "free")(hp)
+        e2e = {"value": flops_c2c(shape) / dt / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "ms_per_step": dt * 1e3, "steps": e2e_steps,
+               "api": "fftw_plan_dft_3d + fftw_execute on fftw_malloc'd host memory"}
+    lib.destroy_plan("d", plan)
+
+    cpu = None if args.no_cpu else cpu_reference_run(1, 0, sample_n=256)
+    line = {
+        "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": gflops, "unit": "GFLOP/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 c2c double in place, forward, device resident" % n,
+                   "l2": "array (%.0f GiB) is larger than L2, no flush needed" % (array_bytes / GIB),
+                   "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
+                   "plan": " ".join(plan_txt.split())},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--estimate", action="store_true", help="plan with FFTW_ESTIMATE instead of FFTW_MEASURE")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

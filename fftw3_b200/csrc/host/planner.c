@@ -646,20 +646,84 @@ static int plan_c2c(b2_plan *p)
     return 0;
 }
 
+/* In-place real transforms whose single-pass (odd n) kernel would read and
+   write the same memory are only safe when every line owns its bytes: all
+   outer/batch strides equal on both sides and at least one row long.  Other
+   layouts (e.g. interleaved vectors) get their input staged through scratch,
+   the counterpart of the reference's buffered solvers (rdft/buffered2.c). */
+static int rows_self_contained(const b2_problem *q, int last)
+{
+    int i;
+    int64_t n = q->sz.d[last].n;
+    int64_t nr = (q->kind == B2_R2C) ? n : n / 2 + 1, nw = (q->kind == B2_R2C) ? n / 2 + 1 : n;
+    int64_t ext_in = (nr - 1) * llabs(q->sz.d[last].is) + 2;
+    int64_t ext_out = (nw - 1) * llabs(q->sz.d[last].os) + 2;
+    int64_t ext = ext_in > ext_out ? ext_in : ext_out;
+    for (i = 0; i < q->sz.rnk; ++i) {
+        if (i == last) continue;
+        if (q->sz.d[i].is != q->sz.d[i].os || llabs(q->sz.d[i].is) < ext) return 0;
+    }
+    for (i = 0; i < q->vecsz.rnk; ++i)
+        if (q->vecsz.d[i].is != q->vecsz.d[i].os || llabs(q->vecsz.d[i].is) < ext) return 0;
+    return 1;
+}
+
+/* copy the whole input of a real transform into scratch slot 2 (dense,
+   row-major over [vecsz..., sz...]) and rewrite the problem's input strides */
+static int stage_input(b2_plan *p, b2_problem *q, int last, int *src0, int *src1)
+{
+    b2_tensor t;
+    int i, k = 0, rc;
+    int cmplx = (q->kind == B2_C2R);
+    int64_t ld = cmplx ? 2 : 1;
+    int64_t nlast = cmplx ? q->sz.d[last].n / 2 + 1 : q->sz.d[last].n;
+    b2_tensor_init(&t, 0);
+    /* dense strides: last transform dim fastest, then the other sz dims, then vecsz */
+    for (i = q->sz.rnk - 1; i >= 0; --i) {
+        t.d[k].n = (i == last) ? nlast : q->sz.d[i].n;
+        t.d[k].is = q->sz.d[i].is; t.d[k].os = ld;
+        q->sz.d[i].is = ld;
+        ld *= t.d[k].n; ++k;
+    }
+    for (i = q->vecsz.rnk - 1; i >= 0; --i) {
+        t.d[k].n = q->vecsz.d[i].n;
+        t.d[k].is = q->vecsz.d[i].is; t.d[k].os = ld;
+        q->vecsz.d[i].is = ld;
+        ld *= t.d[k].n; ++k;
+    }
+    t.rnk = k;
+    need_scratch(p, 2, (size_t)ld * real_size(q->prec));
+    rc = emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_SCRATCH2, 0), &t, 1);
+    if (rc) return rc;
+    if (cmplx) {
+        rc = emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_SCRATCH2, 1), &t, 1);
+        if (rc) return rc;
+    }
+    *src0 = BUF_SCRATCH2; *src1 = BUF_SCRATCH2;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ r2c */
 static int plan_r2c(b2_plan *p)
 {
-    const b2_problem *q = &p->prob;
+    b2_problem qq = p->prob;
+    const b2_problem *q = &qq;
     int last = q->sz.rnk - 1, d, rc;
     int64_t n, is, os;
     b2_tensor batch;
     b2_ops ops;
     b2_view in, out;
+    int src0 = BUF_IN0, src1 = BUF_IN0;
     if (q->sz.rnk < 1) {
         /* rank 0 r2c: copy real part, zero imaginary: express as n=1 transform */
         return -1;
     }
-    n = q->sz.d[last].n; is = q->sz.d[last].is; os = q->sz.d[last].os;
+    n = q->sz.d[last].n;
+    if (p->inplace && (n % 2) && !rows_self_contained(q, last)) {
+        rc = stage_input(p, &qq, last, &src0, &src1);
+        if (rc) return rc;
+    }
+    is = q->sz.d[last].is; os = q->sz.d[last].os;
     other_dims(q, last, 0, &batch);
     memset(&ops, 0, sizeof ops);
     out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = os;
@@ -705,7 +769,7 @@ static int plan_r2c(b2_plan *p)
         rc = emit_realop(p, &c, &fb);
         if (rc) return rc;
     } else {
-        in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN0, 0); in.stride = is;
+        in.re = mkref(src0, 0); in.im = mkref(src0, 0); in.stride = is;
         ops.pre_op = B2D_LOAD_REAL; ops.post_op = B2D_STORE_TRUNC; ops.n_out = (int)(n / 2 + 1);
         rc = emit_fft1d(p, q->prec, n, in, out, &batch, ops, 1, "r2c odd");
         if (rc) return rc;
@@ -732,15 +796,23 @@ static int plan_r2c(b2_plan *p)
 /* ------------------------------------------------------------------ c2r */
 static int plan_c2r(b2_plan *p)
 {
-    const b2_problem *q = &p->prob;
+    b2_problem qq = p->prob;
+    const b2_problem *q = &qq;
     int last = q->sz.rnk - 1, d, rc;
     int64_t n, is, os;
     b2_tensor batch;
     b2_ops ops;
     b2_view in, out;
     int src_re = BUF_IN0, src_im = BUF_IN1;
+    int64_t im_off = 0;
     if (q->sz.rnk < 1) return -1;
-    n = q->sz.d[last].n; is = q->sz.d[last].is; os = q->sz.d[last].os;
+    n = q->sz.d[last].n;
+    if (p->inplace && (n % 2) && !rows_self_contained(q, last)) {
+        rc = stage_input(p, &qq, last, &src_re, &src_im);
+        if (rc) return rc;
+        im_off = 1;
+    }
+    is = q->sz.d[last].is; os = q->sz.d[last].os;
     memset(&ops, 0, sizeof ops);
 
     if (q->sz.rnk > 1) {
@@ -762,7 +834,7 @@ static int plan_c2r(b2_plan *p)
             for (i = 0; i < q->vecsz.rnk; ++i) { b2.d[k] = q->vecsz.d[i]; b2.d[k].os = q->vecsz.d[i].is; ++k; }
             b2.rnk = k;
             /* backward = forward with re/im swapped */
-            in.re = mkref(src_im, 0); in.im = mkref(src_re, 0); in.stride = q->sz.d[d].is;
+            in.re = mkref(src_im, im_off); in.im = mkref(src_re, 0); in.stride = q->sz.d[d].is;
             rc = emit_fft1d(p, q->prec, q->sz.d[d].n, in, in, &b2, ops, 1, "c2r outer dft");
             if (rc) return rc;
         }
@@ -780,7 +852,7 @@ static int plan_c2r(b2_plan *p)
         need_scratch(p, 0, (size_t)(b2_tensor_count(&wb) > 0 ? b2_tensor_count(&wb) : 1) * (size_t)m * esz);
         memset(&c, 0, sizeof c);
         c.prec = q->prec; c.op = B2D_ROP_C2R_PRE; c.n = (int)n; c.m = (int)m; c.xs = is;
-        c.x_re = mkref(src_re, 0); c.x_im = mkref(src_im, 0);
+        c.x_re = mkref(src_re, 0); c.x_im = mkref(src_im, im_off);
         c.work_slot = 0; c.wdist = m; c.user_is_out = 0;
         c.tw = plan_table(p, q->prec, TAB_R2C, n, 0);
         if (!c.tw) return -1;
@@ -802,7 +874,7 @@ static int plan_c2r(b2_plan *p)
         rc = emit_fft1d(p, q->prec, m, wv, out, &fb, ops, 1, "c2r half-size dft");
         if (rc) return rc;
     } else {
-        in.re = mkref(src_re, 0); in.im = mkref(src_im, 0); in.stride = is;
+        in.re = mkref(src_re, 0); in.im = mkref(src_im, im_off); in.stride = is;
         ops.pre_op = B2D_LOAD_HERMCONJ; ops.post_op = B2D_STORE_REALPART;
         ops.n_in = (int)n; ops.n_out = (int)n;
         rc = emit_fft1d(p, q->prec, n, in, out, &batch, ops, 1, "c2r odd");

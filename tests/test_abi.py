@@ -1,0 +1,52 @@
+"""The product C-ABI library loads on a GPU-less box and exports every symbol
+include/fftw3.h declares; without a device plan creation fails cleanly (NULL),
+it never computes on the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    inc = open(os.path.join(ROOT, "include", "fftw3_api.inc")).read()
+    names = set(re.findall(r"FFTW3_NS\((\w+)\)\s*\(", inc))
+    names -= {"plan_s"}
+    names |= {"version", "cc", "codelet_optim"}
+    ext = re.findall(r"\b(fftw_b200_\w+)\s*\(", open(os.path.join(ROOT, "include", "fftw3.h")).read())
+    return sorted(names), sorted(set(ext))
+
+
+def test_exports_every_declared_symbol():
+    from fftw3_b200 import binding
+    path = binding.default_library_path()
+    if not os.path.exists(path):
+        binding.build_library()
+    lib = C.CDLL(path)
+    names, ext = declared_symbols()
+    assert len(names) >= 76      # 73 functions + version, cc, codelet_optim
+    missing = [p + n for p in ("fftw_", "fftwf_") for n in names if not hasattr(lib, p + n)]
+    missing += [e for e in ext if not hasattr(lib, e)]
+    assert not missing, missing
+    for alias in ("libfftw3.so.3", "libfftw3f.so.3"):
+        assert os.path.exists(os.path.join(os.path.dirname(path), alias))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        return                       # on the GPU box the parity tests cover the real path
+    from fftw3_b200 import binding as B
+    lib = B.load()
+    x = np.zeros(64, np.complex128)
+    p = lib.fn("d", "plan_dft_1d")(64, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    assert not p, "a plan was created without a CUDA device: that would be a CPU fallback"
+
+
+def test_product_library_does_not_reference_oracle():
+    """The shipped library must not link or embed anything from oracle/."""
+    from fftw3_b200 import binding
+    data = open(binding.default_library_path(), "rb").read()
+    assert b"oracle_dft" not in data and b"liboracle" not in data and b"_ref.so" not in data
