@@ -1,13 +1,208 @@
-// fft_fast.cuh -- compile-time specialised Stockham kernels for the hot sizes
-// (register-resident first/last stage, single shared-memory exchange buffer).
-// try_launch() returns 0 when it handled the pass, 1 when the pass is not one
-// of the specialised shapes (caller uses the generic kernel), <0 on error.
+// fft_fast.cuh -- compile-time specialised Stockham kernels for the hot
+// power-of-two sizes ("codelets" of this engine; the generic kernel in
+// fft_generic.cuh is the any-size solver).
+//
+// Differences from the generic pass:
+//   * the first radix stage reads HBM straight into registers and the last
+//     stage stores from registers straight to HBM: shared memory is used only
+//     for the exchanges between stages (one buffer, N complex per transform);
+//   * everything (N, radices, threads) is a template parameter, so the stage
+//     loops are fully unrolled straight-line code around the generated
+//     butterflies; interleaved complex data moves as 128-bit (f64) / 64-bit
+//     (f32) vectors;
+//   * COL variant: a CTA owns TPB adjacent pencils of a strided dimension; lanes
+//     walk the pencils, so each HBM access is TPB*16 contiguous bytes and the
+//     [k][t] shared layout is bank-conflict free.  ROW variant: lanes walk one
+//     contiguous transform.
+//
+// Reference counterpart: the n1/t1 codelets and their drivers
+// (dft/direct.c:92-97, dft/dftw-direct.c:46-56) plus the buffered strided
+// access of dft/buffered.c:41-69 / dft/indirect-transpose.c.
 #pragma once
 #include <cuda_runtime.h>
 #include "fft_generic.cuh"
 
 namespace b2fast {
-inline void init(int /*max_smem*/) {}
-inline size_t smem_bytes(const b2d_fft_pass &) { return 0; }
-inline int try_launch(const b2d_fft_pass &, cudaStream_t) { return 1; }
+using b2::cplx;
+using b2::cmul;
+
+// read-only (texture path) load of one complex twiddle
+__device__ __forceinline__ cplx<double> ldg_c(const cplx<double> *p)
+{
+    double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    cplx<double> r; r.x = v.x; r.y = v.y; return r;
+}
+__device__ __forceinline__ cplx<float> ldg_c(const cplx<float> *p)
+{
+    float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+    cplx<float> r; r.x = v.x; r.y = v.y; return r;
+}
+
+// padded row pitch for the ROW layout (same padding rule as the generic kernel)
+__host__ __device__ constexpr int padk_c(int k) { return k + (k >> 4); }
+__host__ __device__ constexpr int pitch_c(int n) { return padk_c(n - 1) + 2; }
+
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
+struct FastCfg {
+    static constexpr int TPX = N / E;
+    static constexpr int THREADS = TPX * TPB;
+    static constexpr int SMEM_ELEMS = COL ? N * TPB : pitch_c(N) * TPB;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_ELEMS * sizeof(cplx<T>);
+    static_assert(E * R1 * R2 == N, "radices must multiply to N");
+    static_assert(E % R1 == 0 && E % R2 == 0, "later radices must divide the per-thread element count");
+};
+
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
+__global__ void __launch_bounds__(FastCfg<T, N, E, R1, R2, TPB, COL>::THREADS)
+fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
+{
+    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL>;
+    constexpr int TPX = Cfg::TPX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx<T> *sm = reinterpret_cast<cplx<T> *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int t = COL ? (tid % TPB) : (tid / TPX);
+    const int j = COL ? (tid / TPB) : (tid % TPX);
+    auto sidx = [&](int k) -> int { return COL ? (k * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
+
+    const b2::TileCtx c = b2::decode_block(p, (int64_t)blockIdx.x);
+    const int64_t b0 = c.tile0 * TPB + t;
+    const bool valid = b0 < p.bn[0];
+    const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
+    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2];
+    // interleaved data: vector pointer at the lower of (re, im)
+    const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re);
+    cplx<T> *gout = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re);
+    const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
+    const int64_t bin2 = boff_in / 2, bout2 = boff_out / 2;
+    const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
+
+    T re[E], im[E];
+    // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        cplx<T> v; v.x = T(0); v.y = T(0);
+        if (valid) v = gin[bin2 + (int64_t)(j + r * TPX) * is2];
+        re[r] = swap_in ? v.y : v.x;
+        im[r] = swap_in ? v.x : v.y;
+    }
+    Butterfly<E, T>::run(re, im);
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        cplx<T> v; v.x = re[r]; v.y = im[r];
+        sm[sidx(j * E + r)] = v;
+    }
+    __syncthreads();
+
+    // ---- stage 2: radix R1, Ns = E
+    {
+        constexpr int NB = N / R1;            // butterflies per transform
+        constexpr int PER = E / R1;           // butterflies per thread
+        constexpr int TSTEP = N / (E * R1);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = j + i * TPX;
+            const int k = b % E;
+#pragma unroll
+            for (int r = 0; r < R1; ++r) {
+                cplx<T> v = sm[sidx(b + r * NB)];
+                if (r > 0) v = cmul(v, ldg_c(&tw[TSTEP * r * k]));
+                re[i * R1 + r] = v.x; im[i * R1 + r] = v.y;
+            }
+        }
+        if (R2 > 1) __syncthreads();          // all reads done before the buffer is overwritten
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            T xr[R1], xi[R1];
+#pragma unroll
+            for (int r = 0; r < R1; ++r) { xr[r] = re[i * R1 + r]; xi[r] = im[i * R1 + r]; }
+            Butterfly<R1, T>::run(xr, xi);
+#pragma unroll
+            for (int r = 0; r < R1; ++r) { re[i * R1 + r] = xr[r]; im[i * R1 + r] = xi[r]; }
+        }
+        if (R2 > 1) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int b = j + i * TPX;
+                const int k = b % E;
+                const int j0 = (b - k) * R1 + k;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) {
+                    cplx<T> v; v.x = re[i * R1 + r]; v.y = im[i * R1 + r];
+                    sm[sidx(j0 + r * E)] = v;
+                }
+            }
+            __syncthreads();
+        } else {
+            // two-stage transform: this was the last stage (Ns = E = N / R1, so k = b)
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int b = j + i * TPX;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) {
+                    cplx<T> v;
+                    v.x = swap_out ? im[i * R1 + r] : re[i * R1 + r];
+                    v.y = swap_out ? re[i * R1 + r] : im[i * R1 + r];
+                    if (valid) gout[bout2 + (int64_t)(b + r * E) * os2] = v;
+                }
+            }
+            return;
+        }
+    }
+
+    // ---- stage 3: radix R2, Ns = E * R1 (last: k = b, outputs at b + r * Ns)
+    if (R2 > 1) {
+        constexpr int NS = E * R1;
+        constexpr int PER = E / R2;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = j + i * TPX;
+            T xr[R2 > 1 ? R2 : 2], xi[R2 > 1 ? R2 : 2];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                cplx<T> v = sm[sidx(b + r * NS)];
+                if (r > 0) v = cmul(v, ldg_c(&tw[r * b]));
+                xr[r] = v.x; xi[r] = v.y;
+            }
+            Butterfly<(R2 > 1 ? R2 : 2), T>::run(xr, xi);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                cplx<T> v;
+                v.x = swap_out ? xi[r] : xr[r];
+                v.y = swap_out ? xr[r] : xi[r];
+                if (valid) gout[bout2 + (int64_t)(b + r * NS) * os2] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ registry
+struct FastEntry {
+    int prec, n, col, tpb, code;
+    size_t smem;
+    int threads;
+    void (*launch)(const b2d_fft_pass &, int, int, unsigned, cudaStream_t);
+    const void *func;
+};
+
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
+void launch_one(const b2d_fft_pass &p, int swap_in, int swap_out, unsigned blocks, cudaStream_t st)
+{
+    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL>;
+    fast_kernel<T, N, E, R1, R2, TPB, COL><<<blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, swap_in, swap_out);
+}
+
+#define B2_FAST_ENTRY(PREC, T, N, E, R1, R2, TPB, COL, CODE)                                        \
+    { PREC, N, COL, TPB, CODE, FastCfg<T, N, E, R1, R2, TPB, COL>::SMEM_BYTES,                      \
+      FastCfg<T, N, E, R1, R2, TPB, COL>::THREADS, &launch_one<T, N, E, R1, R2, TPB, COL>,          \
+      (const void *)&fast_kernel<T, N, E, R1, R2, TPB, COL> }
+
+const FastEntry *table(int *count);   // defined in fft_fast_table.cu
+
+void init(int max_smem);
+size_t smem_bytes(const b2d_fft_pass &p);
+int available(const b2d_fft_pass &p, int code);
+int try_launch(const b2d_fft_pass &p, cudaStream_t st);
+
 }  // namespace b2fast

@@ -1,0 +1,91 @@
+// fft_fast_dispatch.cu -- lookup and launch of the specialised kernels whose
+// instantiations live in the generated fft_fast_table_*.cu files.
+#include <stdint.h>
+#include "fft_fast.cuh"
+
+namespace b2fast {
+
+extern const FastEntry table_d_row[], table_d_col[], table_f_row[], table_f_col[];
+extern const int table_d_row_count, table_d_col_count, table_f_row_count, table_f_col_count;
+
+static int g_max_smem = 0;
+
+static const FastEntry *find(int prec, int n, int col, int tpb)
+{
+    const FastEntry *t;
+    int cnt, i;
+    if (prec == B2D_F64) { t = col ? table_d_col : table_d_row; cnt = col ? table_d_col_count : table_d_row_count; }
+    else { t = col ? table_f_col : table_f_row; cnt = col ? table_f_col_count : table_f_row_count; }
+    for (i = 0; i < cnt; ++i)
+        if (t[i].n == n && t[i].tpb == tpb) return &t[i];
+    return nullptr;
+}
+
+void init(int max_smem)
+{
+    g_max_smem = max_smem;
+    const FastEntry *tabs[4] = { table_d_row, table_d_col, table_f_row, table_f_col };
+    const int cnts[4] = { table_d_row_count, table_d_col_count, table_f_row_count, table_f_col_count };
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < cnts[k]; ++i)
+            if (tabs[k][i].smem > 48 * 1024)
+                cudaFuncSetAttribute(tabs[k][i].func, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tabs[k][i].smem);
+}
+
+// structural applicability (known at plan time)
+static const FastEntry *entry_for(const b2d_fft_pass &p)
+{
+    if (!p.kernel) return nullptr;
+    if (p.pre_op || p.post_op || p.bluestein) return nullptr;
+    if (p.load_col != p.store_col) return nullptr;
+    const int col = p.kernel >= 1000;
+    if (col != p.load_col) return nullptr;
+    const int tpb = p.kernel % 1000;
+    if ((p.is & 1) || (p.os & 1)) return nullptr;
+    for (int i = 0; i < B2D_MAX_BATCH_DIMS; ++i)
+        if ((p.bis[i] & 1) || (p.bos[i] & 1)) return nullptr;
+    if (col && (p.bis[0] != 2 || p.bos[0] != 2)) return nullptr;     // adjacent pencils
+    if (!col && (p.is != 2 || p.os != 2)) return nullptr;            // contiguous transforms
+    const FastEntry *e = find(p.prec, p.n, col, tpb);
+    if (e && (int)e->smem > g_max_smem && g_max_smem) return nullptr;
+    return e;
+}
+
+int available(const b2d_fft_pass &p, int code)
+{
+    b2d_fft_pass q = p;
+    q.kernel = code;
+    return entry_for(q) != nullptr;
+}
+
+size_t smem_bytes(const b2d_fft_pass &p)
+{
+    const FastEntry *e = entry_for(p);
+    return e ? e->smem : 0;
+}
+
+int try_launch(const b2d_fft_pass &p, cudaStream_t st)
+{
+    const FastEntry *e = entry_for(p);
+    if (!e) return 1;
+    const size_t rs = p.prec == B2D_F32 ? 4 : 8;
+    const intptr_t din = (const char *)p.in_im - (const char *)p.in_re;
+    const intptr_t dout = (char *)p.out_im - (char *)p.out_re;
+    // interleaved (im = re +- 1 scalar) and vector-aligned, else the generic kernel handles it
+    if ((din != (intptr_t)rs && din != -(intptr_t)rs) || (dout != (intptr_t)rs && dout != -(intptr_t)rs)) return 1;
+    const int swap_in = din < 0, swap_out = dout < 0;
+    const uintptr_t lo_in = (uintptr_t)(swap_in ? p.in_im : p.in_re);
+    const uintptr_t lo_out = (uintptr_t)(swap_out ? p.out_im : p.out_re);
+    if ((lo_in % (2 * rs)) || (lo_out % (2 * rs))) return 1;
+    const int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
+    const int64_t blocks = tiles0 * p.bn[1] * p.bn[2];
+    if (blocks <= 0) return 0;
+    if (blocks > 2147483647LL) return -1;
+    b2d_fft_pass q = p;
+    q.tpb = e->tpb;                  // decode_block() uses the tile width
+    e->launch(q, swap_in, swap_out, (unsigned)blocks, st);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace b2fast

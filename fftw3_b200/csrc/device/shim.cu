@@ -147,6 +147,12 @@ size_t b2d_fft_pass_smem(const b2d_fft_pass *p)
     return p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
 }
 
+int b2d_fast_available(const b2d_fft_pass *p, int code)
+{
+    if (ensure_init()) return 0;
+    return b2fast::available(*p, code);
+}
+
 int b2d_launch_fft_pass(const b2d_fft_pass *p)
 {
     if (ensure_init()) return -1;
@@ -156,7 +162,7 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     int rc = b2fast::try_launch(*p, g_stream);
     if (rc == 0) { g_launches++; return 0; }
     if (rc < 0) { snprintf(g_err, sizeof g_err, "fast kernel launch failed"); return -1; }
-    size_t smem = b2d_fft_pass_smem(p);
+    size_t smem = p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
     if (smem > g_max_smem) { snprintf(g_err, sizeof g_err, "pass needs %zu B smem", smem); return -1; }
     int threads = p->tpb * p->tpx;
     if (threads < 32) threads = 32;

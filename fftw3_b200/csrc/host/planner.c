@@ -173,15 +173,45 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
     f->tpx = tpx;
 }
 
-#define NVARIANTS 12
+#define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
+#define NFAST 6               /* specialised-kernel variants 12..17: tile width 1,2,4,8,16,32 */
 
 static int configure_variant(b2d_fft_pass *f, int variant)
 {
-    int ns = b2_factorize(f->n, f->prec, variant % 3, f->radix);
+    int ns;
+    f->kernel = 0;
+    if (variant >= NVARIANTS) {
+        int tpb = 1 << (variant - NVARIANTS);
+        int code = ((f->load_col || f->store_col) ? 1000 : 0) + tpb;
+        if (variant >= NVARIANTS + NFAST) return -1;
+        if (!b2d_fast_available(f, code)) return -1;
+        /* generic geometry stays configured: it is the fallback for misaligned new arrays */
+        ns = b2_factorize(f->n, f->prec, 0, f->radix);
+        if (ns == 0) return -1;
+        f->nstages = ns < 0 ? 0 : ns;
+        fill_geometry(f, 0);
+        f->kernel = code;
+        return 0;
+    }
+    ns = b2_factorize(f->n, f->prec, variant % 3, f->radix);
     if (ns == 0) return -1;
     f->nstages = ns < 0 ? 0 : ns;
     fill_geometry(f, variant);
     if (b2d_fft_pass_smem(f) > b2d_max_smem_per_block()) return -1;
+    return 0;
+}
+
+/* closed-form choice (FFTW_ESTIMATE): a specialised kernel when one exists */
+static int estimate_variant(b2d_fft_pass *f)
+{
+    static const int col_pref[] = { 3, 4, 2, 5 }, row_pref[] = { 1, 2, 0, 3, 4, 5 };
+    int col = f->load_col || f->store_col, i;
+    const int *pref = col ? col_pref : row_pref;
+    int npref = col ? 4 : 6;
+    for (i = 0; i < npref; ++i) {
+        b2d_fft_pass t = *f;
+        if (!configure_variant(&t, NVARIANTS + pref[i])) return NVARIANTS + pref[i];
+    }
     return 0;
 }
 
@@ -300,7 +330,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         if (b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
         if (!have && pat >= 1) {
-            int v, nv = (pat >= 2) ? NVARIANTS : 6, bestv = -1;
+            int v, nv = NVARIANTS + NFAST, bestv = -1;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
@@ -312,14 +342,22 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
             for (v = 0; v < nv; ++v) {
                 double t;
                 b2d_fft_pass trial = *f;
+                if (v >= 6 && v < NVARIANTS && pat < 2) continue;   /* extra generic shapes: PATIENT only */
                 if (configure_variant(&trial, v)) continue;
                 /* skip duplicates of an earlier geometry */
                 t = time_pass(&trial, inplace, dri, dro);
+                if (getenv("FFTW3_B200_VERBOSE")) {
+                    double bytes = 4.0 * real_size(prec) * (double)f->n * (double)(f->bn[0] * f->bn[1] * f->bn[2]);
+                    fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
+                            f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
+                            (long long)f->bn[1], (long long)f->bn[2], v, trial.kernel ? "codelet" : "generic",
+                            trial.kernel ? trial.kernel % 1000 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
+                }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
             }
             if (bestv >= 0) { variant = bestv; have = 1; p->cost += bestt; }
         }
-        if (!have) variant = 0;
+        if (!have) variant = estimate_variant(f);
         if (configure_variant(f, variant)) {
             if (configure_variant(f, 0)) return -1;
             variant = 0;
@@ -1047,9 +1085,11 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             const b2d_fft_pass *q = &s->u.fft;
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
-            fprintf(f, " batch=%lldx%lldx%lld tpb=%d tpx=%d %s->%s%s)", (long long)q->bn[0], (long long)q->bn[1],
-                    (long long)q->bn[2], q->tpb, q->tpx, q->load_col ? "col" : "row",
-                    q->store_col ? "col" : "row", q->bluestein ? " bluestein" : "");
+            fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
+            if (q->kernel) fprintf(f, "codelet-tile=%d", q->kernel % 1000);
+            else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
+            fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
+                    q->bluestein ? " bluestein" : "");
         } else if (s->kind == STEP_COPY) {
             fprintf(f, "\n  (copy %lldx%lldx%lldx%lld)", (long long)s->u.copy.n[0], (long long)s->u.copy.n[1],
                     (long long)s->u.copy.n[2], (long long)s->u.copy.n[3]);

@@ -55,6 +55,8 @@ typedef struct b2d_fft_pass {
                                  1: consecutive lanes walk batch dim 0 (COL)         */
     int pre_op, post_op;
     int bluestein;            /* 1: forward stages, x aux1[k], inverse stages        */
+    int kernel;               /* 0: generic runtime-radix kernel; else code of a
+                                 specialised kernel: tile width + 1000 for COL      */
     int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
     int64_t is, os;           /* element stride along the transform                  */
     int64_t bn[B2D_MAX_BATCH_DIMS], bis[B2D_MAX_BATCH_DIMS], bos[B2D_MAX_BATCH_DIMS];
@@ -128,6 +130,7 @@ int  b2d_timer_stop(float *ms);
 /* ---- kernels ---- */
 int  b2d_launch_fft_pass(const b2d_fft_pass *p);
 size_t b2d_fft_pass_smem(const b2d_fft_pass *p);  /* dynamic smem bytes it needs   */
+int  b2d_fast_available(const b2d_fft_pass *p, int code); /* specialised kernel exists for this shape? */
 int  b2d_launch_copy(const b2d_copy *c);
 int  b2d_launch_realop(const b2d_realop *r);
 

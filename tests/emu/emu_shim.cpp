@@ -104,6 +104,7 @@ size_t b2d_fft_pass_smem(const b2d_fft_pass *p)
 {
     return p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
 }
+int b2d_fast_available(const b2d_fft_pass *, int) { return 0; }   /* specialised kernels are GPU-only */
 int b2d_launch_fft_pass(const b2d_fft_pass *p)
 {
     if (b2d_fft_pass_smem(p) > b2d_max_smem_per_block()) {
