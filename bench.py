@@ -168,11 +168,15 @@ def run_ours(args):
     ar = torch.view_as_real(a)
     ar.copy_(torch.rand(ar.shape, dtype=torch.float64, device=dev, generator=g) - 0.5)
     flags = B.FFTW_MEASURE if not args.estimate else B.FFTW_ESTIMATE
+    if args.wisdom and os.path.exists(args.wisdom):
+        lib.fn("d", "import_wisdom_from_filename")(args.wisdom.encode())
     t0 = time.perf_counter()
     plan = lib.fn("d", "plan_dft_3d")(n, n, n, a.data_ptr(), a.data_ptr(), B.FFTW_FORWARD, flags)
     assert plan, "fftw_plan_dft_3d returned NULL"
     plan_s = time.perf_counter() - t0
     plan_txt = lib.sprint_plan("d", plan)
+    if args.wisdom:
+        lib.fn("d", "export_wisdom_to_filename")(args.wisdom.encode())
     # data for the timed runs (planning may have scribbled on nothing: it times on scratch)
     lib.lib.fftw_b200_set_async(1)
     for _ in range(max(3, args.warmup)):
@@ -266,6 +270,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--estimate", action="store_true", help="plan with FFTW_ESTIMATE instead of FFTW_MEASURE")
+    ap.add_argument("--wisdom", default=None, help="wisdom file to import before planning and export after")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
