@@ -9,15 +9,21 @@
 //   * everything (N, radices, threads) is a template parameter, so the stage
 //     loops are fully unrolled straight-line code around the generated
 //     butterflies; interleaved complex data moves as 128-bit (f64) / 64-bit
-//     (f32) vectors;
+//     (f32) vectors with streaming (evict-first) cache hints;
+//   * twiddles: a thread loads at most 6 table entries per stage and derives the
+//     others with one complex multiply each (two-level w^(4a+c) = w^(4a) w^c, and
+//     compile-time roots of unity for the butterflies it owns beyond the first)
+//     -- the L1 load pipe, not HBM, was the limiter with one load per twiddle
+//     (profiles/r01_ncu_full_fast_kernels_summary.txt);
 //   * COL variant: a CTA owns TPB adjacent pencils of a strided dimension; lanes
 //     walk the pencils, so each HBM access is TPB*16 contiguous bytes and the
 //     [k][t] shared layout is bank-conflict free.  ROW variant: lanes walk one
 //     contiguous transform.
 //
 // Reference counterpart: the n1/t1 codelets and their drivers
-// (dft/direct.c:92-97, dft/dftw-direct.c:46-56) plus the buffered strided
-// access of dft/buffered.c:41-69 / dft/indirect-transpose.c.
+// (dft/direct.c:92-97, dft/dftw-direct.c:46-56; twiddle policies of
+// genfft/twiddle.ml, "-twiddle-log3") plus the buffered strided access of
+// dft/buffered.c:41-69 / dft/indirect-transpose.c.
 #pragma once
 #include <cuda_runtime.h>
 #include "fft_generic.cuh"
@@ -26,7 +32,6 @@ namespace b2fast {
 using b2::cplx;
 using b2::cmul;
 
-// read-only (texture path) load of one complex twiddle
 __device__ __forceinline__ cplx<double> ldg_c(const cplx<double> *p)
 {
     double2 v = __ldg(reinterpret_cast<const double2 *>(p));
@@ -37,26 +42,85 @@ __device__ __forceinline__ cplx<float> ldg_c(const cplx<float> *p)
     float2 v = __ldg(reinterpret_cast<const float2 *>(p));
     cplx<float> r; r.x = v.x; r.y = v.y; return r;
 }
+// streaming loads / stores: the array is touched once per pass
+__device__ __forceinline__ cplx<double> ld_stream(const cplx<double> *p)
+{
+    double2 v = __ldcs(reinterpret_cast<const double2 *>(p));
+    cplx<double> r; r.x = v.x; r.y = v.y; return r;
+}
+__device__ __forceinline__ cplx<float> ld_stream(const cplx<float> *p)
+{
+    float2 v = __ldcs(reinterpret_cast<const float2 *>(p));
+    cplx<float> r; r.x = v.x; r.y = v.y; return r;
+}
+__device__ __forceinline__ void st_stream(cplx<double> *p, cplx<double> v)
+{
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(v.x, v.y));
+}
+__device__ __forceinline__ void st_stream(cplx<float> *p, cplx<float> v)
+{
+    __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y));
+}
+
+// compile-time root of unity W_E^m (m is a constant after unrolling)
+template <int E, typename T>
+__device__ __forceinline__ cplx<T> unit_root(int m)
+{
+    cplx<T> c;
+    if (E == 4) unit_root4<T>(m, c.x, c.y);
+    else if (E == 8) unit_root8<T>(m, c.x, c.y);
+    else if (E == 16) unit_root16<T>(m, c.x, c.y);
+    else unit_root32<T>(m, c.x, c.y);
+    return c;
+}
+
+// w[r] = table[step * r] for r = 1..R-1 (w[0] unused): direct loads for R <= 4,
+// two-level for larger R (3 + R/4 - 1 loads, one complex multiply for the rest)
+template <int R, typename T>
+__device__ __forceinline__ void load_twiddles(const cplx<T> *tw, int step, cplx<T> (&w)[R])
+{
+    if (R <= 4) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r] = ldg_c(&tw[step * r]);
+    } else {
+#pragma unroll
+        for (int c = 1; c < 4; ++c) w[c] = ldg_c(&tw[step * c]);
+#pragma unroll
+        for (int a = 1; a < R / 4; ++a) {
+            w[4 * a] = ldg_c(&tw[step * 4 * a]);
+#pragma unroll
+            for (int c = 1; c < 4; ++c) w[4 * a + c] = cmul(w[4 * a], w[c]);
+        }
+    }
+}
 
 // padded row pitch for the ROW layout (same padding rule as the generic kernel)
 __host__ __device__ constexpr int padk_c(int k) { return k + (k >> 4); }
 __host__ __device__ constexpr int pitch_c(int n) { return padk_c(n - 1) + 2; }
 
-template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
 struct FastCfg {
     static constexpr int TPX = N / E;
     static constexpr int THREADS = TPX * TPB;
     static constexpr int SMEM_ELEMS = COL ? N * TPB : pitch_c(N) * TPB;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_ELEMS * sizeof(cplx<T>);
+    // resident CTAs per SM we ask ptxas to make room for (register cap)
+    static constexpr int BY_SMEM = (int)(232448 / (SMEM_BYTES + 1024)) > 0 ? (int)(232448 / (SMEM_BYTES + 1024)) : 1;
+    static constexpr int BY_REGS = 65536 / (THREADS * (sizeof(T) == 8 ? (E >= 16 ? 84 : 56) : (E >= 32 ? 84 : (E >= 16 ? 56 : 40))));
+    static constexpr int BY_THREADS = 2048 / THREADS;
+    static constexpr int MINB_ = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+    static constexpr int MINB__ = (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) > 0 ? (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) : 1;
+    static constexpr int MINB = FLAVOR == 1 ? MINB__ : 1;   // flavor 1: cap registers for more resident CTAs
     static_assert(E * R1 * R2 == N, "radices must multiply to N");
     static_assert(E % R1 == 0 && E % R2 == 0, "later radices must divide the per-thread element count");
+    static_assert(TPX % E == 0 || R2 == 1, "stage-2 twiddle index must be thread-constant");
 };
 
-template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
-__global__ void __launch_bounds__(FastCfg<T, N, E, R1, R2, TPB, COL>::THREADS)
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
+__global__ void __launch_bounds__(FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::MINB)
 fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
 {
-    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL>;
+    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>;
     constexpr int TPX = Cfg::TPX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T> *sm = reinterpret_cast<cplx<T> *>(smem_raw);
@@ -72,18 +136,18 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
     const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2];
     // interleaved data: vector pointer at the lower of (re, im)
-    const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re);
-    cplx<T> *gout = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re);
+    const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re) + boff_in / 2;
+    cplx<T> *gout = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re) + boff_out / 2;
     const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
-    const int64_t bin2 = boff_in / 2, bout2 = boff_out / 2;
     const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
+    const bool keep_in = p.cache & 1, keep_out = p.cache & 2;   // L2-resident side of a blocked pass pair
 
     T re[E], im[E];
     // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = T(0); v.y = T(0);
-        if (valid) v = gin[bin2 + (int64_t)(j + r * TPX) * is2];
+        if (valid) v = keep_in ? *(gin + (int64_t)(j + r * TPX) * is2) : ld_stream(gin + (int64_t)(j + r * TPX) * is2);
         re[r] = swap_in ? v.y : v.x;
         im[r] = swap_in ? v.x : v.y;
     }
@@ -95,19 +159,22 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     }
     __syncthreads();
 
-    // ---- stage 2: radix R1, Ns = E
+    // ---- stage 2: radix R1, Ns = E.  Butterflies b = j + i*TPX; k = b % E.
     {
         constexpr int NB = N / R1;            // butterflies per transform
         constexpr int PER = E / R1;           // butterflies per thread
         constexpr int TSTEP = N / (E * R1);
+        cplx<T> w[R1];
+        // TPX % E == 0 for three-stage sizes: k = j % E for every butterfly of this thread
+        if (R2 > 1 || PER == 1) load_twiddles<R1, T>(tw, TSTEP * (j % E), w);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int b = j + i * TPX;
-            const int k = b % E;
+            if (R2 == 1 && PER > 1) load_twiddles<R1, T>(tw, TSTEP * (b % E), w);
 #pragma unroll
             for (int r = 0; r < R1; ++r) {
                 cplx<T> v = sm[sidx(b + r * NB)];
-                if (r > 0) v = cmul(v, ldg_c(&tw[TSTEP * r * k]));
+                if (r > 0) v = cmul(v, w[r]);
                 re[i * R1 + r] = v.x; im[i * R1 + r] = v.y;
             }
         }
@@ -144,34 +211,44 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
                     cplx<T> v;
                     v.x = swap_out ? im[i * R1 + r] : re[i * R1 + r];
                     v.y = swap_out ? re[i * R1 + r] : im[i * R1 + r];
-                    if (valid) gout[bout2 + (int64_t)(b + r * E) * os2] = v;
+                    if (valid) { if (keep_out) *(gout + (int64_t)(b + r * E) * os2) = v; else st_stream(gout + (int64_t)(b + r * E) * os2, v); }
                 }
             }
             return;
         }
     }
 
-    // ---- stage 3: radix R2, Ns = E * R1 (last: k = b, outputs at b + r * Ns)
+    // ---- stage 3: radix R2, Ns = E * R1 (last: k = b, outputs at b + r * Ns).
+    // twiddle W_N^(r b) with b = j + i*TPX:  W_N^(r j) * W_E^(r i)  (TPX = N / E)
     if (R2 > 1) {
         constexpr int NS = E * R1;
         constexpr int PER = E / R2;
+        constexpr int R2_ = R2 > 1 ? R2 : 2;
+        cplx<T> w[R2_];
+        load_twiddles<R2_, T>(tw, j, w);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int b = j + i * TPX;
-            T xr[R2 > 1 ? R2 : 2], xi[R2 > 1 ? R2 : 2];
+            T xr[R2_], xi[R2_];
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
                 cplx<T> v = sm[sidx(b + r * NS)];
-                if (r > 0) v = cmul(v, ldg_c(&tw[r * b]));
+                if (r > 0) {
+                    cplx<T> wr = w[r];
+                    if (i > 0) {
+                        wr = cmul(wr, unit_root<E, T>((r * i) % E));
+                    }
+                    v = cmul(v, wr);
+                }
                 xr[r] = v.x; xi[r] = v.y;
             }
-            Butterfly<(R2 > 1 ? R2 : 2), T>::run(xr, xi);
+            Butterfly<R2_, T>::run(xr, xi);
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
                 cplx<T> v;
                 v.x = swap_out ? xi[r] : xr[r];
                 v.y = swap_out ? xr[r] : xi[r];
-                if (valid) gout[bout2 + (int64_t)(b + r * NS) * os2] = v;
+                if (valid) { if (keep_out) *(gout + (int64_t)(b + r * NS) * os2) = v; else st_stream(gout + (int64_t)(b + r * NS) * os2, v); }
             }
         }
     }
@@ -186,17 +263,17 @@ struct FastEntry {
     const void *func;
 };
 
-template <typename T, int N, int E, int R1, int R2, int TPB, bool COL>
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
 void launch_one(const b2d_fft_pass &p, int swap_in, int swap_out, unsigned blocks, cudaStream_t st)
 {
-    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL>;
-    fast_kernel<T, N, E, R1, R2, TPB, COL><<<blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, swap_in, swap_out);
+    using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>;
+    fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR><<<blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, swap_in, swap_out);
 }
 
-#define B2_FAST_ENTRY(PREC, T, N, E, R1, R2, TPB, COL, CODE)                                        \
-    { PREC, N, COL, TPB, CODE, FastCfg<T, N, E, R1, R2, TPB, COL>::SMEM_BYTES,                      \
-      FastCfg<T, N, E, R1, R2, TPB, COL>::THREADS, &launch_one<T, N, E, R1, R2, TPB, COL>,          \
-      (const void *)&fast_kernel<T, N, E, R1, R2, TPB, COL> }
+#define B2_FAST_ENTRY(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE)                                        \
+    { PREC, N, COL, TPB, CODE, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::SMEM_BYTES,                      \
+      FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS, &launch_one<T, N, E, R1, R2, TPB, COL, FLAVOR>,          \
+      (const void *)&fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR> }
 
 const FastEntry *table(int *count);   // defined in fft_fast_table.cu
 

@@ -10,14 +10,14 @@ extern const int table_d_row_count, table_d_col_count, table_f_row_count, table_
 
 static int g_max_smem = 0;
 
-static const FastEntry *find(int prec, int n, int col, int tpb)
+static const FastEntry *find(int prec, int n, int col, int code)
 {
     const FastEntry *t;
     int cnt, i;
     if (prec == B2D_F64) { t = col ? table_d_col : table_d_row; cnt = col ? table_d_col_count : table_d_row_count; }
     else { t = col ? table_f_col : table_f_row; cnt = col ? table_f_col_count : table_f_row_count; }
     for (i = 0; i < cnt; ++i)
-        if (t[i].n == n && t[i].tpb == tpb) return &t[i];
+        if (t[i].n == n && t[i].code == code) return &t[i];
     return nullptr;
 }
 
@@ -41,13 +41,12 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
     if (p.load_col != p.store_col) return nullptr;
     const int col = p.kernel >= 1000;
     if (col != p.load_col) return nullptr;
-    const int tpb = p.kernel % 1000;
     if ((p.is & 1) || (p.os & 1)) return nullptr;
     for (int i = 0; i < B2D_MAX_BATCH_DIMS; ++i)
         if ((p.bis[i] & 1) || (p.bos[i] & 1)) return nullptr;
     if (col && (p.bis[0] != 2 || p.bos[0] != 2)) return nullptr;     // adjacent pencils
     if (!col && (p.is != 2 || p.os != 2)) return nullptr;            // contiguous transforms
-    const FastEntry *e = find(p.prec, p.n, col, tpb);
+    const FastEntry *e = find(p.prec, p.n, col, p.kernel);
     if (e && (int)e->smem > g_max_smem && g_max_smem) return nullptr;
     return e;
 }

@@ -89,6 +89,7 @@ typedef struct b2_plan {
     double est_flops_add, est_flops_mul, est_flops_fma;
     double cost;              /* measured ms (or estimate) */
     int is_nop;
+    size_t l2_block_bytes;    /* group size for L2-blocked pass pairs (0 = off) */
     int inplace;
     int destroys_input;
     /* host staging state (execute on host pointers) */

@@ -17,6 +17,10 @@
 
 double b2_timelimit = -1.0;
 
+/* working-set size for L2-blocked pass pairs (B200: 126 MB L2 over two dies);
+   FFTW3_B200_L2_BLOCK_MB overrides, 0 disables */
+#define B2_DEFAULT_L2_BLOCK_MB 0    /* measured on B200: per-group launches lose more to tails than L2 reuse wins */
+
 /* ------------------------------------------------------------------ helpers */
 typedef struct {           /* where a complex (or real) line lives */
     b2_ref re, im;
@@ -141,6 +145,7 @@ typedef struct {
     int pre_op, post_op;
     int n_in, n_out;          /* 0 = n */
     int64_t big_n, tw4_split; /* STORE_TWIDDLE4: enclosing size and lo-table length */
+    int cache;                /* L2 residency hints (b2d_fft_pass.cache) */
 } b2_ops;
 
 static void fill_geometry(b2d_fft_pass *f, int variant)
@@ -174,15 +179,17 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 }
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
-#define NFAST 6               /* specialised-kernel variants 12..17: tile width 1,2,4,8,16,32 */
+#define NFAST 12              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor
+                                 (12..17 uncapped registers, 18..23 capped for more resident CTAs) */
 
 static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
     if (variant >= NVARIANTS) {
-        int tpb = 1 << (variant - NVARIANTS);
-        int code = ((f->load_col || f->store_col) ? 1000 : 0) + tpb;
+        int tpb = 1 << ((variant - NVARIANTS) % 6);
+        int flavor = (variant - NVARIANTS) / 6;
+        int code = ((f->load_col || f->store_col) ? 1000 : 0) + 100 * flavor + tpb;
         if (variant >= NVARIANTS + NFAST) return -1;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
@@ -294,6 +301,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     f->prec = prec;
     f->n = (int)(bluestein_m ? bluestein_m : n);
     f->pre_op = ops.pre_op; f->post_op = ops.post_op;
+    f->cache = ops.cache;
     f->n_in = ops.n_in ? ops.n_in : (int)n;
     f->n_out = ops.n_out ? ops.n_out : (int)n;
     f->is = in.stride; f->os = out.stride;
@@ -351,7 +359,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
                             f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
                             (long long)f->bn[1], (long long)f->bn[2], v, trial.kernel ? "codelet" : "generic",
-                            trial.kernel ? trial.kernel % 1000 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
+                            trial.kernel ? trial.kernel % 100 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
                 }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
             }
@@ -670,7 +678,62 @@ static int plan_c2c(b2_plan *p)
         if (rc) return rc;
         return emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_OUT1, 0), &q->vecsz, 1);
     }
-    for (d = q->sz.rnk - 1; d >= 0; --d) {
+    d = q->sz.rnk - 1;
+    /* L2 blocking of the two innermost passes.  The pass over the last dim and
+       the pass over the next one only couple elements that share every other
+       index, so they can be run group by group over the outermost remaining
+       dim: with a group small enough to stay in the 126 MB L2, the second pass
+       reads what the first just wrote from L2 and the pair costs one HBM read
+       and one HBM write instead of two of each ("fused multi-pass": the role of
+       the reference's cache-oblivious rank-geq2 / buffered recursion,
+       dft/rank-geq2.c:42-52, dft/buffered.c:41-69, on a cache that is shared
+       by all SMs). */
+    if (q->sz.rnk >= 2 && p->l2_block_bytes > 0) {
+        int oi = -1, ovec = 0, i;
+        int64_t best = 0, per = 2 * (int64_t)real_size(q->prec), nout, G;
+        for (i = 0; i < q->sz.rnk - 2; ++i)
+            if (llabs(q->sz.d[i].os) > best) { best = llabs(q->sz.d[i].os); oi = i; ovec = 0; }
+        for (i = 0; i < q->vecsz.rnk; ++i)
+            if (llabs(q->vecsz.d[i].os) > best) { best = llabs(q->vecsz.d[i].os); oi = i; ovec = 1; }
+        if (oi >= 0) {
+            const b2_dim *od = ovec ? &q->vecsz.d[oi] : &q->sz.d[oi];
+            nout = od->n;
+            for (i = 0; i < q->sz.rnk; ++i) if (ovec || i != oi) per *= q->sz.d[i].n;
+            for (i = 0; i < q->vecsz.rnk; ++i) if (!ovec || i != oi) per *= q->vecsz.d[i].n;
+            if (!p->inplace) per *= 2;
+            G = (int64_t)p->l2_block_bytes / (per > 0 ? per : 1);
+            if (G >= 1 && G < nout && nout / G <= 4096) {
+                int64_t g0;
+                for (g0 = 0; g0 < nout; g0 += G) {
+                    int64_t cnt = (nout - g0 < G) ? nout - g0 : G;
+                    int pass;
+                    for (pass = 0; pass < 2; ++pass) {
+                        b2_problem qq = *q;
+                        b2_tensor batch;
+                        b2_view in, out;
+                        int dd = q->sz.rnk - 1 - pass;
+                        b2_dim *md = ovec ? &qq.vecsz.d[oi] : &qq.sz.d[oi];
+                        md->n = cnt;
+                        other_dims(&qq, dd, pass, &batch);
+                        out.re = mkref(BUF_OUT0, g0 * od->os); out.im = mkref(BUF_OUT1, g0 * od->os);
+                        out.stride = q->sz.d[dd].os;
+                        if (pass == 0) {
+                            in.re = mkref(BUF_IN0, g0 * od->is); in.im = mkref(BUF_IN1, g0 * od->is);
+                            in.stride = q->sz.d[dd].is;
+                        } else in = out;
+                        none.cache = pass ? 1 : 2;   /* first pass leaves its output in L2 for the second */
+                        rc = emit_fft1d(p, q->prec, q->sz.d[dd].n, in, out, &batch, none, 1,
+                                        pass ? "dft(in place, L2 group)" : "dft(L2 group)");
+                        none.cache = 0;
+                        if (rc) return rc;
+                    }
+                }
+                first = 0;
+                d = q->sz.rnk - 3;
+            }
+        }
+    }
+    for (; d >= 0; --d) {
         b2_tensor batch;
         b2_view in, out;
         other_dims(q, d, !first, &batch);
@@ -1036,6 +1099,12 @@ b2_plan *b2_mkplan(const b2_problem *prob)
     }
     p->inplace = (prob->in0 == prob->out0);
     if (prob->kind == B2_C2C && prob->in0 == prob->out1 && prob->in1 == prob->out0) p->inplace = 0;
+    {
+        const char *e = getenv("FFTW3_B200_L2_BLOCK_MB");
+        const char *ek = getenv("FFTW3_B200_L2_BLOCK_KB");      /* finer unit, for tests */
+        p->l2_block_bytes = (size_t)(e ? atol(e) : B2_DEFAULT_L2_BLOCK_MB) << 20;
+        if (ek) p->l2_block_bytes = (size_t)atol(ek) << 10;
+    }
     if (b2_tensor_count(&p->prob.vecsz) == 0) { p->is_nop = 1; return p; }
     if (p->inplace && prob->kind != B2_R2C && prob->kind != B2_C2R) {
         /* in-place needs identical input and output locations (dft/problem.c:95-99) */
@@ -1081,12 +1150,16 @@ void b2_plan_print(const b2_plan *p, FILE *f)
     fprintf(f, "(b200-plan");
     for (i = 0; i < p->nsteps; ++i) {
         const b2_step *s = &p->steps[i];
+        if (i >= 6 && i < p->nsteps - 3) {
+            if (i == 6) fprintf(f, "\n  ... %d more passes ...", p->nsteps - 9);
+            continue;
+        }
         if (s->kind == STEP_FFT) {
             const b2d_fft_pass *q = &s->u.fft;
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel) fprintf(f, "codelet-tile=%d", q->kernel % 1000);
+            if (q->kernel) fprintf(f, "codelet-tile=%d%s", q->kernel % 100, (q->kernel / 100) % 10 ? "r" : "");
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
                     q->bluestein ? " bluestein" : "");

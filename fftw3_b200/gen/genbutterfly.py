@@ -391,6 +391,14 @@ def main():
     for n in RADICES:
         src, _ = emit(n)
         parts.append(src)
+    # compile-time roots of unity W_E^m = exp(-2 pi i m / E), used by the specialised
+    # kernels to derive per-butterfly twiddles from one loaded base twiddle
+    for e in (4, 8, 16, 32):
+        cs = [root(m, e) for m in range(e)]
+        cases = "\n".join("    case %d: re = T(%s); im = T(%s); break;" % (m, repr(c[0]), repr(c[1]))
+                          for m, c in enumerate(cs))
+        parts.append("template <typename T>\n__host__ __device__ __forceinline__ void unit_root%d(int m, T &re, T &im)\n"
+                     "{\n    switch (m) {\n%s\n    default: re = T(1.0); im = T(0.0); break;\n    }\n}\n" % (e, cases))
     # dispatcher
     parts.append("template <int R, typename T> struct Butterfly;\n")
     for n in RADICES:

@@ -55,6 +55,8 @@ typedef struct b2d_fft_pass {
                                  1: consecutive lanes walk batch dim 0 (COL)         */
     int pre_op, post_op;
     int bluestein;            /* 1: forward stages, x aux1[k], inverse stages        */
+    int cache;                /* bit 0: input is expected in L2 (plain loads), bit 1: keep
+                                 the output in L2 (plain stores); else streaming hints  */
     int kernel;               /* 0: generic runtime-radix kernel; else code of a
                                  specialised kernel: tile width + 1000 for COL      */
     int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
