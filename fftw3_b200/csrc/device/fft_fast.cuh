@@ -134,10 +134,13 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     const int64_t b0 = c.tile0 * TPB + t;
     const bool valid = b0 < p.bn[0];
     const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
-    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2];
+    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
     // interleaved data: vector pointer at the lower of (re, im)
     const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re) + boff_in / 2;
-    cplx<T> *gout = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re) + boff_out / 2;
+    // peer scatter: batch dim 2 selects the destination buffer (a peer GPU's exchange
+    // buffer mapped over NVLink): the transpose is fused with its collective
+    cplx<T> *gout = (p.npeer ? reinterpret_cast<cplx<T> *>(p.peer_out[c.b2])
+                             : reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re)) + boff_out / 2;
     const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
     const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
     const bool keep_in = p.cache & 1, keep_out = p.cache & 2;   // L2-resident side of a blocked pass pair

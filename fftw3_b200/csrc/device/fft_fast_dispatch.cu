@@ -70,12 +70,16 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;
     const intptr_t din = (const char *)p.in_im - (const char *)p.in_re;
-    const intptr_t dout = (char *)p.out_im - (char *)p.out_re;
+    const intptr_t dout = p.npeer ? (intptr_t)rs : (char *)p.out_im - (char *)p.out_re;
     // interleaved (im = re +- 1 scalar) and vector-aligned, else the generic kernel handles it
     if ((din != (intptr_t)rs && din != -(intptr_t)rs) || (dout != (intptr_t)rs && dout != -(intptr_t)rs)) return 1;
     const int swap_in = din < 0, swap_out = dout < 0;
     const uintptr_t lo_in = (uintptr_t)(swap_in ? p.in_im : p.in_re);
-    const uintptr_t lo_out = (uintptr_t)(swap_out ? p.out_im : p.out_re);
+    uintptr_t lo_out = (uintptr_t)(swap_out ? p.out_im : p.out_re);
+    if (p.npeer) {
+        lo_out = 0;
+        for (int i = 0; i < p.npeer; ++i) lo_out |= (uintptr_t)p.peer_out[i];
+    }
     if ((lo_in % (2 * rs)) || (lo_out % (2 * rs))) return 1;
     const int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
     const int64_t blocks = tiles0 * p.bn[1] * p.bn[2];

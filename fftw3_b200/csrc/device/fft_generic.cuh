@@ -101,10 +101,14 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
 
 // --------------------------------------------------------------- store element
 template <typename T>
-B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int k, cplx<T> z)
+B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t peer, int k, cplx<T> z)
 {
     T *re = (T *)p.out_re;
     T *im = (T *)p.out_im;
+    if (p.npeer) {            // batch dim 2 selects the destination buffer (peer GPU), interleaved
+        re = (T *)p.peer_out[peer];
+        im = re + 1;
+    }
     const int op = p.post_op;
     if ((op & B2D_STORE_TRUNC) && k >= p.n_out) return;
     if (op & B2D_STORE_TWIDDLE4) {
@@ -161,7 +165,7 @@ B2_HD void phase_offsets(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx 
         int64_t b0 = c.tile0 * p.tpb + tid;
         s.b0[tid] = (b0 < p.bn[0]) ? b0 : -1;
         s.boff_in[tid] = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
-        s.boff_out[tid] = b0 * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2];
+        s.boff_out[tid] = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
     }
 }
 
@@ -254,7 +258,8 @@ B2_HD void phase_pointwise(const b2d_fft_pass &p, cplx<T> *buf, int pitch, int t
 
 // final phase: shared -> global
 template <typename T>
-B2_HD void phase_store(const b2d_fft_pass &p, const Smem<T> &s, const cplx<T> *src, int tid, int nthreads)
+B2_HD void phase_store(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx &c, const cplx<T> *src, int tid,
+                       int nthreads)
 {
     const int n = p.n, tpb = p.tpb;
     const int total = n * tpb;
@@ -265,7 +270,7 @@ B2_HD void phase_store(const b2d_fft_pass &p, const Smem<T> &s, const cplx<T> *s
         if (s.b0[t] < 0) continue;
         cplx<T> z = src[(size_t)t * s.pitch + padk(k)];
         if (p.bluestein) z.y = -z.y;
-        store_elem<T>(p, s.boff_out[t], s.b0[t], k, z);
+        store_elem<T>(p, s.boff_out[t], s.b0[t], c.b2, k, z);
     }
 }
 
@@ -296,7 +301,7 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
             __syncthreads();
         }
     }
-    phase_store<T>(p, s, src, tid, nthreads);
+    phase_store<T>(p, s, c, src, tid, nthreads);
 }
 #endif
 

@@ -195,6 +195,11 @@ B2_HD void copy_elem(const b2d_copy &c, int64_t idx)
     int64_t oo = i0 * c.os[0] + i1 * c.os[1] + i2 * c.os[2] + i3 * c.os[3];
     const T *in = (const T *)c.in;
     T *out = (T *)c.out;
+    if (c.npeer) { in = (const T *)c.peer_in[i3]; io -= i3 * c.is[3]; }
+    if (c.elem_reals == 2 && (((uintptr_t)(in + io) | (uintptr_t)(out + oo)) % (2 * sizeof(T))) == 0) {
+        *reinterpret_cast<cplx<T> *>(out + oo) = *reinterpret_cast<const cplx<T> *>(in + io);
+        return;
+    }
     out[oo] = in[io];
     if (c.elem_reals == 2) out[oo + 1] = in[io + 1];
 }

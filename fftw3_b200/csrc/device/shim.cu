@@ -123,6 +123,27 @@ int b2d_sync(void)
 void b2d_set_stream(void *s) { g_stream = (cudaStream_t)s; }
 void *b2d_get_stream(void) { return (void *)g_stream; }
 
+int b2d_ipc_export(void *devptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, devptr);
+    if (e != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle, &h, 64);
+    return 0;
+}
+void *b2d_ipc_import(const unsigned char handle[64])
+{
+    if (ensure_init()) return nullptr;
+    cudaIpcMemHandle_t h;
+    void *p = nullptr;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fail(e, "cudaIpcOpenMemHandle"); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void b2d_ipc_close(void *devptr) { if (devptr) cudaIpcCloseMemHandle(devptr); }
+
 int b2d_timer_start(void)
 {
     if (ensure_init()) return -1;

@@ -673,7 +673,16 @@ static int plan_c2c(b2_plan *p)
     memset(&none, 0, sizeof none);
     if (q->sz.rnk == 0) {
         /* rank-0: copy (rdft/rank0.c); re and im planes separately */
+        int64_t di = (char *)q->in1 - (char *)q->in0, dout = (char *)q->out1 - (char *)q->out0;
+        int64_t rs = (int64_t)real_size(q->prec);
+        int even = 1, i;
         if (p->inplace) return 0;
+        for (i = 0; i < q->vecsz.rnk; ++i) if ((q->vecsz.d[i].is | q->vecsz.d[i].os) & 1) even = 0;
+        if (even && di == dout && (di == rs || di == -rs)) {
+            /* interleaved on both sides: move whole complex numbers (128-bit for double) */
+            int lo_in = di > 0 ? BUF_IN0 : BUF_IN1, lo_out = di > 0 ? BUF_OUT0 : BUF_OUT1;
+            return emit_copy(p, q->prec, mkref(lo_in, 0), mkref(lo_out, 0), &q->vecsz, 2);
+        }
         rc = emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_OUT0, 0), &q->vecsz, 1);
         if (rc) return rc;
         return emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_OUT1, 0), &q->vecsz, 1);

@@ -1,0 +1,327 @@
+"""fftw3_b200.dist -- slab-decomposed 3-D transforms over several GPUs, one
+process per GPU (the fftw_mpi_plan_dft_3d equivalent; see
+include/fftw3_b200_dist.h for the C-ABI and the reference files it mirrors).
+
+This module is plumbing only: it allocates the exchange buffers, trades CUDA-IPC
+handles or runs the all-to-all through ``torch.distributed``, and puts the
+barriers between the stages.  All arithmetic and all data movement inside a GPU
+(and, on the peer path, between GPUs) is done by the library's CUDA kernels.
+
+Exchange paths
+  * ``peer``        the last local FFT pass stores straight into the peers'
+                    exchange buffers (CUDA IPC mappings over NVLink/NVSwitch):
+                    transpose fused with its collective; ranks only meet at
+                    barriers.  GPU only.
+  * ``collective``  the pass writes a local send buffer and an all-to-all moves
+                    it (NCCL on GPUs; send/recv pairs on the gloo backend used by
+                    the CPU unit tests).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import binding as B
+
+FFTW_MPI_TRANSPOSED_OUT = 1 << 30          # same bit as mpi/fftw3-mpi.h:214
+
+
+def _declare(lib):
+    L = lib.lib
+    if getattr(L, "_dist_declared", False):
+        return
+    P, I = C.c_void_p, C.c_int
+    SP = C.POINTER(C.c_ssize_t)
+    L.fftw_b200_dist_local_size_3d.restype = C.c_ssize_t
+    L.fftw_b200_dist_local_size_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, SP, SP, SP, SP]
+    L.fftw_b200_dist_plan_dft_3d.restype = P
+    L.fftw_b200_dist_plan_dft_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
+    L.fftw_b200_dist_num_stages.argtypes = [P]
+    L.fftw_b200_dist_execute_stage.argtypes = [P, I]
+    L.fftw_b200_dist_destroy_plan.argtypes = [P]
+    L.fftw_b200_device_malloc.restype = P
+    L.fftw_b200_device_malloc.argtypes = [C.c_size_t]
+    L.fftw_b200_device_free.argtypes = [P]
+    L.fftw_b200_ipc_export.argtypes = [P, C.c_char_p]
+    L.fftw_b200_ipc_import.restype = P
+    L.fftw_b200_ipc_import.argtypes = [C.c_char_p]
+    L.fftw_b200_ipc_close.argtypes = [P]
+    L._dist_declared = True
+
+
+def local_size_3d(lib, n0, n1, n2, rank, nranks):
+    """(alloc_elements, local_n0, local_0_start, local_n1, local_1_start)"""
+    _declare(lib)
+    v = [C.c_ssize_t() for _ in range(4)]
+    alloc = lib.lib.fftw_b200_dist_local_size_3d(n0, n1, n2, rank, nranks, *[C.byref(x) for x in v])
+    return (int(alloc),) + tuple(int(x.value) for x in v)
+
+
+def _blk(n, p):
+    return (n + p - 1) // p
+
+
+def _share(n, p, r):
+    b = _blk(n, p)
+    return max(0, min(b, n - b * r))
+
+
+class SlabPlan3D:
+    """Distributed c2c double transform of an n0 x n1 x n2 array.
+
+    ``local`` is this rank's slab: a complex128 tensor (CUDA, or CPU for the
+    unit tests with the emulated device layer) of at least ``alloc`` elements
+    whose first local_n0*n1*n2 entries are [local_n0][n1][n2].
+    """
+
+    def __init__(self, lib, n0, n1, n2, local, group=None, sign=B.FFTW_FORWARD, flags=B.FFTW_MEASURE,
+                 transposed_out=False, exchange="auto"):
+        _declare(lib)
+        self.lib, self.L = lib, lib.lib
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n = (n0, n1, n2)
+        self.local = local
+        self.transposed_out = transposed_out
+        self.cuda = local.is_cuda
+        if exchange == "auto":
+            exchange = "peer" if (self.cuda and self.P > 1) else "collective"
+        self.exchange = exchange
+        alloc, self.ln0, self.s0, self.ln1, self.s1 = local_size_3d(lib, n0, n1, n2, self.rank, self.P)
+        self.alloc = alloc
+        assert local.numel() >= alloc and local.dtype == torch.complex128 and local.is_contiguous()
+        P, r = self.P, self.rank
+        b0, b1 = _blk(n0, P), _blk(n1, P)
+        self._owned = []
+        self._opened = []
+        # chunk (src s -> dst d) = [ln0(s)][ln1(d)][n2]
+        if exchange == "peer":
+            self.zptr = self._dev_alloc(alloc * 16)
+            handles = [None] * P
+            h = C.create_string_buffer(64)
+            assert self.L.fftw_b200_ipc_export(self.zptr, h) == 0, "cudaIpcGetMemHandle failed"
+            dist.all_gather_object(handles, bytes(h.raw), group=group)
+            self.peer = []
+            for s in range(P):
+                if s == r:
+                    self.peer.append(self.zptr)
+                else:
+                    ptr = self.L.fftw_b200_ipc_import(handles[s])
+                    assert ptr, "cudaIpcOpenMemHandle failed for rank %d" % s
+                    self._opened.append(ptr)
+                    self.peer.append(ptr)
+            # my rows start at r*b0 inside every peer's [n0][ln1(d)][n2]
+            push = [self.peer[d] + 16 * (r * b0) * _share(n1, P, d) * n2 for d in range(P)]
+            pull = [self.peer[s] + 16 * (r * b0) * _share(n1, P, s) * n2 for s in range(P)]
+            zbuf = self.zptr
+        else:
+            mk = (lambda: torch.empty(alloc, dtype=torch.complex128, device=local.device))
+            self.send, self.recv = mk(), mk()
+            self.send_counts = [self.ln0 * _share(n1, P, d) * n2 for d in range(P)]
+            self.recv_counts = [_share(n0, P, s) * self.ln1 * n2 for s in range(P)]
+            so = np.concatenate([[0], np.cumsum(self.send_counts)])[:-1]
+            push = [self.send.data_ptr() + 16 * int(so[d]) for d in range(P)]
+            zbuf = self.recv.data_ptr()
+            if not transposed_out:
+                self.recv2 = mk()
+                # second exchange: I send rows of zbuf = [n0][ln1][n2] for dest d: contiguous
+                self.send2_counts = [_share(n0, P, d) * self.ln1 * n2 for d in range(P)]
+                self.recv2_counts = [self.ln0 * _share(n1, P, s) * n2 for s in range(P)]
+                ro = np.concatenate([[0], np.cumsum(self.recv2_counts)])[:-1]
+                pull = [self.recv2.data_ptr() + 16 * int(ro[s]) for s in range(P)]
+        VP = C.c_void_p * P
+        push_arr = VP(*push)
+        pull_arr = None if transposed_out else VP(*pull)
+        self.plan = self.L.fftw_b200_dist_plan_dft_3d(n0, n1, n2, r, P, local.data_ptr(), zbuf, push_arr, pull_arr,
+                                                     int(sign), int(flags))
+        assert self.plan, "fftw_b200_dist_plan_dft_3d returned NULL"
+        self.nstages = self.L.fftw_b200_dist_num_stages(self.plan)
+        self._token = torch.zeros(1, device=local.device)
+
+    # ---- helpers ---------------------------------------------------------
+    def _dev_alloc(self, nbytes):
+        p = self.L.fftw_b200_device_malloc(nbytes)
+        assert p, "device allocation of %d bytes failed" % nbytes
+        self._owned.append(p)
+        return p
+
+    def _barrier(self):
+        if self.P > 1:
+            # stream-ordered on NCCL: every rank's kernels queued before it are complete when it ends
+            dist.all_reduce(self._token, group=self.group)
+
+    def _alltoall(self, out, out_counts, inp, in_counts):
+        if self.P == 1:
+            out[:in_counts[0]].copy_(inp[:in_counts[0]])
+            return
+        n_out, n_in = sum(out_counts), sum(in_counts)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all_single(torch.view_as_real(out[:n_out]), torch.view_as_real(inp[:n_in]),
+                                   [2 * c // 2 for c in out_counts], [2 * c // 2 for c in in_counts], group=self.group)
+            return
+        # gloo has no all-to-all: pairwise send/recv (mpi/transpose-pairwise.c:49-99 in spirit)
+        oo = np.concatenate([[0], np.cumsum(out_counts)])
+        io = np.concatenate([[0], np.cumsum(in_counts)])
+        ops = []
+        bufs = []
+        for k in range(self.P):
+            d = (self.rank + k) % self.P
+            s = (self.rank - k) % self.P
+            if d == self.rank:
+                out[oo[s]:oo[s + 1]].copy_(inp[io[d]:io[d + 1]])
+                continue
+            sb = torch.view_as_real(inp[io[d]:io[d + 1]]).contiguous()
+            rb = torch.empty((out_counts[s], 2), dtype=torch.float64)
+            bufs.append((s, rb))
+            if in_counts[d]:
+                ops.append(dist.P2POp(dist.isend, sb, d, group=self.group))
+            if out_counts[s]:
+                ops.append(dist.P2POp(dist.irecv, rb, s, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for s, rb in bufs:
+            out[oo[s]:oo[s + 1]].copy_(torch.view_as_complex(rb))
+
+    # ---- execution -------------------------------------------------------
+    def execute(self):
+        L = self.L
+        if self.exchange == "peer":
+            self._barrier()                         # peers are done reading their zbuf from the last call
+            L.fftw_b200_dist_execute_stage(self.plan, 0)
+            self._barrier()                         # all blocks have landed
+            L.fftw_b200_dist_execute_stage(self.plan, 1)
+            if self.nstages == 3:
+                self._barrier()                     # every rank's dim-0 transforms are complete
+                L.fftw_b200_dist_execute_stage(self.plan, 2)
+        else:
+            L.fftw_b200_dist_execute_stage(self.plan, 0)
+            self._alltoall(self.recv, self.recv_counts, self.send, self.send_counts)
+            L.fftw_b200_dist_execute_stage(self.plan, 1)
+            if self.nstages == 3:
+                self._alltoall(self.recv2, self.recv2_counts, self.recv, self.send2_counts)
+                L.fftw_b200_dist_execute_stage(self.plan, 2)
+
+    def destroy(self):
+        if self.plan:
+            self.L.fftw_b200_dist_destroy_plan(self.plan)
+            self.plan = None
+        if self.P > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.L.fftw_b200_ipc_close(p)
+        for p in self._owned:
+            self.L.fftw_b200_device_free(p)
+        self._opened, self._owned = [], []
+
+
+# --------------------------------------------------------------------------
+# bench.py leg for N > 1 (one rank per GPU, launched by torchrun)
+# --------------------------------------------------------------------------
+def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run):
+    import json
+    import os
+    import time
+
+    dev = torch.device("cuda", local_rank)
+    _declare(lib)
+    alloc, ln0, s0, ln1, s1 = local_size_3d(lib, n, n, n, rank, world)
+    local = torch.empty(alloc, dtype=torch.complex128, device=dev)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    lr = torch.view_as_real(local)
+    lr.copy_(torch.rand(lr.shape, dtype=torch.float64, device=dev, generator=g) - 0.5)
+    flags = B.FFTW_ESTIMATE if args.estimate else B.FFTW_MEASURE
+    exchange = os.environ.get("FFTW3_B200_EXCHANGE", "peer")
+    t0 = time.perf_counter()
+    plan = SlabPlan3D(lib, n, n, n, local, flags=flags, transposed_out=False, exchange=exchange)
+    plan_s = time.perf_counter() - t0
+    lib.lib.fftw_b200_set_async(1)
+
+    def timed(pl, steps, warmup):
+        for _ in range(warmup):
+            pl.execute()
+            lr.mul_(1.0 / n ** 1.5)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            pl.execute()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)          # slowest rank defines the step
+        return float(ms.item()), lib.launch_count() - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(plan, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # the same transform with FFTW_MPI_TRANSPOSED_OUT semantics (one exchange instead of two)
+    plan_t = SlabPlan3D(lib, n, n, n, local, flags=flags, transposed_out=True, exchange=exchange)
+    ms_t, _ = timed(plan_t, max(2, args.steps // 2), 2)
+
+    # e2e: host slabs, H2D + transform + D2H every step, through the public call
+    e2e = None
+    if not args.no_e2e:
+        nel = ln0 * n * n
+        host = torch.empty(max(nel, 1), dtype=torch.complex128).pin_memory()
+        host.fill_(0.25)
+        steps = max(1, min(args.steps, 2))
+        for it in range(steps + 1):
+            if it == 1:
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+            local[:nel].copy_(host[:nel], non_blocking=True)
+            plan.execute()
+            host[:nel].copy_(local[:nel], non_blocking=True)
+            torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": flops_c2c((n, n, n)) / float(dt.item()) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": 16 * nel * world, "d2h_bytes_per_step": 16 * nel * world,
+               "ms_per_step": float(dt.item()) * 1e3, "steps": steps,
+               "api": "fftw3_b200.dist.SlabPlan3D.execute on pinned host slabs (one per rank)"}
+    lib.lib.fftw_b200_set_async(0)
+    plan.destroy()
+    plan_t.destroy()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                            "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    slab_bytes = 16 * ln0 * n * n
+    passes = 4                                  # Y, X(+scatter), Z, gather
+    achieved = passes * 2 * slab_bytes / (ms * 1e-3) / 1e9
+    nv_bytes = 2 * slab_bytes * (world - 1) / world      # two exchanges, sent per GPU
+    line = {
+        "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": flops_c2c((n, n, n)) / (ms * 1e-3) / 1e9,
+        "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 c2c double in place, forward, slab-decomposed over %d GPUs, natural-order "
+                               "output (two exchanges)" % (n, world),
+                   "exchange": exchange, "l2": "slabs are larger than L2, no flush needed",
+                   "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
+                   "transposed_out_ms_per_step": ms_t,
+                   "transposed_out_gflops": flops_c2c((n, n, n)) / (ms_t * 1e-3) / 1e9},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "passes": passes, "per": "GPU",
+                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback (of fallback)",
+                     "nvlink": {"sent_bytes_per_gpu_per_step": nv_bytes,
+                                "if_serialised_gbs": nv_bytes / (ms * 1e-3) / 1e9, "peak_gbs": 770.0}},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+    }
+    print(json.dumps(line))

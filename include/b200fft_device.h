@@ -20,6 +20,7 @@ extern "C" {
 
 #define B2D_MAX_STAGES 12
 #define B2D_MAX_BATCH_DIMS 3
+#define B2D_MAX_PEERS 16
 
 enum { B2D_F64 = 0, B2D_F32 = 1 };
 
@@ -70,6 +71,11 @@ typedef struct b2d_fft_pass {
     int64_t aux_split;        /* TWIDDLE4: lo-table length L (e = hi*L + lo)          */
     int64_t big_n;            /* TWIDDLE4: N of the enclosing transform               */
     double scale;
+    /* peer scatter (multi-GPU exchange fused into the pass): when npeer > 0 batch
+       dim 2 does not stride the output but selects peer_out[b2], an interleaved
+       complex buffer that may live on another GPU (CUDA IPC / NVLink peer mapping) */
+    int npeer;
+    void *peer_out[B2D_MAX_PEERS];
 } b2d_fft_pass;
 
 /* strided N-d copy / rank-0 transform (kernel/cpy2d.c, rdft/rank0.c analogue);
@@ -81,6 +87,9 @@ typedef struct b2d_copy {
     int64_t n[4], is[4], os[4];     /* dim 0 fastest                                */
     const void *in;
     void *out;
+    /* peer gather: when npeer > 0 dim 3 selects the SOURCE buffer peer_in[i3] */
+    int npeer;
+    const void *peer_in[B2D_MAX_PEERS];
 } b2d_copy;
 
 /* r2c / c2r even-length split (rdft/ct-hc2c-direct.c:45-60 analogue) and r2r
@@ -124,6 +133,11 @@ int  b2d_sync(void);
 void b2d_set_stream(void *cuda_stream);  /* NULL = legacy default stream              */
 void *b2d_get_stream(void);
 size_t b2d_max_smem_per_block(void);
+
+/* CUDA IPC: share a b2d_malloc'ed buffer with the other single-GPU processes of a job */
+int  b2d_ipc_export(void *devptr, unsigned char handle[64]);
+void *b2d_ipc_import(const unsigned char handle[64]);
+void b2d_ipc_close(void *devptr);
 
 /* timing on the launch stream (planner measurements) */
 int  b2d_timer_start(void);

@@ -1,0 +1,70 @@
+/* fftw3_b200_dist.h -- slab-decomposed multi-GPU transforms, one process per GPU.
+ *
+ * This is the B200 counterpart of the reference's MPI interface
+ * (mpi/fftw3-mpi.h:58-215): the data distribution, the local sizes and the
+ * TRANSPOSED_OUT option are the same; the communicator is replaced by
+ * (rank, nranks) plus plain device pointers, because the exchange runs over
+ * NVLink either as direct peer stores/loads into CUDA-IPC-mapped buffers or as an
+ * NCCL all-to-all issued by the caller between stages.
+ *
+ *   reference                                  here
+ *   fftw_mpi_local_size_3d_transposed   ->     fftw_b200_dist_local_size_3d      (mpi/api.c:248-352)
+ *   fftw_mpi_plan_dft_3d                ->     fftw_b200_dist_plan_dft_3d        (mpi/api.c:560-648,
+ *                                               mpi/dft-rank-geq2-transposed.c:47-70,113-214)
+ *   fftw_execute (of an MPI plan)       ->     fftw_b200_dist_execute_stage x N with a barrier / all-to-all
+ *                                               between stages (mpi/transpose-alltoall.c:49-100)
+ *
+ * Distribution (mpi/block.c:37-50): block = ceil(n / nranks); rank r owns the
+ * index range [r*block, min(n, (r+1)*block)) of the distributed dimension --
+ * dimension 0 for the input, dimension 1 for the transposed intermediate.
+ */
+#ifndef FFTW3_B200_DIST_H
+#define FFTW3_B200_DIST_H
+
+#include <stddef.h>
+#include "fftw3.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fftw_b200_dist_plan_s *fftw_b200_dist_plan;
+
+/* Elements (complex) each rank must allocate for its local array and for each
+ * exchange buffer; also returns the rank's share of dim 0 and of dim 1. */
+ptrdiff_t fftw_b200_dist_local_size_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                       ptrdiff_t *local_n0, ptrdiff_t *local_0_start,
+                                       ptrdiff_t *local_n1, ptrdiff_t *local_1_start);
+
+/* Plan a forward/backward c2c double transform of an n0 x n1 x n2 array.
+ *   local         this rank's slab  [local_n0][n1][n2], transformed in place
+ *   zbuf          this rank's exchange buffer, receives [n0][local_n1][n2]
+ *   push_targets  nranks pointers: where the block destined to rank d must be
+ *                 written -- the peer's zbuf (+ this rank's row offset) for the
+ *                 direct NVLink path, or a slice of a local send buffer when the
+ *                 caller runs an all-to-all between the stages
+ *   pull_sources  nranks pointers to the blocks coming back from rank s for the
+ *                 natural-order output, or NULL for FFTW_MPI_TRANSPOSED_OUT
+ *                 semantics (result left as [local_n1][n0][n2] in `local`)
+ * Stages: 0 = local 2-D transforms fused with the scatter of the exchange,
+ *         1 = transforms along dim 0, 2 = gather back (natural order only).
+ * The caller synchronises the ranks between stages. */
+fftw_b200_dist_plan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                               fftw_complex *local, fftw_complex *zbuf,
+                                               void *const *push_targets, void *const *pull_sources,
+                                               int sign, unsigned flags);
+int  fftw_b200_dist_num_stages(const fftw_b200_dist_plan p);
+void fftw_b200_dist_execute_stage(const fftw_b200_dist_plan p, int stage);
+void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);
+
+/* device memory that can be shared with the other ranks of the job (CUDA IPC) */
+void *fftw_b200_device_malloc(size_t bytes);
+void  fftw_b200_device_free(void *p);
+int   fftw_b200_ipc_export(void *devptr, unsigned char handle[64]);
+void *fftw_b200_ipc_import(const unsigned char handle[64]);
+void  fftw_b200_ipc_close(void *devptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -52,7 +52,7 @@ static void run_fft_pass(const b2d_fft_pass &p)
             if (p.bluestein && rep == 0)
                 for (int t = 0; t < nthreads; ++t) phase_pointwise<T>(p, src, s.pitch, t, nthreads);
         }
-        for (int t = 0; t < nthreads; ++t) phase_store<T>(p, s, src, t, nthreads);
+        for (int t = 0; t < nthreads; ++t) phase_store<T>(p, s, c, src, t, nthreads);
     }
 }
 
@@ -94,6 +94,9 @@ int b2d_memset(void *d, int b, size_t n) { memset(d, b, n); return 0; }
 int b2d_sync(void) { return 0; }
 void b2d_set_stream(void *) {}
 void *b2d_get_stream(void) { return NULL; }
+int b2d_ipc_export(void *, unsigned char *) { return -1; }     /* no IPC in the unit-test double */
+void *b2d_ipc_import(const unsigned char *) { return NULL; }
+void b2d_ipc_close(void *) {}
 int b2d_timer_start(void) { g_t0 = std::chrono::steady_clock::now(); return 0; }
 int b2d_timer_stop(float *ms)
 {

@@ -175,3 +175,30 @@ def test_reference_accuracy_metric(gpu_lib):
         assert r.returncode == 0, r.stderr
         vals = [float(v) for v in r.stdout.split()]
         assert vals[1] < bound and vals[4] < bound, (prob, vals)
+
+
+def test_dist_single_rank_gpu(gpu_lib):
+    """The slab plan degenerates to a local 3-D transform on one GPU (P = 1):
+    checks the stage composition (Y, X, Z, gather) on the real kernels."""
+    import torch
+    import torch.distributed as dist
+    from fftw3_b200 import dist as D
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29611", rank=0, world_size=1)
+    rng = np.random.default_rng(11)
+    shape = (32, 64, 128)
+    x = F.rand_complex(rng, shape, "d")
+    for transposed in (False, True):
+        local = torch.from_numpy(x.reshape(-1).copy()).cuda()
+        pl = D.SlabPlan3D(gpu_lib, *shape, local, flags=B.FFTW_ESTIMATE, transposed_out=transposed,
+                          exchange="collective")
+        pl.execute()
+        torch.cuda.synchronize()
+        pl.destroy()
+        got = local.cpu().numpy()
+        ref = O.dft(x)
+        if transposed:
+            got = got.reshape(shape[1], shape[0], shape[2]).transpose(1, 0, 2)
+        else:
+            got = got.reshape(shape)
+        assert O.rel_l2(got, ref) <= F.tol_for("d", shape)
