@@ -202,3 +202,13 @@ def test_dist_single_rank_gpu(gpu_lib):
         else:
             got = got.reshape(shape)
         assert O.rel_l2(got, ref) <= F.tol_for("d", shape)
+
+
+import goldencheck as G  # noqa: E402
+
+
+@pytest.mark.parametrize("name,x,want", G.cases(), ids=[c[0] for c in G.cases()])
+def test_reference_golden_vectors(gpu_lib, name, x, want):
+    """committed outputs of the reference's own code (tests/golden/make_golden.py)"""
+    got = G.via_lib(gpu_lib, name, x)
+    assert O.rel_l2(got, want) < 3e-15
