@@ -70,7 +70,7 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;
     const intptr_t din = (const char *)p.in_im - (const char *)p.in_re;
-    const intptr_t dout = p.npeer ? (intptr_t)rs : (char *)p.out_im - (char *)p.out_re;
+    const intptr_t dout = (char *)p.out_im - (char *)p.out_re;   /* also tells the peer path whether to swap */
     // interleaved (im = re +- 1 scalar) and vector-aligned, else the generic kernel handles it
     if ((din != (intptr_t)rs && din != -(intptr_t)rs) || (dout != (intptr_t)rs && dout != -(intptr_t)rs)) return 1;
     const int swap_in = din < 0, swap_out = dout < 0;

@@ -106,8 +106,9 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
     T *re = (T *)p.out_re;
     T *im = (T *)p.out_im;
     if (p.npeer) {            // batch dim 2 selects the destination buffer (peer GPU), interleaved
-        re = (T *)p.peer_out[peer];
-        im = re + 1;
+        T *base = (T *)p.peer_out[peer];
+        if ((const char *)p.out_im < (const char *)p.out_re) { im = base; re = base + 1; }   // backward: swapped
+        else { re = base; im = base + 1; }
     }
     const int op = p.post_op;
     if ((op & B2D_STORE_TRUNC) && k >= p.n_out) return;

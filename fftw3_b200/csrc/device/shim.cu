@@ -123,6 +123,27 @@ int b2d_sync(void)
 void b2d_set_stream(void *s) { g_stream = (cudaStream_t)s; }
 void *b2d_get_stream(void) { return (void *)g_stream; }
 
+void *b2d_aux_stream(int idx)
+{
+    static cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (ensure_init() || idx < 0 || idx >= 4) return nullptr;
+    if (!aux[idx]) {
+        if (cudaStreamCreateWithFlags(&aux[idx], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    }
+    return (void *)aux[idx];
+}
+
+int b2d_stream_wait_stream(void *waiter, void *signaler)
+{
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return fail(e, "event create");
+    e = cudaEventRecord(ev, (cudaStream_t)signaler);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)waiter, ev, 0);
+    cudaEventDestroy(ev);                  /* released once the recorded work completes */
+    return e == cudaSuccess ? 0 : fail(e, "stream wait");
+}
+
 int b2d_ipc_export(void *devptr, unsigned char handle[64])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -7,15 +7,21 @@
  *   back (mpi/dft-rank-geq2.c:40-59 via dft-rank1-bigvec.c:45-65).
  * What is different: the reference's transpose = local transpose + MPI_Alltoall
  * + local transpose (mpi/transpose-alltoall.c:49-100).  Here both local
- * transposes are folded into FFT passes:
+ * transposes are folded into FFT passes and the exchange into their stores:
  *   stage 0  Y: FFT along n1, in place (strided pass)
  *            X: FFT along n2 (contiguous rows), stored straight into the block
  *               layout of the exchange -- [dest][i0][k1'][k2] -- i.e. into the
- *               peers' buffers over NVLink, or into a local send buffer
+ *               peers' buffers over NVLink, or into a local send buffer.
+ *               The slab is cut into chunks of planes: X of chunk c (NVLink
+ *               bound) runs on a side stream while Y of chunk c+1 (HBM bound)
+ *               runs on the main stream.
  *   stage 1  Z: FFT along n0 reading the received blocks, which already form
  *               [n0][local_n1][n2]; written in place (natural order follows) or
  *               as [local_n1][n0][n2] into `local` (TRANSPOSED_OUT)
- *   stage 2     gather the blocks back into [local_n0][n1][n2]
+ *   stage 2     gather the blocks back into [local_n0][n1][n2] (peer loads).
+ *               Stages 1 and 2 are cut into chunks of columns so that the
+ *               gather of chunk c overlaps Z of chunk c+1; the caller puts a
+ *               barrier between Z_c and gather_c.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -25,10 +31,12 @@ typedef double C[2];
 
 struct fftw_b200_dist_plan_s {
     int nranks, rank, nstages;
-    b2_plan *y;              /* stage 0 */
-    b2_plan **x;             /* stage 0, one per destination */
-    b2_plan *z;              /* stage 1 */
-    b2_plan **g;             /* stage 2, one per source */
+    int c0, c1;              /* chunks of stage 0 (planes) and of stages 1/2 (columns) */
+    int x_fused[64];         /* per chunk: one X launch scatters to every destination */
+    b2_plan **y;             /* [c0] */
+    b2_plan **x;             /* [c0] fused or [c0 * nranks] */
+    b2_plan **z;             /* [c1] */
+    b2_plan **g;             /* [c1 * nranks] */
 };
 typedef struct fftw_b200_dist_plan_s *dplan;
 
@@ -64,18 +72,33 @@ static void dim(b2_tensor *t, int64_t n, int64_t is, int64_t os)
     t->d[t->rnk].n = n; t->d[t->rnk].is = is; t->d[t->rnk].os = os; t->rnk++;
 }
 
+static void init_problem(b2_problem *q, unsigned flags)
+{
+    memset(q, 0, sizeof *q);
+    q->prec = B2D_F64; q->kind = B2_C2C; q->flags = flags;
+    b2_tensor_init(&q->sz, 0); b2_tensor_init(&q->vecsz, 0);
+}
+
 void fftw_b200_dist_destroy_plan(dplan p)
 {
     int i;
     if (!p) return;
-    b2_plan_destroy(p->y);
-    b2_plan_destroy(p->z);
-    for (i = 0; i < p->nranks; ++i) {
-        if (p->x) b2_plan_destroy(p->x[i]);
-        if (p->g) b2_plan_destroy(p->g[i]);
-    }
-    free(p->x); free(p->g);
+    for (i = 0; p->y && i < p->c0; ++i) b2_plan_destroy(p->y[i]);
+    for (i = 0; p->x && i < p->c0 * p->nranks; ++i) b2_plan_destroy(p->x[i]);
+    for (i = 0; p->z && i < p->c1; ++i) b2_plan_destroy(p->z[i]);
+    for (i = 0; p->g && i < p->c1 * p->nranks; ++i) b2_plan_destroy(p->g[i]);
+    free(p->y); free(p->x); free(p->z); free(p->g);
     free(p);
+}
+
+static int chunks_for(int64_t n)
+{
+    const char *e = getenv("FFTW3_B200_DIST_CHUNKS");
+    int c = e ? atoi(e) : 4;
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    while (c > 1 && n / c < 2) c /= 2;
+    return c;
 }
 
 dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
@@ -84,74 +107,98 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
 {
     dplan p;
     b2_problem q;
-    int d;
+    int d, c;
     int64_t b1 = blk(n1, nranks);
     int64_t ln0 = share(n0, nranks, rank), ln1 = share(n1, nranks, rank);
+    /* the single-launch scatter needs equal blocks and device-resident arrays (host arrays
+       are staged per plan from the plan's own tensors, which describe one destination) */
+    int even1 = (n1 % nranks == 0) && nranks <= B2D_MAX_PEERS && b2d_pointer_is_device(local) == 1;
     if (n0 <= 0 || n1 <= 0 || n2 <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return NULL;
     if (sign != -1 && sign != 1) return NULL;
     p = (dplan)calloc(1, sizeof *p);
     if (!p) return NULL;
     p->nranks = nranks; p->rank = rank;
     p->nstages = pull_sources ? 3 : 2;
-    p->x = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));
-    p->g = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));
-    if (!p->x || !p->g) goto fail;
+    p->c0 = ln0 > 0 ? chunks_for(ln0) : 1;
+    p->c1 = pull_sources ? chunks_for(b1) : 1;     /* from the block size: identical on every rank */
+    p->y = (b2_plan **)calloc((size_t)p->c0, sizeof(b2_plan *));
+    p->x = (b2_plan **)calloc((size_t)p->c0 * nranks, sizeof(b2_plan *));
+    p->z = (b2_plan **)calloc((size_t)p->c1, sizeof(b2_plan *));
+    p->g = (b2_plan **)calloc((size_t)p->c1 * nranks, sizeof(b2_plan *));
+    if (!p->y || !p->x || !p->z || !p->g) goto fail;
 
-    /* Y: FFT along n1 in place on [ln0][n1][n2] */
-    memset(&q, 0, sizeof q);
-    q.prec = B2D_F64; q.kind = B2_C2C; q.flags = flags;
-    b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
-    dim(&q.sz, n1, 2 * n2, 2 * n2);
-    dim(&q.vecsz, ln0, 2 * n1 * n2, 2 * n1 * n2);
-    dim(&q.vecsz, n2, 2, 2);
-    set_ptrs(&q, (double *)local, (double *)local, sign);
-    p->y = b2_mkplan(&q);
-    if (!p->y) goto fail;
-
-    /* X: FFT along n2, rows (i0, k1 in block d) -> push_targets[d] as [i0][k1'][k2] */
-    for (d = 0; d < nranks; ++d) {
-        int64_t l1 = share(n1, nranks, d);
-        memset(&q, 0, sizeof q);
-        q.prec = B2D_F64; q.kind = B2_C2C; q.flags = flags;
-        b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
-        dim(&q.sz, n2, 2, 2);
-        dim(&q.vecsz, ln0, 2 * n1 * n2, 2 * l1 * n2);
-        dim(&q.vecsz, l1, 2 * n2, 2 * n2);
-        set_ptrs(&q, (double *)local + 2 * d * b1 * n2, (double *)push_targets[d], sign);
-        p->x[d] = b2_mkplan(&q);
-        if (!p->x[d]) goto fail;
-    }
-
-    /* Z: FFT along n0 on zbuf = [n0][ln1][n2] */
-    memset(&q, 0, sizeof q);
-    q.prec = B2D_F64; q.kind = B2_C2C; q.flags = flags;
-    b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
-    if (pull_sources) {
-        dim(&q.sz, n0, 2 * ln1 * n2, 2 * ln1 * n2);
-        dim(&q.vecsz, ln1 * n2, 2, 2);
-        set_ptrs(&q, (double *)zbuf, (double *)zbuf, sign);
-    } else {
-        /* TRANSPOSED_OUT: [n0][ln1][n2] -> local as [ln1][n0][n2] */
-        dim(&q.sz, n0, 2 * ln1 * n2, 2 * n2);
-        dim(&q.vecsz, ln1, 2 * n2, 2 * n0 * n2);
+    for (c = 0; c < p->c0; ++c) {
+        int64_t lo = ln0 * c / p->c0, cnt = ln0 * (c + 1) / p->c0 - lo;   /* planes of this chunk */
+        double *lin = (double *)local + 2 * lo * n1 * n2;
+        /* Y: FFT along n1 in place on [cnt][n1][n2] */
+        init_problem(&q, flags);
+        dim(&q.sz, n1, 2 * n2, 2 * n2);
+        dim(&q.vecsz, cnt, 2 * n1 * n2, 2 * n1 * n2);
         dim(&q.vecsz, n2, 2, 2);
-        set_ptrs(&q, (double *)zbuf, (double *)local, sign);
-    }
-    p->z = b2_mkplan(&q);
-    if (!p->z) goto fail;
-
-    /* gather back: block from rank s = [ln0][l1(s)][n2] -> local[i0][s*b1 + k1'][k2] */
-    if (pull_sources) {
+        set_ptrs(&q, lin, lin, sign);
+        p->y[c] = b2_mkplan(&q);
+        if (!p->y[c]) goto fail;
+        /* X: FFT along n2, rows (i0, k1 in block d) -> push_targets[d] as [i0][k1'][k2] */
         for (d = 0; d < nranks; ++d) {
             int64_t l1 = share(n1, nranks, d);
-            memset(&q, 0, sizeof q);
-            q.prec = B2D_F64; q.kind = B2_C2C; q.flags = flags | B2F_ESTIMATE;
-            b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
-            dim(&q.vecsz, ln0, 2 * l1 * n2, 2 * n1 * n2);
-            dim(&q.vecsz, l1 * n2, 2, 2);
-            set_ptrs(&q, (double *)pull_sources[d], (double *)local + 2 * d * b1 * n2, -1);
-            p->g[d] = b2_mkplan(&q);
-            if (!p->g[d]) goto fail;
+            b2_plan *xp;
+            init_problem(&q, flags);
+            dim(&q.sz, n2, 2, 2);
+            dim(&q.vecsz, cnt, 2 * n1 * n2, 2 * l1 * n2);
+            dim(&q.vecsz, l1, 2 * n2, 2 * n2);
+            set_ptrs(&q, lin + 2 * d * b1 * n2, (double *)push_targets[d] + 2 * lo * l1 * n2, sign);
+            xp = b2_mkplan(&q);
+            if (!xp) goto fail;
+            p->x[c * nranks + d] = xp;
+            if (d == 0 && even1 && nranks > 1 && cnt > 1 && l1 > 1 && xp->nsteps == 1 && xp->steps[0].kind == STEP_FFT
+                && xp->steps[0].u.fft.bn[2] == 1 && xp->steps[0].u.fft.bn[0] == l1) {
+                /* all destinations get equal blocks: let batch dim 2 walk the destinations and
+                   select the peer buffer, so ONE launch scatters the whole chunk */
+                b2d_fft_pass *f = &xp->steps[0].u.fft;
+                int k;
+                f->bn[2] = nranks; f->bis[2] = 2 * b1 * n2; f->bos[2] = 0;
+                f->npeer = nranks;
+                for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)push_targets[k] + 2 * lo * l1 * n2;
+                p->x_fused[c] = 1;
+                break;
+            }
+        }
+    }
+
+    for (c = 0; c < p->c1; ++c) {
+        /* columns (k1', k2) of this chunk: k1' in [lo, lo + cnt) */
+        int64_t lo = ln1 * c / p->c1, cnt = ln1 * (c + 1) / p->c1 - lo;
+        init_problem(&q, flags);
+        if (pull_sources) {
+            /* Z in place on zbuf = [n0][ln1][n2] */
+            dim(&q.sz, n0, 2 * ln1 * n2, 2 * ln1 * n2);
+            dim(&q.vecsz, cnt * n2, 2, 2);
+            set_ptrs(&q, (double *)zbuf + 2 * lo * n2, (double *)zbuf + 2 * lo * n2, sign);
+        } else {
+            /* TRANSPOSED_OUT: [n0][ln1][n2] -> local as [ln1][n0][n2] */
+            dim(&q.sz, n0, 2 * ln1 * n2, 2 * n2);
+            dim(&q.vecsz, ln1, 2 * n2, 2 * n0 * n2);
+            dim(&q.vecsz, n2, 2, 2);
+            set_ptrs(&q, (double *)zbuf, (double *)local, sign);
+        }
+        p->z[c] = b2_mkplan(&q);
+        if (!p->z[c]) goto fail;
+    }
+    if (pull_sources) {
+        /* gather back: block from rank s = [ln0][l1(s)][n2] -> local[i0][s*b1 + k1'][k2];
+           chunk c takes the k1' range that rank s transformed in ITS chunk c */
+        for (d = 0; d < nranks; ++d) {
+            int64_t l1 = share(n1, nranks, d);
+            for (c = 0; c < p->c1; ++c) {
+                /* the same split every rank applies to its own columns in stage 1 */
+                int64_t lo = l1 * c / p->c1, cnt = l1 * (c + 1) / p->c1 - lo;
+                init_problem(&q, flags | B2F_ESTIMATE);
+                dim(&q.vecsz, ln0, 2 * l1 * n2, 2 * n1 * n2);
+                dim(&q.vecsz, cnt * n2, 2, 2);
+                set_ptrs(&q, (double *)pull_sources[d] + 2 * lo * n2, (double *)local + 2 * (d * b1 + lo) * n2, -1);
+                p->g[c * nranks + d] = b2_mkplan(&q);
+                if (!p->g[c * nranks + d]) goto fail;
+            }
         }
     }
     return p;
@@ -161,25 +208,57 @@ fail:
 }
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
+int fftw_b200_dist_num_chunks(const dplan p, int stage) { return stage == 0 ? p->c0 : p->c1; }
 
 static void run(b2_plan *pl)
 {
     if (pl) b2_execute(pl, pl->prob.in0, pl->prob.in1, pl->prob.out0, pl->prob.out1);
 }
 
+/* one chunk of a stage.  Stage 0: Y_c on the caller's stream, X_c on side stream 0.
+   Stage 1: Z_c on the caller's stream.  Stage 2: gather_c on side stream 1, after
+   everything the caller's stream holds so far (the caller's barrier included). */
+void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
+{
+    int d, saved = b2_async_mode;
+    void *mainst = b2d_get_stream();
+    b2_async_mode = 1;
+    if (stage == 0 && c < p->c0) {
+        void *aux = b2d_aux_stream(0);
+        run(p->y[c]);
+        if (aux) { b2d_stream_wait_stream(aux, mainst); b2d_set_stream(aux); }
+        if (p->x_fused[c]) run(p->x[c * p->nranks]);
+        else for (d = 0; d < p->nranks; ++d) run(p->x[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
+        b2d_set_stream(mainst);
+    } else if (stage == 1 && c < p->c1) {
+        run(p->z[c]);
+    } else if (stage == 2 && c < p->c1) {
+        void *aux = b2d_aux_stream(1);
+        if (aux) { b2d_stream_wait_stream(aux, mainst); b2d_set_stream(aux); }
+        for (d = 0; d < p->nranks; ++d) run(p->g[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
+        b2d_set_stream(mainst);
+    }
+    b2_async_mode = saved;
+}
+
+/* make the caller's stream wait for the side streams */
+void fftw_b200_dist_join(const dplan p)
+{
+    void *mainst = b2d_get_stream();
+    int i;
+    (void)p;
+    for (i = 0; i < 2; ++i) {
+        void *aux = b2d_aux_stream(i);
+        if (aux) b2d_stream_wait_stream(mainst, aux);
+    }
+    if (!b2_async_mode) b2d_sync();
+}
+
 void fftw_b200_dist_execute_stage(const dplan p, int stage)
 {
-    int d;
-    if (stage == 0) {
-        run(p->y);
-        /* start with the block for the next rank so that the ranks do not all
-           hammer the same destination at once */
-        for (d = 0; d < p->nranks; ++d) run(p->x[(p->rank + 1 + d) % p->nranks]);
-    } else if (stage == 1) {
-        run(p->z);
-    } else if (stage == 2) {
-        for (d = 0; d < p->nranks; ++d) run(p->g[(p->rank + 1 + d) % p->nranks]);
-    }
+    int c, n = fftw_b200_dist_num_chunks(p, stage);
+    for (c = 0; c < n; ++c) fftw_b200_dist_execute_chunk(p, stage, c);
+    fftw_b200_dist_join(p);
 }
 
 void *fftw_b200_device_malloc(size_t bytes) { return b2d_malloc(bytes); }

@@ -39,6 +39,9 @@ def _declare(lib):
     L.fftw_b200_dist_plan_dft_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
     L.fftw_b200_dist_num_stages.argtypes = [P]
     L.fftw_b200_dist_execute_stage.argtypes = [P, I]
+    L.fftw_b200_dist_num_chunks.argtypes = [P, I]
+    L.fftw_b200_dist_execute_chunk.argtypes = [P, I, I]
+    L.fftw_b200_dist_join.argtypes = [P]
     L.fftw_b200_dist_destroy_plan.argtypes = [P]
     L.fftw_b200_device_malloc.restype = P
     L.fftw_b200_device_malloc.argtypes = [C.c_size_t]
@@ -192,10 +195,16 @@ class SlabPlan3D:
             self._barrier()                         # peers are done reading their zbuf from the last call
             L.fftw_b200_dist_execute_stage(self.plan, 0)
             self._barrier()                         # all blocks have landed
-            L.fftw_b200_dist_execute_stage(self.plan, 1)
-            if self.nstages == 3:
-                self._barrier()                     # every rank's dim-0 transforms are complete
-                L.fftw_b200_dist_execute_stage(self.plan, 2)
+            if self.nstages == 2:
+                L.fftw_b200_dist_execute_stage(self.plan, 1)
+            else:
+                # chunked: the gather of chunk c (peer loads on a side stream) overlaps
+                # the dim-0 transforms of chunk c+1
+                for c in range(L.fftw_b200_dist_num_chunks(self.plan, 1)):
+                    L.fftw_b200_dist_execute_chunk(self.plan, 1, c)
+                    self._barrier()                 # every rank finished its chunk c
+                    L.fftw_b200_dist_execute_chunk(self.plan, 2, c)
+                L.fftw_b200_dist_join(self.plan)
         else:
             L.fftw_b200_dist_execute_stage(self.plan, 0)
             self._alltoall(self.recv, self.recv_counts, self.send, self.send_counts)

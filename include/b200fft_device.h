@@ -132,6 +132,9 @@ int  b2d_memset(void *dst, int byte, size_t bytes);
 int  b2d_sync(void);
 void b2d_set_stream(void *cuda_stream);  /* NULL = legacy default stream              */
 void *b2d_get_stream(void);
+/* side streams for overlapping NVLink-bound kernels with HBM-bound ones */
+void *b2d_aux_stream(int idx);                           /* lazily created, non-blocking  */
+int  b2d_stream_wait_stream(void *waiter, void *signaler); /* event edge signaler -> waiter */
 size_t b2d_max_smem_per_block(void);
 
 /* CUDA IPC: share a b2d_malloc'ed buffer with the other single-GPU processes of a job */

@@ -55,6 +55,17 @@ fftw_b200_dist_plan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdi
                                                int sign, unsigned flags);
 int  fftw_b200_dist_num_stages(const fftw_b200_dist_plan p);
 void fftw_b200_dist_execute_stage(const fftw_b200_dist_plan p, int stage);
+/* Finer control for overlapping the exchange with compute: every stage is cut
+ * into chunks (planes for stage 0, columns for stages 1 and 2; the chunk count of
+ * stages 1/2 is the same on every rank).  Stage-0 chunks pipeline internally
+ * (scatter of chunk c on a side stream under the transforms of chunk c+1).
+ * For natural-order output the caller runs, per chunk c:
+ *     execute_chunk(p, 1, c); <barrier on the current stream>; execute_chunk(p, 2, c);
+ * and finally fftw_b200_dist_join(p): the gather of chunk c (side stream, NVLink
+ * bound) then overlaps the dim-0 transforms of chunk c+1. */
+int  fftw_b200_dist_num_chunks(const fftw_b200_dist_plan p, int stage);
+void fftw_b200_dist_execute_chunk(const fftw_b200_dist_plan p, int stage, int chunk);
+void fftw_b200_dist_join(const fftw_b200_dist_plan p);
 void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);
 
 /* device memory that can be shared with the other ranks of the job (CUDA IPC) */

@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Measure every BASELINE.json config on one GPU (device-resident arrays, CUDA
+events, FFTW_MEASURE) and print one JSON line per config:
+GFLOP/s in the reference's convention (libbench2/mflops.c:19-27) and the
+fraction of the HBM roofline for ONE read + ONE write of the arrays
+(BASELINE.md section 3)."""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from fftw3_b200 import binding as B  # noqa: E402
+
+
+def timeit(lib, prec, plan, reps, scale_fn=None):
+    lib.lib.fftw_b200_set_async(1)
+    for _ in range(3):
+        lib.execute(prec, plan)
+        if scale_fn:
+            scale_fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.launch_count()
+        e0.record()
+        for _ in range(reps):
+            lib.execute(prec, plan)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / reps)
+        if scale_fn:
+            scale_fn()
+    launches = (lib.launch_count() - l0) // reps
+    lib.lib.fftw_b200_set_async(0)
+    return best, launches
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--flags", default="measure")
+    a = ap.parse_args()
+    lib = B.load()
+    peak = 6454.3
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    flags = B.FFTW_MEASURE if a.flags == "measure" else B.FFTW_ESTIMATE
+    dev = "cuda"
+    out = []
+
+    def report(name, flops, bytes_1pass, ms, launches, plan, prec):
+        line = {"config": name, "ms": ms, "gflops": flops / ms / 1e6, "ideal_gbs_1pass": bytes_1pass / ms / 1e6,
+                "roofline_frac_1pass": bytes_1pass / ms / 1e6 / peak, "launches": launches,
+                "plan": " ".join(lib.sprint_plan(prec, plan).split())[:600]}
+        print(json.dumps(line), flush=True)
+        out.append(line)
+
+    def want(k):
+        return not a.only or k in a.only.split(",")
+
+    if want("C1"):
+        n, hm = 1024, 16384
+        x = torch.rand(hm, n, 2, dtype=torch.float64, device=dev) - 0.5
+        y = torch.empty_like(x)
+        p = lib.plan_many_dft("d", [n], hm, x.data_ptr(), None, 1, n, y.data_ptr(), None, 1, n, -1, flags)
+        ms, l = timeit(lib, "d", p, 20)
+        report("C1 c2c f64 N=1024 x16384 out-of-place", 5 * n * hm * math.log2(n), 2 * 16 * n * hm, ms, l, p, "d")
+        lib.destroy_plan("d", p)
+        p = lib.plan_many_dft("d", [n], hm, x.data_ptr(), None, 1, n, x.data_ptr(), None, 1, n, -1, flags)
+        ms, l = timeit(lib, "d", p, 20, lambda: x.mul_(1 / 32.0))
+        report("C1 c2c f64 N=1024 x16384 in-place", 5 * n * hm * math.log2(n), 2 * 16 * n * hm, ms, l, p, "d")
+        lib.destroy_plan("d", p)
+        del x, y
+    if want("C2"):
+        n, hm = 1 << 20, 256
+        x = torch.rand(hm, n, dtype=torch.float32, device=dev) - 0.5
+        y = torch.empty(hm, n // 2 + 1, 2, dtype=torch.float32, device=dev)
+        p = lib.plan_many_dft_r2c("f", [n], hm, x.data_ptr(), None, 1, n, y.data_ptr(), None, 1, n // 2 + 1, flags)
+        assert p
+        ms, l = timeit(lib, "f", p, 5)
+        nb = 4 * n * hm + 8 * (n // 2 + 1) * hm
+        report("C2 r2c f32 N=2^20 x256", 2.5 * n * hm * math.log2(n), nb, ms, l, p, "f")
+        lib.destroy_plan("f", p)
+        p = lib.plan_many_dft_c2r("f", [n], hm, y.data_ptr(), None, 1, n // 2 + 1, x.data_ptr(), None, 1, n, flags)
+        assert p
+        ms, l = timeit(lib, "f", p, 5, lambda: y.mul_(1e-3))
+        report("C2 c2r f32 N=2^20 x256", 2.5 * n * hm * math.log2(n), nb, ms, l, p, "f")
+        lib.destroy_plan("f", p)
+        del x, y
+    if want("C3"):
+        n = 512
+        x = torch.rand(n, n, n, 2, dtype=torch.float64, device=dev) - 0.5
+        p = lib.fn("d", "plan_dft_3d")(n, n, n, x.data_ptr(), x.data_ptr(), -1, flags)
+        ms, l = timeit(lib, "d", p, 10, lambda: x.mul_(1.0 / n ** 1.5))
+        report("C3 c2c f64 512^3 in-place (3 passes; frac is for 1 pass-equivalent)", 5 * n ** 3 * math.log2(n ** 3),
+               2 * 16 * n ** 3, ms, l, p, "d")
+        lib.destroy_plan("d", p)
+        del x
+    if want("C5a"):
+        n, hm = 1009, 16384
+        x = torch.rand(hm, n, 2, dtype=torch.float64, device=dev) - 0.5
+        y = torch.empty_like(x)
+        p = lib.plan_many_dft("d", [n], hm, x.data_ptr(), None, 1, n, y.data_ptr(), None, 1, n, -1, flags)
+        ms, l = timeit(lib, "d", p, 10)
+        report("C5a c2c f64 prime N=1009 x16384", 5 * n * hm * math.log2(n), 2 * 16 * n * hm, ms, l, p, "d")
+        lib.destroy_plan("d", p)
+        del x, y
+    if want("C5b"):
+        n = 4096
+        x = torch.rand(n, n, dtype=torch.float64, device=dev) - 0.5
+        y = torch.empty_like(x)
+        p = lib.fn("d", "plan_r2r_2d")(n, n, x.data_ptr(), y.data_ptr(), 5, 5, flags)
+        assert p
+        ms, l = timeit(lib, "d", p, 10)
+        report("C5b REDFT10 f64 4096^2 (2 dims; frac is for 1 pass-equivalent)", 2.5 * n * n * math.log2(n * n),
+               2 * 8 * n * n, ms, l, p, "d")
+        lib.destroy_plan("d", p)
+        del x, y
+    if want("C1f"):
+        n, hm = 1024, 16384
+        x = torch.rand(hm, n, 2, dtype=torch.float32, device=dev) - 0.5
+        y = torch.empty_like(x)
+        p = lib.plan_many_dft("f", [n], hm, x.data_ptr(), None, 1, n, y.data_ptr(), None, 1, n, -1, flags)
+        ms, l = timeit(lib, "f", p, 20)
+        report("(extra) c2c f32 N=1024 x16384", 5 * n * hm * math.log2(n), 2 * 8 * n * hm, ms, l, p, "f")
+        lib.destroy_plan("f", p)
+
+
+if __name__ == "__main__":
+    main()
