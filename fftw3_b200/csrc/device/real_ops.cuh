@@ -220,8 +220,17 @@ __global__ void realop_kernel(const __grid_constant__ b2d_realop r, int len, int
 template <typename T>
 __global__ void copy_kernel(const __grid_constant__ b2d_copy c, int64_t total)
 {
+    // grid-stride, 4 independent elements in flight per thread (peer loads over NVLink
+    // need the memory-level parallelism)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < total) copy_elem<T>(c, idx);
+    for (; idx + 3 * stride < total; idx += 4 * stride) {
+        copy_elem<T>(c, idx);
+        copy_elem<T>(c, idx + stride);
+        copy_elem<T>(c, idx + 2 * stride);
+        copy_elem<T>(c, idx + 3 * stride);
+    }
+    for (; idx < total; idx += stride) copy_elem<T>(c, idx);
 }
 #endif
 

@@ -128,7 +128,9 @@ void *b2d_aux_stream(int idx)
     static cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
     if (ensure_init() || idx < 0 || idx >= 4) return nullptr;
     if (!aux[idx]) {
-        if (cudaStreamCreateWithFlags(&aux[idx], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        int lo = 0, hi = 0;                 /* hi = numerically lowest = greatest priority */
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&aux[idx], cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
     }
     return (void *)aux[idx];
 }
@@ -206,6 +208,7 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     if (rc < 0) { snprintf(g_err, sizeof g_err, "fast kernel launch failed"); return -1; }
     size_t smem = p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
     if (smem > g_max_smem) { snprintf(g_err, sizeof g_err, "pass needs %zu B smem", smem); return -1; }
+    if (p->grid_limit > 0 && blocks > p->grid_limit) blocks = p->grid_limit;
     int threads = p->tpb * p->tpx;
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
@@ -224,7 +227,8 @@ int b2d_launch_copy(const b2d_copy *c)
     if (ensure_init()) return -1;
     int64_t total = c->n[0] * c->n[1] * c->n[2] * c->n[3];
     if (total <= 0) return 0;
-    int64_t blocks = (total + 255) / 256;
+    int64_t blocks = (total + 4 * 256 - 1) / (4 * 256);
+    if (c->grid_limit > 0 && blocks > c->grid_limit) blocks = c->grid_limit;
     if (blocks > 2147483647LL) { snprintf(g_err, sizeof g_err, "copy grid too large"); return -1; }
     if (c->prec == B2D_F32) b2::copy_kernel<float><<<(unsigned)blocks, 256, 0, g_stream>>>(*c, total);
     else b2::copy_kernel<double><<<(unsigned)blocks, 256, 0, g_stream>>>(*c, total);

@@ -91,6 +91,25 @@ void fftw_b200_dist_destroy_plan(dplan p)
     free(p);
 }
 
+/* CTAs granted to an NVLink-bound pass (scatter, gather) that runs next to an HBM-bound one */
+static int comm_ctas(void)
+{
+    const char *e = getenv("FFTW3_B200_DIST_COMM_CTAS");
+    int sms = b2d_sm_count();
+    if (e) return atoi(e);
+    return sms > 0 ? sms : 148;
+}
+
+static void limit_grid(b2_plan *pl, int limit)
+{
+    int i;
+    if (!pl || limit <= 0) return;
+    for (i = 0; i < pl->nsteps; ++i) {
+        if (pl->steps[i].kind == STEP_FFT) pl->steps[i].u.fft.grid_limit = limit;
+        else if (pl->steps[i].kind == STEP_COPY) pl->steps[i].u.copy.grid_limit = limit;
+    }
+}
+
 static int chunks_for(int64_t n)
 {
     const char *e = getenv("FFTW3_B200_DIST_CHUNKS");
@@ -150,6 +169,7 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
             xp = b2_mkplan(&q);
             if (!xp) goto fail;
             p->x[c * nranks + d] = xp;
+            if (nranks > 1 && p->c0 > 1) limit_grid(xp, comm_ctas());
             if (d == 0 && even1 && nranks > 1 && cnt > 1 && l1 > 1 && xp->nsteps == 1 && xp->steps[0].kind == STEP_FFT
                 && xp->steps[0].u.fft.bn[2] == 1 && xp->steps[0].u.fft.bn[0] == l1) {
                 /* all destinations get equal blocks: let batch dim 2 walk the destinations and
@@ -198,6 +218,7 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
                 set_ptrs(&q, (double *)pull_sources[d] + 2 * lo * n2, (double *)local + 2 * (d * b1 + lo) * n2, -1);
                 p->g[c * nranks + d] = b2_mkplan(&q);
                 if (!p->g[c * nranks + d]) goto fail;
+                if (nranks > 1 && p->c1 > 1) limit_grid(p->g[c * nranks + d], 2 * comm_ctas());
             }
         }
     }

@@ -76,6 +76,9 @@ typedef struct b2d_fft_pass {
        complex buffer that may live on another GPU (CUDA IPC / NVLink peer mapping) */
     int npeer;
     void *peer_out[B2D_MAX_PEERS];
+    /* 0: one CTA per tile.  > 0: launch at most this many CTAs, which loop over the
+       tiles -- used to keep an NVLink-bound pass from occupying every SM */
+    int grid_limit;
 } b2d_fft_pass;
 
 /* strided N-d copy / rank-0 transform (kernel/cpy2d.c, rdft/rank0.c analogue);
@@ -90,6 +93,7 @@ typedef struct b2d_copy {
     /* peer gather: when npeer > 0 dim 3 selects the SOURCE buffer peer_in[i3] */
     int npeer;
     const void *peer_in[B2D_MAX_PEERS];
+    int grid_limit;                 /* as in b2d_fft_pass */
 } b2d_copy;
 
 /* r2c / c2r even-length split (rdft/ct-hc2c-direct.c:45-60 analogue) and r2r
