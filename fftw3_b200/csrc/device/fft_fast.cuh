@@ -130,136 +130,130 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     const int j = COL ? (tid / TPB) : (tid % TPX);
     auto sidx = [&](int k) -> int { return COL ? (k * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
 
-    // grid-stride over tiles (see fft_generic_kernel): gridDim.x may be smaller than the tile count
-    const int64_t ntiles = b2::grid_blocks(p);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const b2::TileCtx c = b2::decode_block(p, tile);
-        const int64_t b0 = c.tile0 * TPB + t;
-        const bool valid = b0 < p.bn[0];
-        const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
-        const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
-        // interleaved data: vector pointer at the lower of (re, im)
-        const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re) + boff_in / 2;
-        // peer scatter: batch dim 2 selects the destination buffer (a peer GPU's exchange
-        // buffer mapped over NVLink): the transpose is fused with its collective
-        cplx<T> *gout = (p.npeer ? reinterpret_cast<cplx<T> *>(p.peer_out[c.b2])
-                                 : reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re)) + boff_out / 2;
-        const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
-        const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
-        const bool keep_in = p.cache & 1, keep_out = p.cache & 2;   // L2-resident side of a blocked pass pair
+    const b2::TileCtx c = b2::decode_block(p, (int64_t)blockIdx.x);
+    const int64_t b0 = c.tile0 * TPB + t;
+    const bool valid = b0 < p.bn[0];
+    const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
+    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
+    // interleaved data: vector pointer at the lower of (re, im)
+    const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re) + boff_in / 2;
+    // peer scatter: batch dim 2 selects the destination buffer (a peer GPU's exchange
+    // buffer mapped over NVLink): the transpose is fused with its collective
+    cplx<T> *gout = (p.npeer ? reinterpret_cast<cplx<T> *>(p.peer_out[c.b2])
+                             : reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re)) + boff_out / 2;
+    const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
+    const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
+    const bool keep_in = p.cache & 1, keep_out = p.cache & 2;   // L2-resident side of a blocked pass pair
 
-        T re[E], im[E];
-        // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
-    #pragma unroll
-        for (int r = 0; r < E; ++r) {
-            cplx<T> v; v.x = T(0); v.y = T(0);
-            if (valid) v = keep_in ? *(gin + (int64_t)(j + r * TPX) * is2) : ld_stream(gin + (int64_t)(j + r * TPX) * is2);
-            re[r] = swap_in ? v.y : v.x;
-            im[r] = swap_in ? v.x : v.y;
-        }
-        Butterfly<E, T>::run(re, im);
-    #pragma unroll
-        for (int r = 0; r < E; ++r) {
-            cplx<T> v; v.x = re[r]; v.y = im[r];
-            sm[sidx(j * E + r)] = v;
-        }
-        __syncthreads();
+    T re[E], im[E];
+    // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        cplx<T> v; v.x = T(0); v.y = T(0);
+        if (valid) v = keep_in ? *(gin + (int64_t)(j + r * TPX) * is2) : ld_stream(gin + (int64_t)(j + r * TPX) * is2);
+        re[r] = swap_in ? v.y : v.x;
+        im[r] = swap_in ? v.x : v.y;
+    }
+    Butterfly<E, T>::run(re, im);
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        cplx<T> v; v.x = re[r]; v.y = im[r];
+        sm[sidx(j * E + r)] = v;
+    }
+    __syncthreads();
 
-        // ---- stage 2: radix R1, Ns = E.  Butterflies b = j + i*TPX; k = b % E.
-        {
-            constexpr int NB = N / R1;            // butterflies per transform
-            constexpr int PER = E / R1;           // butterflies per thread
-            constexpr int TSTEP = N / (E * R1);
-            cplx<T> w[R1];
-            // TPX % E == 0 for three-stage sizes: k = j % E for every butterfly of this thread
-            if (R2 > 1 || PER == 1) load_twiddles<R1, T>(tw, TSTEP * (j % E), w);
-    #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int b = j + i * TPX;
-                if (R2 == 1 && PER > 1) load_twiddles<R1, T>(tw, TSTEP * (b % E), w);
-    #pragma unroll
-                for (int r = 0; r < R1; ++r) {
-                    cplx<T> v = sm[sidx(b + r * NB)];
-                    if (r > 0) v = cmul(v, w[r]);
-                    re[i * R1 + r] = v.x; im[i * R1 + r] = v.y;
-                }
-            }
-            if (R2 > 1) __syncthreads();          // all reads done before the buffer is overwritten
-    #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                T xr[R1], xi[R1];
-    #pragma unroll
-                for (int r = 0; r < R1; ++r) { xr[r] = re[i * R1 + r]; xi[r] = im[i * R1 + r]; }
-                Butterfly<R1, T>::run(xr, xi);
-    #pragma unroll
-                for (int r = 0; r < R1; ++r) { re[i * R1 + r] = xr[r]; im[i * R1 + r] = xi[r]; }
-            }
-            if (R2 > 1) {
-    #pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int b = j + i * TPX;
-                    const int k = b % E;
-                    const int j0 = (b - k) * R1 + k;
-    #pragma unroll
-                    for (int r = 0; r < R1; ++r) {
-                        cplx<T> v; v.x = re[i * R1 + r]; v.y = im[i * R1 + r];
-                        sm[sidx(j0 + r * E)] = v;
-                    }
-                }
-                __syncthreads();
-            } else {
-                // two-stage transform: this was the last stage (Ns = E = N / R1, so k = b)
-    #pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int b = j + i * TPX;
-    #pragma unroll
-                    for (int r = 0; r < R1; ++r) {
-                        cplx<T> v;
-                        v.x = swap_out ? im[i * R1 + r] : re[i * R1 + r];
-                        v.y = swap_out ? re[i * R1 + r] : im[i * R1 + r];
-                        if (valid) { if (keep_out) *(gout + (int64_t)(b + r * E) * os2) = v; else st_stream(gout + (int64_t)(b + r * E) * os2, v); }
-                    }
-                }
-                __syncthreads();
-                continue;
+    // ---- stage 2: radix R1, Ns = E.  Butterflies b = j + i*TPX; k = b % E.
+    {
+        constexpr int NB = N / R1;            // butterflies per transform
+        constexpr int PER = E / R1;           // butterflies per thread
+        constexpr int TSTEP = N / (E * R1);
+        cplx<T> w[R1];
+        // TPX % E == 0 for three-stage sizes: k = j % E for every butterfly of this thread
+        if (R2 > 1 || PER == 1) load_twiddles<R1, T>(tw, TSTEP * (j % E), w);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = j + i * TPX;
+            if (R2 == 1 && PER > 1) load_twiddles<R1, T>(tw, TSTEP * (b % E), w);
+#pragma unroll
+            for (int r = 0; r < R1; ++r) {
+                cplx<T> v = sm[sidx(b + r * NB)];
+                if (r > 0) v = cmul(v, w[r]);
+                re[i * R1 + r] = v.x; im[i * R1 + r] = v.y;
             }
         }
-
-        // ---- stage 3: radix R2, Ns = E * R1 (last: k = b, outputs at b + r * Ns).
-        // twiddle W_N^(r b) with b = j + i*TPX:  W_N^(r j) * W_E^(r i)  (TPX = N / E)
+        if (R2 > 1) __syncthreads();          // all reads done before the buffer is overwritten
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            T xr[R1], xi[R1];
+#pragma unroll
+            for (int r = 0; r < R1; ++r) { xr[r] = re[i * R1 + r]; xi[r] = im[i * R1 + r]; }
+            Butterfly<R1, T>::run(xr, xi);
+#pragma unroll
+            for (int r = 0; r < R1; ++r) { re[i * R1 + r] = xr[r]; im[i * R1 + r] = xi[r]; }
+        }
         if (R2 > 1) {
-            constexpr int NS = E * R1;
-            constexpr int PER = E / R2;
-            constexpr int R2_ = R2 > 1 ? R2 : 2;
-            cplx<T> w[R2_];
-            load_twiddles<R2_, T>(tw, j, w);
-    #pragma unroll
+#pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int b = j + i * TPX;
-                T xr[R2_], xi[R2_];
-    #pragma unroll
-                for (int r = 0; r < R2; ++r) {
-                    cplx<T> v = sm[sidx(b + r * NS)];
-                    if (r > 0) {
-                        cplx<T> wr = w[r];
-                        if (i > 0) {
-                            wr = cmul(wr, unit_root<E, T>((r * i) % E));
-                        }
-                        v = cmul(v, wr);
-                    }
-                    xr[r] = v.x; xi[r] = v.y;
-                }
-                Butterfly<R2_, T>::run(xr, xi);
-    #pragma unroll
-                for (int r = 0; r < R2; ++r) {
-                    cplx<T> v;
-                    v.x = swap_out ? xi[r] : xr[r];
-                    v.y = swap_out ? xr[r] : xi[r];
-                    if (valid) { if (keep_out) *(gout + (int64_t)(b + r * NS) * os2) = v; else st_stream(gout + (int64_t)(b + r * NS) * os2, v); }
+                const int k = b % E;
+                const int j0 = (b - k) * R1 + k;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) {
+                    cplx<T> v; v.x = re[i * R1 + r]; v.y = im[i * R1 + r];
+                    sm[sidx(j0 + r * E)] = v;
                 }
             }
+            __syncthreads();
+        } else {
+            // two-stage transform: this was the last stage (Ns = E = N / R1, so k = b)
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int b = j + i * TPX;
+#pragma unroll
+                for (int r = 0; r < R1; ++r) {
+                    cplx<T> v;
+                    v.x = swap_out ? im[i * R1 + r] : re[i * R1 + r];
+                    v.y = swap_out ? re[i * R1 + r] : im[i * R1 + r];
+                    if (valid) { if (keep_out) *(gout + (int64_t)(b + r * E) * os2) = v; else st_stream(gout + (int64_t)(b + r * E) * os2, v); }
+                }
+            }
+            return;
         }
-        __syncthreads();          // shared buffer is reused by the next tile
+    }
+
+    // ---- stage 3: radix R2, Ns = E * R1 (last: k = b, outputs at b + r * Ns).
+    // twiddle W_N^(r b) with b = j + i*TPX:  W_N^(r j) * W_E^(r i)  (TPX = N / E)
+    if (R2 > 1) {
+        constexpr int NS = E * R1;
+        constexpr int PER = E / R2;
+        constexpr int R2_ = R2 > 1 ? R2 : 2;
+        cplx<T> w[R2_];
+        load_twiddles<R2_, T>(tw, j, w);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int b = j + i * TPX;
+            T xr[R2_], xi[R2_];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                cplx<T> v = sm[sidx(b + r * NS)];
+                if (r > 0) {
+                    cplx<T> wr = w[r];
+                    if (i > 0) {
+                        wr = cmul(wr, unit_root<E, T>((r * i) % E));
+                    }
+                    v = cmul(v, wr);
+                }
+                xr[r] = v.x; xi[r] = v.y;
+            }
+            Butterfly<R2_, T>::run(xr, xi);
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                cplx<T> v;
+                v.x = swap_out ? xi[r] : xr[r];
+                v.y = swap_out ? xr[r] : xi[r];
+                if (valid) { if (keep_out) *(gout + (int64_t)(b + r * NS) * os2) = v; else st_stream(gout + (int64_t)(b + r * NS) * os2, v); }
+            }
+        }
     }
 }
 

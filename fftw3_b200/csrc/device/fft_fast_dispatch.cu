@@ -85,10 +85,9 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     const int64_t blocks = tiles0 * p.bn[1] * p.bn[2];
     if (blocks <= 0) return 0;
     if (blocks > 2147483647LL) return -1;
-    int64_t launch_blocks = (p.grid_limit > 0 && blocks > p.grid_limit) ? p.grid_limit : blocks;
     b2d_fft_pass q = p;
     q.tpb = e->tpb;                  // decode_block() uses the tile width
-    e->launch(q, swap_in, swap_out, (unsigned)launch_blocks, st);
+    e->launch(q, swap_in, swap_out, (unsigned)blocks, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -282,33 +282,27 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const Smem<T> s = carve<T>(p, smem_raw);
-    // grid-stride over tiles: the host may launch fewer CTAs than tiles (grid_limit) so that an
-    // NVLink-bound pass leaves room for an HBM-bound one running next to it
-    const int64_t ntiles = grid_blocks(p);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileCtx c = decode_block(p, tile);
-        phase_offsets<T>(p, s, c, tid);
-        __syncthreads();
-        phase_load<T>(p, s, tid, nthreads);
-        __syncthreads();
-        cplx<T> *src = s.a, *dst = s.b;
-        const int reps = p.bluestein ? 2 : 1;
-        for (int rep = 0; rep < reps; ++rep) {
-            int ns = 1;
-            for (int st = 0; st < p.nstages; ++st) {
-                phase_stage<T>(p, st, ns, src, dst, s.pitch, tid, nthreads);
-                __syncthreads();
-                ns *= p.radix[st];
-                cplx<T> *tmp = src; src = dst; dst = tmp;
-            }
-            if (p.bluestein && rep == 0) {
-                phase_pointwise<T>(p, src, s.pitch, tid, nthreads);
-                __syncthreads();
-            }
+    const TileCtx c = decode_block(p, (int64_t)blockIdx.x);
+    phase_offsets<T>(p, s, c, tid);
+    __syncthreads();
+    phase_load<T>(p, s, tid, nthreads);
+    __syncthreads();
+    cplx<T> *src = s.a, *dst = s.b;
+    const int reps = p.bluestein ? 2 : 1;
+    for (int rep = 0; rep < reps; ++rep) {
+        int ns = 1;
+        for (int st = 0; st < p.nstages; ++st) {
+            phase_stage<T>(p, st, ns, src, dst, s.pitch, tid, nthreads);
+            __syncthreads();
+            ns *= p.radix[st];
+            cplx<T> *tmp = src; src = dst; dst = tmp;
         }
-        phase_store<T>(p, s, c, src, tid, nthreads);
-        __syncthreads();
+        if (p.bluestein && rep == 0) {
+            phase_pointwise<T>(p, src, s.pitch, tid, nthreads);
+            __syncthreads();
+        }
     }
+    phase_store<T>(p, s, c, src, tid, nthreads);
 }
 #endif
 

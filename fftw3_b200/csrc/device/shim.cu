@@ -208,7 +208,6 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     if (rc < 0) { snprintf(g_err, sizeof g_err, "fast kernel launch failed"); return -1; }
     size_t smem = p->prec == B2D_F32 ? b2::smem_bytes<float>(*p) : b2::smem_bytes<double>(*p);
     if (smem > g_max_smem) { snprintf(g_err, sizeof g_err, "pass needs %zu B smem", smem); return -1; }
-    if (p->grid_limit > 0 && blocks > p->grid_limit) blocks = p->grid_limit;
     int threads = p->tpb * p->tpx;
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
