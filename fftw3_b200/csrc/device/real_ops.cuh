@@ -183,6 +183,43 @@ B2_HD void c2r_pre_elem(const b2d_realop &r, int64_t b, int k)
     ((cplx<T> *)r.work)[b * r.wdist + k] = o;
 }
 
+// ---- Bluestein element maps for sizes too large for the one-CTA kernel ----
+template <typename T>
+B2_HD void blue_elem(const b2d_realop &r, int64_t b, int i)
+{
+    cplx<T> *W = (cplx<T> *)r.work + b * r.wdist;
+    const cplx<T> *chirp = (const cplx<T> *)r.tw;
+    const int64_t s = r.xs;
+    if (r.op == B2D_ROP_BLUE_PRE) {
+        cplx<T> z; z.x = T(0); z.y = T(0);
+        if (i < r.n_lim) {
+            int64_t off = realop_user_offset(r, b);
+            const T *xr = (const T *)r.x_re + off, *xi = (const T *)r.x_im + off;
+            const int n = r.n;
+            if (r.flags & B2D_LOAD_REAL) { z.x = xr[(int64_t)i * s]; }
+            else if (r.flags & B2D_LOAD_HERMCONJ) {
+                if (2 * i <= n) { z.x = xr[(int64_t)i * s]; z.y = (i == 0 || 2 * i == n) ? T(0) : -xi[(int64_t)i * s]; }
+                else { z.x = xr[(int64_t)(n - i) * s]; z.y = xi[(int64_t)(n - i) * s]; }
+            } else { z.x = xr[(int64_t)i * s]; z.y = xi[(int64_t)i * s]; }
+            z = cmul(z, chirp[i]);
+        }
+        W[i] = z;
+    } else if (r.op == B2D_ROP_BLUE_MID) {
+        cplx<T> v = cmul(W[i], ((const cplx<T> *)r.aux)[i]);
+        v.y = -v.y;
+        W[i] = v;
+    } else {
+        if (i >= r.n_lim) return;
+        int64_t off = realop_user_offset(r, b);
+        T *yr = (T *)r.y_re + off, *yi = (T *)r.y_im + off;
+        cplx<T> v = W[i];
+        v.y = -v.y;
+        v = cmul(v, chirp[i]);
+        yr[(int64_t)i * s] = v.x * (T)r.scale;
+        if (!(r.flags & B2D_STORE_REALPART)) yi[(int64_t)i * s] = v.y * (T)r.scale;
+    }
+}
+
 // strided N-d copy, one element (1 or 2 reals) per index
 template <typename T>
 B2_HD void copy_elem(const b2d_copy &c, int64_t idx)
@@ -213,6 +250,7 @@ __global__ void realop_kernel(const __grid_constant__ b2d_realop r, int len, int
     if (i >= len) return;
     if (r.op == B2D_ROP_R2C_POST) r2c_post_pair<T>(r, b, i);
     else if (r.op == B2D_ROP_C2R_PRE) c2r_pre_elem<T>(r, b, i);
+    else if (r.op >= B2D_ROP_BLUE_PRE && r.op <= B2D_ROP_BLUE_POST) blue_elem<T>(r, b, i);
     else if (r.op & B2D_ROP_R2R_POST) r2r_post_elem<T>(r, r.op & 15, b, i);
     else r2r_pre_elem<T>(r, r.op & 15, b, i);
 }

@@ -244,6 +244,7 @@ int b2d_launch_realop(const b2d_realop *r)
     int kind = r->op & 15;
     if (r->op == B2D_ROP_R2C_POST) len = r->m / 2 + 1;
     else if (r->op == B2D_ROP_C2R_PRE) len = r->m;
+    else if (r->op >= B2D_ROP_BLUE_PRE && r->op <= B2D_ROP_BLUE_POST) len = (r->op == B2D_ROP_BLUE_POST) ? r->n_lim : r->m;
     else if (r->op & B2D_ROP_R2R_POST) len = r->n;
     else len = b2::r2r_work_len(kind, r->n);
     int64_t nb = r->bn[0] * r->bn[1] * r->bn[2];

@@ -54,7 +54,7 @@ typedef struct {
 } b2_problem;
 
 /* ---- plan ---- */
-enum { BUF_NONE = 0, BUF_IN0, BUF_IN1, BUF_OUT0, BUF_OUT1, BUF_SCRATCH0, BUF_SCRATCH1, BUF_SCRATCH2, BUF_TABLE, BUF_COUNT };
+enum { BUF_NONE = 0, BUF_IN0, BUF_IN1, BUF_OUT0, BUF_OUT1, BUF_SCRATCH0, BUF_SCRATCH1, BUF_SCRATCH2, BUF_SCRATCH3, BUF_TABLE, BUF_COUNT };
 
 typedef struct { int buf; int64_t off; /* in reals (scratch/table: in bytes) */ } b2_ref;
 
@@ -82,8 +82,8 @@ typedef struct b2_plan {
     b2_problem prob;
     int nsteps, cap;
     b2_step *steps;
-    size_t scratch_bytes[3];
-    void *scratch[3];
+    size_t scratch_bytes[4];
+    void *scratch[4];
     int ntables, tcap;
     b2_table **tables;
     double est_flops_add, est_flops_mul, est_flops_fma;

@@ -22,7 +22,7 @@ static void *resolve(const b2_plan *p, b2_ref r, void *const user[4], size_t rs)
     switch (r.buf) {
     case BUF_IN0: case BUF_IN1: case BUF_OUT0: case BUF_OUT1:
         return user[r.buf - BUF_IN0] ? (char *)user[r.buf - BUF_IN0] + r.off * (int64_t)rs : NULL;
-    case BUF_SCRATCH0: case BUF_SCRATCH1: case BUF_SCRATCH2:
+    case BUF_SCRATCH0: case BUF_SCRATCH1: case BUF_SCRATCH2: case BUF_SCRATCH3:
         return (char *)p->scratch[r.buf - BUF_SCRATCH0] + r.off * (int64_t)rs;
     default:
         return NULL;

@@ -415,6 +415,15 @@ static b2_view view_shift(b2_view v, int64_t off)
     return v;
 }
 
+/* real-op steps (defined further down) are also used by the large-Bluestein path */
+typedef struct {
+    int prec, op, n, m; int64_t xs; b2_ref x_re, x_im, y_re, y_im; int work_slot;
+    int64_t wdist; const void *tw; int user_is_out; int64_t *line_base;
+    const void *aux; int flags, n_lim; double scale;
+} rop_ctx;
+static int emit_realop(b2_plan *p, rop_ctx *c, const b2_tensor *wb);
+static void dense_work_strides(b2_tensor *t, int64_t wdist);
+
 /* ----------------------------------------------------- batched 1-D complex FFT */
 typedef struct {
     int prec; int64_t n; b2_view in, out; b2_ops ops; int scratch_slot; const char *note;
@@ -439,7 +448,63 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
         int64_t m = next_pow2(2 * n - 1);
         if (single_pass_fits(m, c->prec))
             return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, (int)m, "bluestein");
-        return -1;   /* large non-smooth sizes: not yet supported */
+        /* padded length too long for one CTA: chirp.pad kernel, FFT_M (four-step), x B, FFT_M,
+           chirp kernel -- the same five steps as dft/bluestein.c:82-128, through scratch */
+        {
+            b2_tensor ub;
+            rop_ctx rc_;
+            b2_view wv;
+            b2_ops none;
+            int i, rc;
+            int64_t lines = 1;
+            size_t esz = 2 * real_size(c->prec);
+            if (c->ops.pre_op & (B2D_LOAD_PAD | B2D_LOAD_CHIRP)) return -1;
+            if (c->ops.post_op & ~(B2D_STORE_REALPART | B2D_STORE_TRUNC)) return -1;
+            for (i = 0; i < brank; ++i) lines *= bd[i].n;
+            need_scratch(p, 3, (size_t)lines * (size_t)m * esz);
+            memset(&none, 0, sizeof none);
+            /* PRE: user line -> work [line][m] */
+            b2_tensor_init(&ub, 0);
+            for (i = 0; i < brank; ++i) { ub.d[i].n = bd[i].n; ub.d[i].is = bd[i].is; }
+            ub.rnk = brank;
+            dense_work_strides(&ub, m);
+            memset(&rc_, 0, sizeof rc_);
+            rc_.prec = c->prec; rc_.op = B2D_ROP_BLUE_PRE; rc_.n = (int)n; rc_.m = (int)m; rc_.xs = in.stride;
+            rc_.x_re = in.re; rc_.x_im = in.im; rc_.work_slot = 3; rc_.wdist = m; rc_.user_is_out = 0;
+            rc_.flags = c->ops.pre_op; rc_.n_lim = (int)n;
+            rc_.tw = plan_table(p, c->prec, TAB_CHIRP, n, 0);
+            rc_.aux = plan_table(p, c->prec, TAB_BLUE_B, n, m);
+            if (!rc_.tw || !rc_.aux) return -1;
+            rc = emit_realop(p, &rc_, &ub);
+            if (rc) return rc;
+            /* FFT_M, x B (conj), FFT_M on the work lines */
+            wv.re = mkref(BUF_SCRATCH3, 0); wv.im = mkref(BUF_SCRATCH3, 1); wv.stride = 2;
+            for (i = 0; i < 2; ++i) {
+                b2_tensor fb;
+                b2_tensor_init(&fb, 1);
+                fb.d[0].n = lines; fb.d[0].is = 2 * m; fb.d[0].os = 2 * m;
+                rc = emit_fft1d(p, c->prec, m, wv, wv, &fb, none, 1, "bluestein FFT_M");
+                if (rc) return rc;
+                if (i == 0) {
+                    b2_tensor mb;
+                    rop_ctx mid = rc_;
+                    mid.op = B2D_ROP_BLUE_MID;
+                    b2_tensor_init(&mb, 1);
+                    mb.d[0].n = lines; mb.d[0].is = 0; mb.d[0].os = 2 * m;
+                    rc = emit_realop(p, &mid, &mb);
+                    if (rc) return rc;
+                }
+            }
+            /* POST: work -> user line */
+            for (i = 0; i < brank; ++i) ub.d[i].is = bd[i].os;
+            rc_.op = B2D_ROP_BLUE_POST; rc_.xs = out.stride;
+            rc_.y_re = out.re; rc_.y_im = out.im; rc_.user_is_out = 1;
+            rc_.x_re = rc_.x_im = mkref(BUF_NONE, 0);
+            rc_.flags = c->ops.post_op;
+            rc_.n_lim = c->ops.n_out ? c->ops.n_out : (int)n;
+            rc_.scale = 1.0 / (double)m;
+            return emit_realop(p, &rc_, &ub);
+        }
     }
 
     /* four-step: n = n1 * n2, pass A strided length-n1 FFTs + twiddle into
@@ -524,27 +589,24 @@ static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
 
 /* every b2_ref offset, user buffer or scratch, is in units of the real scalar type */
 
-/* plain contiguous in-place FFT on a device buffer (used to build Bluestein's B table) */
+/* plain contiguous in-place FFT on a device buffer (used to build Bluestein's B table):
+   an ordinary plan of this library, executed once */
 int b2_run_contig_fft(int prec, int64_t n, void *dev)
 {
-    b2d_fft_pass f;
-    b2_table *tw;
+    b2_problem q;
+    b2_plan *pl;
     int rc;
-    memset(&f, 0, sizeof f);
-    f.prec = prec; f.n = (int)n;
-    f.n_in = f.n_out = (int)n;
-    f.is = f.os = 2;
-    f.bn[0] = f.bn[1] = f.bn[2] = 1;
-    f.scale = 1.0;
-    if (configure_variant(&f, 0)) return -1;
-    tw = b2_table_get(prec, TAB_TWIDDLE, n, 0);
-    if (!tw) return -1;
-    f.tw = tw->dev;
-    f.in_re = dev; f.in_im = (char *)dev + real_size(prec);
-    f.out_re = dev; f.out_im = (char *)dev + real_size(prec);
-    rc = b2d_launch_fft_pass(&f);
-    if (!rc) rc = b2d_sync();
-    b2_table_release(tw);
+    memset(&q, 0, sizeof q);
+    q.prec = prec; q.kind = B2_C2C; q.flags = B2F_ESTIMATE;
+    b2_tensor_init(&q.sz, 1); b2_tensor_init(&q.vecsz, 0);
+    q.sz.d[0].n = n; q.sz.d[0].is = 2; q.sz.d[0].os = 2;
+    q.in0 = dev; q.in1 = (char *)dev + real_size(prec);
+    q.out0 = q.in0; q.out1 = q.in1;
+    pl = b2_mkplan(&q);
+    if (!pl) return -1;
+    b2_execute(pl, q.in0, q.in1, q.out0, q.out1);
+    rc = b2d_sync();
+    b2_plan_destroy(pl);
     return rc;
 }
 
@@ -581,10 +643,7 @@ static int emit_copy(b2_plan *p, int prec, b2_ref in, b2_ref out, const b2_tenso
 }
 
 /* --------------------------------------------------------------- real ops */
-typedef struct {
-    int prec, op, n, m; int64_t xs; b2_ref x_re, x_im, y_re, y_im; int work_slot;
-    int64_t wdist; const void *tw; int user_is_out; int64_t *line_base;
-} rop_ctx;
+
 
 static int rop_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff)
 {
@@ -601,10 +660,12 @@ static int rop_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_
     for (i = 0; i < brank; ++i) { r->bn[i] = bd[i].n; r->bxs[i] = bd[i].is; lines *= bd[i].n; }
     r->wdist = c->wdist;
     r->tw = c->tw;
+    r->aux = c->aux; r->flags = c->flags; r->n_lim = c->n_lim; r->scale = c->scale;
     s->r[0] = c->x_re; s->r[1] = c->x_im; s->r[2] = c->y_re; s->r[3] = c->y_im;
     if (c->user_is_out) { s->r[2].off += ioff; s->r[3].off += ioff; }
     else { s->r[0].off += ioff; s->r[1].off += ioff; }
     s->r[4] = mkref(BUF_SCRATCH0 + c->work_slot, ooff);   /* dense work strides are in reals */
+    if (c->op == B2D_ROP_BLUE_MID) { s->r[0] = s->r[1] = s->r[2] = s->r[3] = mkref(BUF_NONE, 0); }
     snprintf(s->note, sizeof s->note, "realop %d", c->op);
     (void)lines;
     return 0;
@@ -1115,21 +1176,59 @@ b2_plan *b2_mkplan(const b2_problem *prob)
         if (ek) p->l2_block_bytes = (size_t)atol(ek) << 10;
     }
     if (b2_tensor_count(&p->prob.vecsz) == 0) { p->is_nop = 1; return p; }
-    if (p->inplace && prob->kind != B2_R2C && prob->kind != B2_C2R) {
-        /* in-place needs identical input and output locations (dft/problem.c:95-99) */
-        if (!b2_tensor_inplace_ok(&p->prob.sz) || !b2_tensor_inplace_ok(&p->prob.vecsz)) {
-            b2_plan_destroy(p);
-            return NULL;
+    {
+        /* In place with different input and output strides (e.g. an in-place transpose
+           expressed as a rank-0 transform, rdft/rank0.c:345-381, rdft/vrank3-transpose.c):
+           the reference marks the plain problem unsolvable (dft/problem.c:95-99) and solves
+           it through buffered/indirect solvers (dft/indirect.c:55-108).  Same idea here:
+           transform into dense plan-owned scratch, then one strided copy to the output. */
+        int via_scratch = 0, k;
+        b2_problem saved = p->prob;
+        int64_t dense = 0;
+        if (p->inplace && prob->kind != B2_R2C && prob->kind != B2_C2R &&
+            (!b2_tensor_inplace_ok(&p->prob.sz) || !b2_tensor_inplace_ok(&p->prob.vecsz))) {
+            int64_t ld = (prob->kind == B2_C2C) ? 2 : 1;
+            via_scratch = 1;
+            for (i = p->prob.sz.rnk - 1; i >= 0; --i) { p->prob.sz.d[i].os = ld; ld *= p->prob.sz.d[i].n; }
+            for (i = p->prob.vecsz.rnk - 1; i >= 0; --i) { p->prob.vecsz.d[i].os = ld; ld *= p->prob.vecsz.d[i].n; }
+            dense = ld;
+            p->inplace = 0;
+        }
+        switch (prob->kind) {
+        case B2_C2C: rc = plan_c2c(p); break;
+        case B2_R2C: rc = plan_r2c(p); break;
+        case B2_C2R: rc = plan_c2r(p); break;
+        case B2_R2R: rc = plan_r2r(p); break;
+        }
+        if (!rc && via_scratch) {
+            b2_tensor t;
+            size_t rsz = (prob->prec == B2D_F32) ? 4 : 8;
+            for (i = 0; i < p->nsteps; ++i)
+                for (k = 0; k < 6; ++k) {
+                    b2_ref *r = &p->steps[i].r[k];
+                    if (r->buf == BUF_OUT0) r->buf = BUF_SCRATCH2;
+                    else if (r->buf == BUF_OUT1) { r->buf = BUF_SCRATCH2; r->off += 1; }
+                }
+            if ((size_t)dense * rsz > p->scratch_bytes[2]) p->scratch_bytes[2] = (size_t)dense * rsz;
+            /* copy back: dense strides (now in .os of the rewritten problem) -> the user's */
+            b2_tensor_init(&t, 0);
+            for (i = 0; i < p->prob.sz.rnk; ++i) {
+                t.d[t.rnk].n = p->prob.sz.d[i].n; t.d[t.rnk].is = p->prob.sz.d[i].os;
+                t.d[t.rnk].os = saved.sz.d[i].os; t.rnk++;
+            }
+            for (i = 0; i < p->prob.vecsz.rnk; ++i) {
+                t.d[t.rnk].n = p->prob.vecsz.d[i].n; t.d[t.rnk].is = p->prob.vecsz.d[i].os;
+                t.d[t.rnk].os = saved.vecsz.d[i].os; t.rnk++;
+            }
+            rc = emit_copy(p, prob->prec, mkref(BUF_SCRATCH2, 0), mkref(BUF_OUT0, 0), &t, 1);
+            if (!rc && prob->kind == B2_C2C)
+                rc = emit_copy(p, prob->prec, mkref(BUF_SCRATCH2, 1), mkref(BUF_OUT1, 0), &t, 1);
+            p->prob = saved;
+            p->inplace = 1;
         }
     }
-    switch (prob->kind) {
-    case B2_C2C: rc = plan_c2c(p); break;
-    case B2_R2C: rc = plan_r2c(p); break;
-    case B2_C2R: rc = plan_c2r(p); break;
-    case B2_R2R: rc = plan_r2r(p); break;
-    }
     if (rc) { b2_plan_destroy(p); return NULL; }
-    for (i = 0; i < 3; ++i) {
+    for (i = 0; i < 4; ++i) {
         if (p->scratch_bytes[i]) {
             p->scratch[i] = b2d_malloc(p->scratch_bytes[i]);
             if (!p->scratch[i]) { b2_plan_destroy(p); return NULL; }
@@ -1146,7 +1245,7 @@ void b2_plan_destroy(b2_plan *p)
     b2_plan_lock_destroy(p);
     for (i = 0; i < p->ntables; ++i) b2_table_release(p->tables[i]);
     free(p->tables);
-    for (i = 0; i < 3; ++i) b2d_free(p->scratch[i]);
+    for (i = 0; i < 4; ++i) b2d_free(p->scratch[i]);
     for (i = 0; i < 4; ++i) b2d_free(p->stage_dev[i]);
     free(p->steps);
     free(p);

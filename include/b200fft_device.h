@@ -110,11 +110,20 @@ typedef struct b2d_realop {
     void *y_re, *y_im;
     void *work;                /* interleaved complex work buffer                     */
     const void *tw;            /* op-specific table                                   */
+    const void *aux;           /* BLUE_MID: FFT of the Bluestein filter (m complex)   */
+    int flags;                 /* BLUE_PRE: B2D_LOAD_* ; BLUE_POST: B2D_STORE_*       */
+    int n_lim;                 /* BLUE_PRE: valid inputs ; BLUE_POST: outputs stored   */
+    double scale;              /* BLUE_POST: 1 / m                                    */
 } b2d_realop;
 
 enum {
     B2D_ROP_R2C_POST = 1,   /* work[0..n/2) = FFT(z), write X[0..n/2] to user (cr,ci)  */
     B2D_ROP_C2R_PRE = 2,    /* user X[0..n/2] -> work z-spectrum for backward FFT     */
+    /* Bluestein for sizes whose padded length m does not fit one CTA (dft/bluestein.c:82-128):
+       PRE  work[i] = i < n ? load(x_i) * chirp_i : 0          (i < m)
+       MID  work[i] = conj(work[i] * B_i)                      (between the two FFT_m)
+       POST y_k = conj(work[k]) * chirp_k * scale              (k < n_lim)                  */
+    B2D_ROP_BLUE_PRE = 3, B2D_ROP_BLUE_MID = 4, B2D_ROP_BLUE_POST = 5,
     B2D_ROP_R2R_PRE = 16,   /* + kind: user real line -> complex work sequence        */
     B2D_ROP_R2R_POST = 32   /* + kind: complex work spectrum -> user real line        */
 };

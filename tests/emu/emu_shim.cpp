@@ -63,6 +63,7 @@ static void run_realop(const b2d_realop &r)
     int kind = r.op & 15, len;
     if (r.op == B2D_ROP_R2C_POST) len = r.m / 2 + 1;
     else if (r.op == B2D_ROP_C2R_PRE) len = r.m;
+    else if (r.op >= B2D_ROP_BLUE_PRE && r.op <= B2D_ROP_BLUE_POST) len = (r.op == B2D_ROP_BLUE_POST) ? r.n_lim : r.m;
     else if (r.op & B2D_ROP_R2R_POST) len = r.n;
     else len = r2r_work_len(kind, r.n);
     int64_t nb = r.bn[0] * r.bn[1] * r.bn[2];
@@ -70,6 +71,7 @@ static void run_realop(const b2d_realop &r)
         for (int i = 0; i < len; ++i) {
             if (r.op == B2D_ROP_R2C_POST) r2c_post_pair<T>(r, b, i);
             else if (r.op == B2D_ROP_C2R_PRE) c2r_pre_elem<T>(r, b, i);
+            else if (r.op >= B2D_ROP_BLUE_PRE && r.op <= B2D_ROP_BLUE_POST) blue_elem<T>(r, b, i);
             else if (r.op & B2D_ROP_R2R_POST) r2r_post_elem<T>(r, kind, b, i);
             else r2r_pre_elem<T>(r, kind, b, i);
         }

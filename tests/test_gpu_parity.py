@@ -212,3 +212,23 @@ def test_reference_golden_vectors(gpu_lib, name, x, want):
     """committed outputs of the reference's own code (tests/golden/make_golden.py)"""
     got = G.via_lib(gpu_lib, name, x)
     assert O.rel_l2(got, want) < 3e-15
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n", [2053, 4100, 10007])
+def test_large_bluestein(gpu_lib, prec, n):
+    err, tol = F.c2c(gpu_lib, prec, (n,), howmany=3)
+    assert err <= tol
+    err, tol = F.r2c(gpu_lib, prec, (n,), howmany=2)
+    assert err <= tol
+
+
+def test_inplace_transpose_and_stride_change(gpu_lib):
+    rng = np.random.default_rng(8)
+    x = F.rand_complex(rng, (96, 96), "d")
+    x0 = x.copy()
+    p = gpu_lib.plan_guru_dft("d", [(96, 96, 1), (96, 1, 96)], [], x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    assert p
+    gpu_lib.execute("d", p)
+    gpu_lib.destroy_plan("d", p)
+    assert O.rel_l2(x.T, O.dft(x0)) <= F.tol_for("d", (96, 96))

@@ -151,9 +151,6 @@ def test_null_on_invalid(emu_lib):
     assert not f(-3, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
     assert not emu_lib.plan_many_dft("d", [8], -1, x.ctypes.data, None, 1, 8, x.ctypes.data, None, 1, 8, -1,
                                      B.FFTW_ESTIMATE)                          # howmany < 0
-    # in place with different strides is unsolvable (dft/problem.c:95-99)
-    assert not emu_lib.plan_many_dft("d", [8], 2, x.ctypes.data, None, 1, 8, x.ctypes.data, None, 2, 16, -1,
-                                     B.FFTW_ESTIMATE)
     # multi-dimensional out-of-place c2r cannot preserve its input
     y = np.zeros(64, np.float64)
     assert not emu_lib.plan_many_dft_c2r("d", [4, 6], 1, x.ctypes.data, None, 1, 16, y.ctypes.data, None, 1, 24,
@@ -203,3 +200,47 @@ def test_plan_introspection(emu_lib):
     ptr = emu_lib.fn("d", "malloc")(1000)
     assert ptr and emu_lib.fn("d", "alignment_of")(ptr) == 0
     emu_lib.fn("d", "free")(ptr)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n", [2053, 4100])
+def test_large_bluestein(emu_lib, prec, n):
+    """prime factors > 13 with a padded length beyond one CTA: five-step Bluestein through scratch"""
+    err, tol = F.c2c(emu_lib, prec, (n,), howmany=2)
+    assert err <= tol
+    if n == 2053:
+        err, tol = F.r2c(emu_lib, prec, (n,), howmany=2)
+        assert err <= tol
+        err, tol = F.c2r(emu_lib, prec, (n,), howmany=2)
+        assert err <= tol
+
+
+def test_inplace_with_different_strides(emu_lib):
+    """in place, is != os: solved through scratch like the reference's buffered/indirect solvers
+    (dft/indirect.c:55-108); includes the in-place transpose idiom (rank-0 guru transform)."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    x = F.rand_complex(rng, (6, 6), "d")
+    x0 = x.copy()
+    p = emu_lib.plan_guru_dft("d", [(6, 6, 1), (6, 1, 6)], [], x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(x.T, O.dft(x0)) < 1e-15
+    a = np.arange(12, dtype=np.float64).reshape(3, 4).copy()
+    a0 = a.copy()
+    h = (B.Iodim * 2)(B.Iodim(3, 4, 1), B.Iodim(4, 1, 3))
+    p = emu_lib.fn("d", "plan_guru_r2r")(0, None, 2, C.cast(h, C.c_void_p), a.ctypes.data, a.ctypes.data, None,
+                                         B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert np.array_equal(a.reshape(-1), a0.T.reshape(-1))
+    y = F.rand_complex(rng, (40,), "d")
+    y0 = y.copy()
+    p = emu_lib.plan_many_dft("d", [8], 2, y.ctypes.data, None, 1, 8, y.ctypes.data, None, 2, 16, -1, B.FFTW_ESTIMATE)
+    assert p
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    for k in range(2):
+        assert O.rel_l2(y[16 * k:16 * k + 16:2], O.dft(y0[8 * k:8 * k + 8])) < 1e-15
