@@ -96,7 +96,7 @@ __device__ __forceinline__ void load_twiddles(const cplx<T> *tw, int step, cplx<
 
 // padded row pitch for the ROW layout (same padding rule as the generic kernel)
 __host__ __device__ constexpr int padk_c(int k) { return k + (k >> 4); }
-__host__ __device__ constexpr int pitch_c(int n) { return padk_c(n - 1) + 2; }
+__host__ __device__ constexpr int pitch_c(int n) { return ((padk_c(n - 1) + 1 + 14) / 16) * 16 + 1; }
 
 template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
 struct FastCfg {
@@ -143,14 +143,55 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
                              : reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re)) + boff_out / 2;
     const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
     const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
-    const bool keep_in = p.cache & 1, keep_out = p.cache & 2;   // L2-resident side of a blocked pass pair
+
+    // final-stage output of element kout of this thread's transform
+    //   FLAVOR 2: four-step twiddle W_big^(kout * b0) fused into the store (two-level table)
+    //   FLAVOR 3: ROW tile stored in COL order: park the result in shared memory (same
+    //             position the thread just read), the CTA streams it out below
+    auto emit = [&](int kout, T vr, T vi) {
+        if (FLAVOR == 2) {
+            int64_t e = (int64_t)kout * b0;
+            int64_t eh, el;
+            if (p.tw4_shift >= 0) { e &= (p.big_n - 1); eh = e >> p.tw4_shift; el = e & (p.aux_split - 1); }
+            else { e %= p.big_n; eh = e / p.aux_split; el = e - eh * p.aux_split; }
+            cplx<T> w = cmul(ldg_c(reinterpret_cast<const cplx<T> *>(p.aux1) + eh),
+                             ldg_c(reinterpret_cast<const cplx<T> *>(p.aux0) + el));
+            cplx<T> v; v.x = vr; v.y = vi;
+            v = cmul(v, w);
+            vr = v.x; vi = v.y;
+        }
+        cplx<T> o;
+        if (FLAVOR == 3) {
+            o.x = vr; o.y = vi;
+            sm[sidx(kout)] = o;
+        } else {
+            o.x = swap_out ? vi : vr;
+            o.y = swap_out ? vr : vi;
+            if (valid) st_stream(gout + (int64_t)kout * os2, o);
+        }
+    };
+    auto flush_col = [&]() {
+        if (FLAVOR != 3) return;
+        __syncthreads();
+        cplx<T> *gbase = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re);
+        for (int idx = tid; idx < N * TPB; idx += Cfg::THREADS) {
+            const int tt = idx % TPB, k = idx / TPB;
+            const int64_t bb = c.tile0 * TPB + tt;
+            if (bb >= p.bn[0]) continue;
+            cplx<T> v = sm[tt * pitch_c(N) + padk_c(k)];
+            cplx<T> o;
+            o.x = swap_out ? v.y : v.x;
+            o.y = swap_out ? v.x : v.y;
+            st_stream(gbase + (bb * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2]) / 2 + (int64_t)k * os2, o);
+        }
+    };
 
     T re[E], im[E];
     // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = T(0); v.y = T(0);
-        if (valid) v = keep_in ? *(gin + (int64_t)(j + r * TPX) * is2) : ld_stream(gin + (int64_t)(j + r * TPX) * is2);
+        if (valid) v = ld_stream(gin + (int64_t)(j + r * TPX) * is2);
         re[r] = swap_in ? v.y : v.x;
         im[r] = swap_in ? v.x : v.y;
     }
@@ -210,13 +251,9 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             for (int i = 0; i < PER; ++i) {
                 const int b = j + i * TPX;
 #pragma unroll
-                for (int r = 0; r < R1; ++r) {
-                    cplx<T> v;
-                    v.x = swap_out ? im[i * R1 + r] : re[i * R1 + r];
-                    v.y = swap_out ? re[i * R1 + r] : im[i * R1 + r];
-                    if (valid) { if (keep_out) *(gout + (int64_t)(b + r * E) * os2) = v; else st_stream(gout + (int64_t)(b + r * E) * os2, v); }
-                }
+                for (int r = 0; r < R1; ++r) emit(b + r * E, re[i * R1 + r], im[i * R1 + r]);
             }
+            flush_col();
             return;
         }
     }
@@ -247,13 +284,9 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             }
             Butterfly<R2_, T>::run(xr, xi);
 #pragma unroll
-            for (int r = 0; r < R2; ++r) {
-                cplx<T> v;
-                v.x = swap_out ? xi[r] : xr[r];
-                v.y = swap_out ? xr[r] : xi[r];
-                if (valid) { if (keep_out) *(gout + (int64_t)(b + r * NS) * os2) = v; else st_stream(gout + (int64_t)(b + r * NS) * os2, v); }
-            }
+            for (int r = 0; r < R2; ++r) emit(b + r * NS, xr[r], xi[r]);
         }
+        flush_col();
     }
 }
 

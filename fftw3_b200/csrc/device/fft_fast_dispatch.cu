@@ -33,19 +33,26 @@ void init(int max_smem)
                                      (int)tabs[k][i].smem);
 }
 
-// structural applicability (known at plan time)
+// structural applicability (known at plan time).  kernel code = tile + 100*flavor + 1000*col;
+// flavor 2 = COL kernel with the four-step twiddle fused in its store, flavor 3 = ROW load
+// with COL (transposed) store.
 static const FastEntry *entry_for(const b2d_fft_pass &p)
 {
     if (!p.kernel) return nullptr;
-    if (p.pre_op || p.post_op || p.bluestein) return nullptr;
-    if (p.load_col != p.store_col) return nullptr;
     const int col = p.kernel >= 1000;
-    if (col != p.load_col) return nullptr;
+    const int flavor = (p.kernel / 100) % 10;
+    if (p.pre_op || p.bluestein) return nullptr;
+    if (flavor == 2) { if (p.post_op != B2D_STORE_TWIDDLE4 || !p.load_col || !p.store_col) return nullptr; }
+    else if (p.post_op) return nullptr;
+    if (flavor == 3) { if (p.load_col || !p.store_col || p.npeer) return nullptr; }
+    else if (p.load_col != p.store_col || col != p.load_col) return nullptr;
     if ((p.is & 1) || (p.os & 1)) return nullptr;
     for (int i = 0; i < B2D_MAX_BATCH_DIMS; ++i)
         if ((p.bis[i] & 1) || (p.bos[i] & 1)) return nullptr;
-    if (col && (p.bis[0] != 2 || p.bos[0] != 2)) return nullptr;     // adjacent pencils
-    if (!col && (p.is != 2 || p.os != 2)) return nullptr;            // contiguous transforms
+    if (p.load_col && p.bis[0] != 2) return nullptr;                 // adjacent pencils on the load side
+    if (p.store_col && p.bos[0] != 2) return nullptr;                // ... and on the store side
+    if (!p.load_col && p.is != 2) return nullptr;                    // contiguous transforms
+    if (!p.store_col && p.os != 2) return nullptr;
     const FastEntry *e = find(p.prec, p.n, col, p.kernel);
     if (e && (int)e->smem > g_max_smem && g_max_smem) return nullptr;
     return e;

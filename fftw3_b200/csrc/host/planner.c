@@ -189,7 +189,11 @@ static int configure_variant(b2d_fft_pass *f, int variant)
     if (variant >= NVARIANTS) {
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
-        int code = ((f->load_col || f->store_col) ? 1000 : 0) + 100 * flavor + tpb;
+        int code;
+        /* pass shapes with their own specialised flavour (see device/fft_fast.cuh) */
+        if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
+        else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
+        code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
         if (variant >= NVARIANTS + NFAST) return -1;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
@@ -212,7 +216,7 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 static int estimate_variant(b2d_fft_pass *f)
 {
     static const int col_pref[] = { 3, 4, 2, 5 }, row_pref[] = { 1, 2, 0, 3, 4, 5 };
-    int col = f->load_col || f->store_col, i;
+    int col = f->load_col || f->store_col, i;       /* wide tiles whenever a side is strided */
     const int *pref = col ? col_pref : row_pref;
     int npref = col ? 4 : 6;
     for (i = 0; i < npref; ++i) {
@@ -323,6 +327,12 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     }
     if (f->post_op & B2D_STORE_TWIDDLE4) {
         f->big_n = ops.big_n; f->aux_split = ops.tw4_split;
+        f->tw4_shift = -1;
+        if ((ops.big_n & (ops.big_n - 1)) == 0 && (ops.tw4_split & (ops.tw4_split - 1)) == 0) {
+            int sh = 0;
+            while (((int64_t)1 << sh) < ops.tw4_split) ++sh;
+            f->tw4_shift = sh;
+        }
         f->aux0 = plan_table(p, prec, TAB_TW4_LO, ops.big_n, ops.tw4_split);
         f->aux1 = plan_table(p, prec, TAB_TW4_HI, ops.big_n, ops.tw4_split);
         if (!f->aux0 || !f->aux1) return -1;

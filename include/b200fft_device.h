@@ -70,6 +70,7 @@ typedef struct b2d_fft_pass {
     const void *aux0, *aux1;  /* op tables                                           */
     int64_t aux_split;        /* TWIDDLE4: lo-table length L (e = hi*L + lo)          */
     int64_t big_n;            /* TWIDDLE4: N of the enclosing transform               */
+    int tw4_shift;            /* log2(aux_split) when big_n and aux_split are powers of two, else -1 */
     double scale;
     /* peer scatter (multi-GPU exchange fused into the pass): when npeer > 0 batch
        dim 2 does not stride the output but selects peer_out[b2], an interleaved
