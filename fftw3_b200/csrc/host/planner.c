@@ -179,6 +179,7 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 }
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
+#define NPIPE 3               /* persistent pipelined strided kernels (fft_pipe.cuh), widest tiles first */
 #define NFAST 12              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor
                                  (12..17 uncapped registers, 18..23 capped for more resident CTAs) */
 
@@ -186,6 +187,24 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
+    if (variant >= NVARIANTS + NFAST) {
+        /* persistent cp.async-pipelined strided kernels: tile widths are whatever the table holds;
+           variant k tries the k-th widest */
+        int want = variant - (NVARIANTS + NFAST), tpb, seen = 0;
+        if (want >= NPIPE) return -1;
+        for (tpb = 32; tpb >= 2; --tpb) {
+            if (!b2d_fast_available(f, 5000 + tpb)) continue;
+            if (seen++ == want) {
+                ns = b2_factorize(f->n, f->prec, 0, f->radix);
+                if (ns == 0) return -1;
+                f->nstages = ns < 0 ? 0 : ns;
+                fill_geometry(f, 0);
+                f->kernel = 5000 + tpb;
+                return 0;
+            }
+        }
+        return -1;
+    }
     if (variant >= NVARIANTS) {
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
@@ -194,7 +213,6 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
         code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
-        if (variant >= NVARIANTS + NFAST) return -1;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
         ns = b2_factorize(f->n, f->prec, 0, f->radix);
@@ -345,10 +363,15 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     /* choose the variant: wisdom -> measure -> heuristic */
     {
         b2_sig sig = b2_sig_of_pass(f, inplace);
-        if (b2_wisdom_lookup(sig, pat, &variant)) have = 1;
+        const char *force = getenv("FFTW3_B200_FORCE_VARIANT");   /* tests: pin a kernel variant */
+        if (force) {
+            b2d_fft_pass trial = *f;
+            if (!configure_variant(&trial, atoi(force))) { variant = atoi(force); have = 2; }
+        }
+        if (!have && b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
         if (!have && pat >= 1) {
-            int v, nv = NVARIANTS + NFAST, bestv = -1;
+            int v, nv = NVARIANTS + NFAST + NPIPE, bestv = -1;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
@@ -368,7 +391,8 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                     double bytes = 4.0 * real_size(prec) * (double)f->n * (double)(f->bn[0] * f->bn[1] * f->bn[2]);
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
                             f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
-                            (long long)f->bn[1], (long long)f->bn[2], v, trial.kernel ? "codelet" : "generic",
+                            (long long)f->bn[1], (long long)f->bn[2], v,
+                            trial.kernel >= 5000 ? "pipelined" : (trial.kernel ? "codelet" : "generic"),
                             trial.kernel ? trial.kernel % 100 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
                 }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
@@ -380,7 +404,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
             if (configure_variant(f, 0)) return -1;
             variant = 0;
         }
-        b2_wisdom_store(sig, pat, variant);
+        if (have != 2) b2_wisdom_store(sig, pat, variant);
     }
     /* op count estimate (reference convention is per-plan add/mul/fma) */
     {
@@ -1277,7 +1301,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel) fprintf(f, "codelet-tile=%d%s", q->kernel % 100, (q->kernel / 100) % 10 ? "r" : "");
+            if (q->kernel >= 5000) fprintf(f, "pipelined-tile=%d", q->kernel - 5000);
+            else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
                     q->bluestein ? " bluestein" : "");

@@ -232,3 +232,16 @@ def test_inplace_transpose_and_stride_change(gpu_lib):
     gpu_lib.execute("d", p)
     gpu_lib.destroy_plan("d", p)
     assert O.rel_l2(x.T, O.dft(x0)) <= F.tol_for("d", (96, 96))
+
+
+@pytest.mark.parametrize("variant", list(range(12, 27)))
+def test_every_specialised_kernel_variant(gpu_lib, variant, monkeypatch):
+    """Pin each specialised-kernel variant of the planner (tile widths x flavours of
+    fft_fast.cuh, pipelined kernels of fft_pipe.cuh) and check parity on shapes that exercise
+    ROW, COL, four-step (fused twiddle store, transposed store) and partial tiles."""
+    monkeypatch.setenv("FFTW3_B200_FORCE_VARIANT", str(variant))
+    for prec in PRECS:
+        for shape, hm, inplace in (((1024,), 37, False), ((512, 30), 3, True), ((13, 1024, 20), 1, True),
+                                   ((1 << 19,), 2, False), ((256, 64, 36), 1, False)):
+            err, tol = F.c2c(gpu_lib, prec, shape, howmany=hm, inplace=inplace, sign=-1 if variant % 2 else 1)
+            assert err <= tol, (variant, prec, shape)
