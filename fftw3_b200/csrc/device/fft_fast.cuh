@@ -62,6 +62,26 @@ __device__ __forceinline__ void st_stream(cplx<float> *p, cplx<float> v)
     __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y));
 }
 
+// Loads that ask L2 to fetch a whole 128 / 256-byte block from DRAM: a narrow COL tile
+// (64 B per row) then costs DRAM one long burst per block instead of several short ones; the
+// neighbouring tiles (other CTAs, scheduled next to this one) find their part in L2.
+template <int BYTES>
+__device__ __forceinline__ cplx<double> ld_l2pf(const cplx<double> *p)
+{
+    cplx<double> r;
+    if (BYTES == 256) asm volatile("ld.global.L2::256B.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    else asm volatile("ld.global.L2::128B.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+template <int BYTES>
+__device__ __forceinline__ cplx<float> ld_l2pf(const cplx<float> *p)
+{
+    cplx<float> r;
+    if (BYTES == 256) asm volatile("ld.global.L2::256B.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    else asm volatile("ld.global.L2::128B.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
 // compile-time root of unity W_E^m (m is a constant after unrolling)
 template <int E, typename T>
 __device__ __forceinline__ cplx<T> unit_root(int m)
@@ -148,7 +168,28 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     //   FLAVOR 2: four-step twiddle W_big^(kout * b0) fused into the store (two-level table)
     //   FLAVOR 3: ROW tile stored in COL order: park the result in shared memory (same
     //             position the thread just read), the CTA streams it out below
-    auto emit = [&](int kout, T vr, T vi) {
+    //   FLAVOR 7: Bluestein in one CTA (dft/bluestein.c:82-128): the stages run twice; the first
+    //             run's outputs are multiplied by B = FFT(filter), conjugated and kept in registers
+    //             -- output b + r*Ns of the last stage IS input j + q*TPX of the next first stage,
+    //             q = i + PER*r -- the second run's outputs get conj * chirp * 1/M and are cut to n_out
+    T bre[FLAVOR == 7 ? E : 1], bim[FLAVOR == 7 ? E : 1];
+    int rep = 0;
+    auto emit = [&](int kout, int q, T vr, T vi) {
+        if (FLAVOR == 7) {
+            cplx<T> v; v.x = vr; v.y = vi;
+            if (rep == 0) {
+                v = cmul(v, ldg_c(reinterpret_cast<const cplx<T> *>(p.aux1) + kout));
+                bre[FLAVOR == 7 ? q : 0] = v.x; bim[FLAVOR == 7 ? q : 0] = -v.y;
+            } else if (valid && kout < p.n_out) {
+                v.y = -v.y;
+                v = cmul(v, ldg_c(reinterpret_cast<const cplx<T> *>(p.aux0) + kout));
+                cplx<T> o;
+                o.x = (swap_out ? v.y : v.x) * (T)p.scale;
+                o.y = (swap_out ? v.x : v.y) * (T)p.scale;
+                st_stream(gout + (int64_t)kout * os2, o);
+            }
+            return;
+        }
         if (FLAVOR == 2) {
             int64_t e = (int64_t)kout * b0;
             int64_t eh, el;
@@ -167,7 +208,10 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         } else {
             o.x = swap_out ? vi : vr;
             o.y = swap_out ? vr : vi;
-            if (valid) st_stream(gout + (int64_t)kout * os2, o);
+            if (valid) {
+                if (FLAVOR == 4) *(gout + (int64_t)kout * os2) = o;     // let L2 merge the halves of a line
+                else st_stream(gout + (int64_t)kout * os2, o);
+            }
         }
     };
     auto flush_col = [&]() {
@@ -191,9 +235,30 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = T(0); v.y = T(0);
-        if (valid) v = ld_stream(gin + (int64_t)(j + r * TPX) * is2);
+        if (FLAVOR == 7) {
+            const int k = j + r * TPX;
+            if (valid && k < p.n_in) v = ld_stream(gin + (int64_t)k * is2);
+        } else if (valid) {
+            // flavors 4-6 (narrow COL tiles): 4 = L2::256B loads + write-back stores,
+            // 5 = L2::128B loads + streaming stores, 6 = L2::256B loads + streaming stores
+            if (FLAVOR == 4 || FLAVOR == 6) v = ld_l2pf<256>(gin + (int64_t)(j + r * TPX) * is2);
+            else if (FLAVOR == 5) v = ld_l2pf<128>(gin + (int64_t)(j + r * TPX) * is2);
+            else v = ld_stream(gin + (int64_t)(j + r * TPX) * is2);
+        }
         re[r] = swap_in ? v.y : v.x;
         im[r] = swap_in ? v.x : v.y;
+        if (FLAVOR == 7) {          // chirp on the logical (re, im) value; padding stays zero
+            cplx<T> z; z.x = re[r]; z.y = im[r];
+            const int k = j + r * TPX;
+            if (k < p.n_in) z = cmul(z, ldg_c(reinterpret_cast<const cplx<T> *>(p.aux0) + k));
+            re[r] = z.x; im[r] = z.y;
+        }
+    }
+    for (rep = 0; rep < (FLAVOR == 7 ? 2 : 1); ++rep) {
+    if (FLAVOR == 7 && rep == 1) {
+        __syncthreads();            // first run's last-stage reads are complete
+#pragma unroll
+        for (int r = 0; r < E; ++r) { re[r] = bre[FLAVOR == 7 ? r : 0]; im[r] = bim[FLAVOR == 7 ? r : 0]; }
     }
     Butterfly<E, T>::run(re, im);
 #pragma unroll
@@ -251,8 +316,9 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             for (int i = 0; i < PER; ++i) {
                 const int b = j + i * TPX;
 #pragma unroll
-                for (int r = 0; r < R1; ++r) emit(b + r * E, re[i * R1 + r], im[i * R1 + r]);
+                for (int r = 0; r < R1; ++r) emit(b + r * E, i + PER * r, re[i * R1 + r], im[i * R1 + r]);
             }
+            if (FLAVOR == 7 && rep == 0) continue;
             flush_col();
             return;
         }
@@ -284,10 +350,11 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             }
             Butterfly<R2_, T>::run(xr, xi);
 #pragma unroll
-            for (int r = 0; r < R2; ++r) emit(b + r * NS, xr[r], xi[r]);
+            for (int r = 0; r < R2; ++r) emit(b + r * NS, i + PER * r, xr[r], xi[r]);
         }
-        flush_col();
+        if (!(FLAVOR == 7 && rep == 0)) flush_col();
     }
+    }   // rep
 }
 
 // ------------------------------------------------------------------ registry

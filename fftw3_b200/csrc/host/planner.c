@@ -180,8 +180,8 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
 #define NPIPE 3               /* persistent pipelined strided kernels (fft_pipe.cuh), widest tiles first */
-#define NFAST 12              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor
-                                 (12..17 uncapped registers, 18..23 capped for more resident CTAs) */
+#define NFAST 42              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor 0..6
+                                 (flavor 0 plain, 1 register-capped, 4-6 L2 prefetch-size loads for narrow COL tiles) */
 
 static int configure_variant(b2d_fft_pass *f, int variant)
 {
@@ -209,9 +209,11 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
         int code;
+        if (flavor == 2 || flavor == 3) return -1;        /* derived from the pass shape below, not selectable */
         /* pass shapes with their own specialised flavour (see device/fft_fast.cuh) */
         if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
+        else if (f->bluestein) { if (flavor) return -1; flavor = 7; }
         code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
