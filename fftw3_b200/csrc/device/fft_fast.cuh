@@ -114,6 +114,31 @@ __device__ __forceinline__ void load_twiddles(const cplx<T> *tw, int step, cplx<
     }
 }
 
+// Stage twiddles staged in shared memory once per CTA: the table entries a thread needs are
+// W^(m*k) for the multipliers m in {1,2,3} (and {4,8,..} for radices > 4); reading them with LDS
+// (~30 cycles) instead of LDG through L1/L2 (up to ~300 cycles) removes most long-scoreboard stalls.
+__host__ __device__ constexpr int tw_nmult(int R) { return R <= 1 ? 0 : (R <= 4 ? R - 1 : 3 + (R / 4 - 1)); }
+__host__ __device__ constexpr int tw_mult(int mi) { return mi < 3 ? mi + 1 : 4 * (mi - 2); }
+
+// w[r] for r = 1..R-1 from a shared table laid out [mi][count] (count entries per multiplier)
+template <int R, typename T>
+__device__ __forceinline__ void smem_twiddles(const cplx<T> *tab, int count, int k, cplx<T> (&w)[R])
+{
+    if (R <= 4) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r] = tab[(r - 1) * count + k];
+    } else {
+#pragma unroll
+        for (int c = 1; c < 4; ++c) w[c] = tab[(c - 1) * count + k];
+#pragma unroll
+        for (int a = 1; a < R / 4; ++a) {
+            w[4 * a] = tab[(2 + a) * count + k];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) w[4 * a + c] = cmul(w[4 * a], w[c]);
+        }
+    }
+}
+
 // padded row pitch for the ROW layout (same padding rule as the generic kernel)
 __host__ __device__ constexpr int padk_c(int k) { return k + (k >> 4); }
 __host__ __device__ constexpr int pitch_c(int n) { return ((padk_c(n - 1) + 1 + 14) / 16) * 16 + 1; }
@@ -123,7 +148,9 @@ struct FastCfg {
     static constexpr int TPX = N / E;
     static constexpr int THREADS = TPX * TPB;
     static constexpr int SMEM_ELEMS = COL ? N * TPB : pitch_c(N) * TPB;
-    static constexpr size_t SMEM_BYTES = (size_t)SMEM_ELEMS * sizeof(cplx<T>);
+    static constexpr int TW2_ELEMS = tw_nmult(R1) * E;            // stage-2 twiddles, index k < E
+    static constexpr int TW3_ELEMS = tw_nmult(R2) * (N / E);      // stage-3 twiddles, index j < TPX
+    static constexpr size_t SMEM_BYTES = (size_t)(SMEM_ELEMS + TW2_ELEMS + TW3_ELEMS) * sizeof(cplx<T>);
     // resident CTAs per SM we ask ptxas to make room for (register cap)
     static constexpr int BY_SMEM = (int)(232448 / (SMEM_BYTES + 1024)) > 0 ? (int)(232448 / (SMEM_BYTES + 1024)) : 1;
     static constexpr int BY_REGS = 65536 / (THREADS * (sizeof(T) == 8 ? (E >= 16 ? 84 : 56) : (E >= 32 ? 84 : (E >= 16 ? 56 : 40))));
@@ -163,6 +190,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
                              : reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re)) + boff_out / 2;
     const int64_t is2 = p.is / 2, os2 = p.os / 2;          // strides in complex units
     const cplx<T> *tw = reinterpret_cast<const cplx<T> *>(p.tw);
+    cplx<T> *tws2 = sm + Cfg::SMEM_ELEMS, *tws3 = tws2 + Cfg::TW2_ELEMS;
 
     // final-stage output of element kout of this thread's transform
     //   FLAVOR 2: four-step twiddle W_big^(kout * b0) fused into the store (two-level table)
@@ -254,6 +282,15 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             re[r] = z.x; im[r] = z.y;
         }
     }
+    // per-CTA twiddle tables: requested after the data loads so both are in flight together
+    {
+        constexpr int TSTEP2 = N / (E * R1);
+        for (int idx = tid; idx < Cfg::TW2_ELEMS; idx += Cfg::THREADS)
+            tws2[idx] = ldg_c(&tw[TSTEP2 * tw_mult(idx / E) * (idx % E)]);
+        for (int idx = tid; idx < Cfg::TW3_ELEMS; idx += Cfg::THREADS)
+            tws3[idx] = ldg_c(&tw[tw_mult(idx / TPX) * (idx % TPX)]);
+        // visible after the barrier that follows the stage-1 exchange writes
+    }
     for (rep = 0; rep < (FLAVOR == 7 ? 2 : 1); ++rep) {
     if (FLAVOR == 7 && rep == 1) {
         __syncthreads();            // first run's last-stage reads are complete
@@ -272,14 +309,13 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     {
         constexpr int NB = N / R1;            // butterflies per transform
         constexpr int PER = E / R1;           // butterflies per thread
-        constexpr int TSTEP = N / (E * R1);
         cplx<T> w[R1];
         // TPX % E == 0 for three-stage sizes: k = j % E for every butterfly of this thread
-        if (R2 > 1 || PER == 1) load_twiddles<R1, T>(tw, TSTEP * (j % E), w);
+        if (R2 > 1 || PER == 1) smem_twiddles<R1, T>(tws2, E, j % E, w);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int b = j + i * TPX;
-            if (R2 == 1 && PER > 1) load_twiddles<R1, T>(tw, TSTEP * (b % E), w);
+            if (R2 == 1 && PER > 1) smem_twiddles<R1, T>(tws2, E, b % E, w);
 #pragma unroll
             for (int r = 0; r < R1; ++r) {
                 cplx<T> v = sm[sidx(b + r * NB)];
@@ -331,7 +367,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         constexpr int PER = E / R2;
         constexpr int R2_ = R2 > 1 ? R2 : 2;
         cplx<T> w[R2_];
-        load_twiddles<R2_, T>(tw, j, w);
+        smem_twiddles<R2_, T>(tws3, TPX, j, w);
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             const int b = j + i * TPX;
