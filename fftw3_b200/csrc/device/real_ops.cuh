@@ -242,6 +242,37 @@ B2_HD void copy_elem(const b2d_copy &c, int64_t idx)
 }
 
 #ifdef __CUDACC__
+// Tiled transposing copy (kernel/transpose.c:24-190, kernel/tile2d.c, rdft/vrank3-transpose.c
+// analogue): when the dimension that is contiguous on the input side (da) is not the one that is
+// contiguous on the output side (db), move 32x32 tiles through shared memory so that both the
+// loads and the stores of a warp are contiguous.  V = one element (real, or a whole complex).
+template <typename V>
+__global__ void transpose_kernel(const __grid_constant__ b2d_copy c, int da, int db, int dc, int dd,
+                                 int64_t tiles_a, int64_t tiles_b)
+{
+    __shared__ V tile[32][33];
+    const int es = c.elem_reals;                        // strides are in reals; V spans es reals
+    int64_t blk = blockIdx.x;
+    const int64_t ta = blk % tiles_a; blk /= tiles_a;
+    const int64_t tb = blk % tiles_b; blk /= tiles_b;
+    const int64_t ic = blk % c.n[dc], id = blk / c.n[dc];
+    const int64_t rest_in = ic * c.is[dc] + id * c.is[dd], rest_out = ic * c.os[dc] + id * c.os[dd];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    const V *in = reinterpret_cast<const V *>(c.in);
+    V *out = reinterpret_cast<V *>(c.out);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t a = ta * 32 + tx, b = tb * 32 + ty + 8 * r;
+        if (a < c.n[da] && b < c.n[db]) tile[ty + 8 * r][tx] = in[(a * c.is[da] + b * c.is[db] + rest_in) / es];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t b = tb * 32 + tx, a = ta * 32 + ty + 8 * r;
+        if (a < c.n[da] && b < c.n[db]) out[(a * c.os[da] + b * c.os[db] + rest_out) / es] = tile[tx][ty + 8 * r];
+    }
+}
+
 template <typename T>
 __global__ void realop_kernel(const __grid_constant__ b2d_realop r, int len, int chunks)
 {

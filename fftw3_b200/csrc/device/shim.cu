@@ -226,6 +226,36 @@ int b2d_launch_copy(const b2d_copy *c)
     if (ensure_init()) return -1;
     int64_t total = c->n[0] * c->n[1] * c->n[2] * c->n[3];
     if (total <= 0) return 0;
+    {
+        /* transposing copy?  the input-contiguous and output-contiguous dims differ and all
+           offsets keep whole elements aligned -> 32x32 tiles through shared memory */
+        int da = -1, db = -1, dc = -1, dd = -1, i;
+        const int es = c->elem_reals;
+        const size_t vs = (size_t)es * (c->prec == B2D_F32 ? 4 : 8);
+        int ok = !c->npeer;
+        for (i = 0; i < 4; ++i) {
+            if (c->n[i] <= 1) continue;
+            if (llabs(c->is[i]) == es && da < 0) da = i;
+            if (llabs(c->os[i]) == es && db < 0) db = i;
+            if ((c->is[i] % es) || (c->os[i] % es)) ok = 0;
+        }
+        if (((uintptr_t)c->in % vs) || ((uintptr_t)c->out % vs)) ok = 0;
+        if (ok && da >= 0 && db >= 0 && da != db && c->n[da] >= 16 && c->n[db] >= 16 &&
+            c->is[da] > 0 && c->os[db] > 0) {
+            for (i = 0; i < 4; ++i) if (i != da && i != db) { if (dc < 0) dc = i; else dd = i; }
+            int64_t ta = (c->n[da] + 31) / 32, tb = (c->n[db] + 31) / 32;
+            int64_t nblk = ta * tb * c->n[dc] * c->n[dd];
+            if (nblk <= 2147483647LL) {
+                if (vs == 4) b2::transpose_kernel<float><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else if (vs == 8) b2::transpose_kernel<double><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else b2::transpose_kernel<double2><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                cudaError_t e2 = cudaGetLastError();
+                if (e2 != cudaSuccess) return fail(e2, "transpose_kernel launch");
+                g_launches++;
+                return 0;
+            }
+        }
+    }
     int64_t blocks = (total + 4 * 256 - 1) / (4 * 256);
     if (c->grid_limit > 0 && blocks > c->grid_limit) blocks = c->grid_limit;
     if (blocks > 2147483647LL) { snprintf(g_err, sizeof g_err, "copy grid too large"); return -1; }

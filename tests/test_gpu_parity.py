@@ -245,3 +245,28 @@ def test_every_specialised_kernel_variant(gpu_lib, variant, monkeypatch):
                                    ((1 << 19,), 2, False), ((256, 64, 36), 1, False)):
             err, tol = F.c2c(gpu_lib, prec, shape, howmany=hm, inplace=inplace, sign=-1 if variant % 2 else 1)
             assert err <= tol, (variant, prec, shape)
+
+
+def test_rank0_transposes(gpu_lib):
+    """rank-0 guru transforms are copies/transposes (rdft/rank0.c, kernel/transpose.c): exercised
+    here out of place (tiled transposing kernel) for real, complex-float and complex-double data."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((300, 200))
+    b = np.zeros((200, 300))
+    h = (B.Iodim * 2)(B.Iodim(300, 200, 1), B.Iodim(200, 1, 300))
+    p = gpu_lib.fn("d", "plan_guru_r2r")(0, None, 2, C.cast(h, C.c_void_p), a.ctypes.data, b.ctypes.data, None,
+                                         B.FFTW_ESTIMATE)
+    assert p
+    gpu_lib.execute("d", p)
+    gpu_lib.destroy_plan("d", p)
+    assert np.array_equal(b, a.T)
+    for prec in PRECS:
+        x = F.rand_complex(rng, (5, 70, 90), prec)
+        y = np.zeros((5, 90, 70), dtype=x.dtype)
+        p = gpu_lib.plan_guru_dft(prec, [], [(5, 6300, 6300), (70, 90, 1), (90, 1, 70)], x.ctypes.data, y.ctypes.data,
+                                  -1, B.FFTW_ESTIMATE)
+        assert p
+        gpu_lib.execute(prec, p)
+        gpu_lib.destroy_plan(prec, p)
+        assert np.array_equal(y, x.transpose(0, 2, 1))
