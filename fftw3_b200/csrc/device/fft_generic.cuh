@@ -132,6 +132,7 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
 template <typename T> struct Smem {
     int64_t *boff_in, *boff_out, *b0;
     cplx<T> *a, *b;
+    cplx<T> *tw;              // twiddle table copied into shared memory (NULL: read it from global)
     int pitch;
 };
 
@@ -147,6 +148,7 @@ B2_HD Smem<T> carve(const b2d_fft_pass &p, unsigned char *raw)
     s.pitch = row_pitch(p.n);
     s.a = (cplx<T> *)(raw + off);
     s.b = s.a + (size_t)p.tpb * s.pitch;
+    s.tw = p.tw_smem ? s.b + (size_t)p.tpb * s.pitch : (cplx<T> *)0;
     return s;
 }
 
@@ -155,7 +157,16 @@ inline size_t smem_bytes(const b2d_fft_pass &p)
 {
     size_t off = (size_t)3 * p.tpb * sizeof(int64_t);
     off = (off + 15) & ~(size_t)15;
-    return off + (size_t)2 * p.tpb * row_pitch(p.n) * sizeof(cplx<T>);
+    return off + ((size_t)2 * p.tpb * row_pitch(p.n) + (p.tw_smem ? (size_t)p.n : 0)) * sizeof(cplx<T>);
+}
+
+// phase: copy the twiddle table into shared memory (when the planner found room for it)
+template <typename T>
+B2_HD void phase_twiddles(const b2d_fft_pass &p, const Smem<T> &s, int tid, int nthreads)
+{
+    if (!s.tw) return;
+    const cplx<T> *g = (const cplx<T> *)p.tw;
+    for (int i = tid; i < p.n; i += nthreads) s.tw[i] = g[i];
 }
 
 // phase 0: per-transform base offsets (threads 0..tpb-1)
@@ -188,28 +199,49 @@ B2_HD void phase_load(const b2d_fft_pass &p, const Smem<T> &s, int tid, int nthr
 // one Stockham stage, radix R, src -> dst
 template <int R, typename T>
 B2_HD void stage_radix(const b2d_fft_pass &p, const cplx<T> *src, cplx<T> *dst, int pitch,
-                       int ns, int tid, int nthreads)
+                       int ns, int tid, int nthreads, const cplx<T> *tw)
 {
     const int n = p.n;
     const int nb = n / R;                 // butterflies per transform
-    const int total = nb * p.tpb;
-    const cplx<T> *tw = (const cplx<T> *)p.tw;
     const int tstep = n / (ns * R);       // W_n^(tstep * r * k) = exp(-2 pi i r k / (ns R))
-    for (int idx = tid; idx < total; idx += nthreads) {
-        int t = idx / nb;
-        int j = idx - t * nb;
-        const cplx<T> *x = src + (size_t)t * pitch;
-        cplx<T> *y = dst + (size_t)t * pitch;
-        int k = j % ns;
+    const bool ns_pow2 = (ns & (ns - 1)) == 0;
+    // thread -> (transform t, first butterfly jj): one division per stage, not per butterfly
+    const int tpx = nthreads / p.tpb > 0 ? nthreads / p.tpb : 1;
+    const int t = tid / tpx;
+    const int jj = tid - t * tpx;
+    if (t >= p.tpb) return;
+    const cplx<T> *x = src + (size_t)t * pitch;
+    cplx<T> *y = dst + (size_t)t * pitch;
+    for (int j = jj; j < nb; j += tpx) {
+        const int k = ns_pow2 ? (j & (ns - 1)) : (j % ns);
         T re[R], im[R];
+        cplx<T> w[R];
+        if (ns > 1) {
+            // two-level twiddles: W^(rk) = W^(4a k) W^(c k), r = 4a + c  (R/4 + 2 table reads, not R - 1)
+            const int base = tstep * k;
+            if (R <= 4) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) w[r] = tw[base * r];
+            } else {
+#pragma unroll
+                for (int c = 1; c < 4 && c < R; ++c) w[c] = tw[base * c];
+#pragma unroll
+                for (int a = 1; a <= (R - 1) / 4; ++a) {
+                    w[4 * a] = tw[base * 4 * a];
+#pragma unroll
+                    for (int c = 1; c < 4; ++c)
+                        if (4 * a + c < R) w[4 * a + c] = cmul(w[4 * a], w[c]);
+                }
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             cplx<T> v = x[padk(j + r * nb)];
-            if (r > 0 && ns > 1) v = cmul(v, tw[(size_t)tstep * r * k]);
+            if (r > 0 && ns > 1) v = cmul(v, w[r]);
             re[r] = v.x; im[r] = v.y;
         }
         Butterfly<R, T>::run(re, im);
-        int j0 = (j - k) * R + k;
+        const int j0 = (j - k) * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             cplx<T> v; v.x = re[r]; v.y = im[r];
@@ -220,22 +252,22 @@ B2_HD void stage_radix(const b2d_fft_pass &p, const cplx<T> *src, cplx<T> *dst, 
 
 template <typename T>
 B2_HD void phase_stage(const b2d_fft_pass &p, int stage, int ns, const cplx<T> *src, cplx<T> *dst,
-                       int pitch, int tid, int nthreads)
+                       int pitch, int tid, int nthreads, const cplx<T> *tw)
 {
     switch (p.radix[stage]) {
-    case 2:  stage_radix<2, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 3:  stage_radix<3, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 4:  stage_radix<4, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 5:  stage_radix<5, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 6:  stage_radix<6, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 7:  stage_radix<7, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 8:  stage_radix<8, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 9:  stage_radix<9, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 10: stage_radix<10, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 11: stage_radix<11, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 12: stage_radix<12, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 13: stage_radix<13, T>(p, src, dst, pitch, ns, tid, nthreads); break;
-    case 16: stage_radix<16, T>(p, src, dst, pitch, ns, tid, nthreads); break;
+    case 2:  stage_radix<2, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 3:  stage_radix<3, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 4:  stage_radix<4, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 5:  stage_radix<5, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 6:  stage_radix<6, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 7:  stage_radix<7, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 8:  stage_radix<8, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 9:  stage_radix<9, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 10: stage_radix<10, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 11: stage_radix<11, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 12: stage_radix<12, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 13: stage_radix<13, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
+    case 16: stage_radix<16, T>(p, src, dst, pitch, ns, tid, nthreads, tw); break;
     default: break;
     }
 }
@@ -284,6 +316,8 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
     const Smem<T> s = carve<T>(p, smem_raw);
     const TileCtx c = decode_block(p, (int64_t)blockIdx.x);
     phase_offsets<T>(p, s, c, tid);
+    phase_twiddles<T>(p, s, tid, nthreads);
+    const cplx<T> *twp = s.tw ? s.tw : (const cplx<T> *)p.tw;
     __syncthreads();
     phase_load<T>(p, s, tid, nthreads);
     __syncthreads();
@@ -292,7 +326,7 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
     for (int rep = 0; rep < reps; ++rep) {
         int ns = 1;
         for (int st = 0; st < p.nstages; ++st) {
-            phase_stage<T>(p, st, ns, src, dst, s.pitch, tid, nthreads);
+            phase_stage<T>(p, st, ns, src, dst, s.pitch, tid, nthreads, twp);
             __syncthreads();
             ns *= p.radix[st];
             cplx<T> *tmp = src; src = dst; dst = tmp;

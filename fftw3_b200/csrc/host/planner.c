@@ -228,6 +228,14 @@ static int configure_variant(b2d_fft_pass *f, int variant)
     if (ns == 0) return -1;
     f->nstages = ns < 0 ? 0 : ns;
     fill_geometry(f, variant);
+    /* twiddle table in shared memory when it fits next to the data (and leaves room for a second CTA
+       when the data alone would) */
+    f->tw_smem = 0;
+    {
+        size_t base = b2d_fft_pass_smem(f), tws = (size_t)f->n * 2 * real_size(f->prec);
+        size_t cap = b2d_max_smem_per_block();
+        if (base + tws <= cap && (base > cap / 2 || base + tws <= cap / 2)) f->tw_smem = 1;
+    }
     if (b2d_fft_pass_smem(f) > b2d_max_smem_per_block()) return -1;
     return 0;
 }

@@ -80,6 +80,7 @@ typedef struct b2d_fft_pass {
     /* 0: one CTA per tile.  > 0: launch at most this many CTAs, which loop over the
        tiles -- used to keep an NVLink-bound pass from occupying every SM */
     int grid_limit;
+    int tw_smem;              /* generic kernel: stage the n-entry twiddle table in shared memory */
 } b2d_fft_pass;
 
 /* strided N-d copy / rank-0 transform (kernel/cpy2d.c, rdft/rank0.c analogue);

@@ -39,13 +39,15 @@ static void run_fft_pass(const b2d_fft_pass &p)
         Smem<T> s = carve<T>(p, base);
         TileCtx c = decode_block(p, blk);
         for (int t = 0; t < nthreads; ++t) phase_offsets<T>(p, s, c, t);
+        for (int t = 0; t < nthreads; ++t) phase_twiddles<T>(p, s, t, nthreads);
+        const cplx<T> *twp = s.tw ? s.tw : (const cplx<T> *)p.tw;
         for (int t = 0; t < nthreads; ++t) phase_load<T>(p, s, t, nthreads);
         cplx<T> *src = s.a, *dst = s.b;
         int reps = p.bluestein ? 2 : 1;
         for (int rep = 0; rep < reps; ++rep) {
             int ns = 1;
             for (int st = 0; st < p.nstages; ++st) {
-                for (int t = 0; t < nthreads; ++t) phase_stage<T>(p, st, ns, src, dst, s.pitch, t, nthreads);
+                for (int t = 0; t < nthreads; ++t) phase_stage<T>(p, st, ns, src, dst, s.pitch, t, nthreads, twp);
                 ns *= p.radix[st];
                 cplx<T> *tmp = src; src = dst; dst = tmp;
             }
