@@ -181,6 +181,84 @@ B2_HD void phase_offsets(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx 
     }
 }
 
+// Plain c2c fast path of the generic kernel: interleaved complex on both sides, no fused ops.
+// Decided per launch (pointer deltas and alignment are run-time facts).
+B2_HD bool plain_ok(const b2d_fft_pass &p, int *swap_in, int *swap_out)
+{
+    const int64_t rs = p.prec == B2D_F32 ? 4 : 8;
+    if (p.pre_op || p.post_op || p.bluestein || p.npeer) return false;
+    const int64_t din = (const char *)p.in_im - (const char *)p.in_re;
+    const int64_t dout = (const char *)p.out_im - (const char *)p.out_re;
+    if ((din != rs && din != -rs) || (dout != rs && dout != -rs)) return false;
+    *swap_in = din < 0; *swap_out = dout < 0;
+    if (((uintptr_t)(din < 0 ? p.in_im : p.in_re) % (2 * rs)) || ((uintptr_t)(dout < 0 ? p.out_im : p.out_re) % (2 * rs))) return false;
+    if ((p.is & 1) || (p.os & 1)) return false;
+    for (int i = 0; i < B2D_MAX_BATCH_DIMS; ++i) if ((p.bis[i] & 1) || (p.bos[i] & 1)) return false;
+    return true;
+}
+
+// vector load / store phases of the plain path: one 128-bit (f64) access per element and no
+// per-element division (lanes walk k in ROW mode, t in COL mode)
+template <typename T>
+B2_HD void phase_load_plain(const b2d_fft_pass &p, const Smem<T> &s, int tid, int nthreads, int swap)
+{
+    const int n = p.n, tpb = p.tpb;
+    const cplx<T> *g = (const cplx<T> *)(swap ? p.in_im : p.in_re);
+    const int64_t is2 = p.is / 2;
+    if (!p.load_col || (nthreads % tpb) != 0) {
+        for (int t = 0; t < tpb; ++t) {
+            if (s.b0[t] < 0) continue;
+            const cplx<T> *gl = g + s.boff_in[t] / 2;
+            cplx<T> *row = s.a + (size_t)t * s.pitch;
+            for (int k = tid; k < n; k += nthreads) {
+                cplx<T> v = gl[(int64_t)k * is2];
+                if (swap) { T u = v.x; v.x = v.y; v.y = u; }
+                row[padk(k)] = v;
+            }
+        }
+    } else {
+        const int t = tid % tpb, step = nthreads / tpb;
+        if (s.b0[t] < 0) return;
+        const cplx<T> *gl = g + s.boff_in[t] / 2;
+        cplx<T> *row = s.a + (size_t)t * s.pitch;
+        for (int k = tid / tpb; k < n; k += step) {
+            cplx<T> v = gl[(int64_t)k * is2];
+            if (swap) { T u = v.x; v.x = v.y; v.y = u; }
+            row[padk(k)] = v;
+        }
+    }
+}
+
+template <typename T>
+B2_HD void phase_store_plain(const b2d_fft_pass &p, const Smem<T> &s, const cplx<T> *src, int tid, int nthreads, int swap)
+{
+    const int n = p.n, tpb = p.tpb;
+    cplx<T> *g = (cplx<T> *)(swap ? p.out_im : p.out_re);
+    const int64_t os2 = p.os / 2;
+    if (!p.store_col || (nthreads % tpb) != 0) {
+        for (int t = 0; t < tpb; ++t) {
+            if (s.b0[t] < 0) continue;
+            cplx<T> *gl = g + s.boff_out[t] / 2;
+            const cplx<T> *row = src + (size_t)t * s.pitch;
+            for (int k = tid; k < n; k += nthreads) {
+                cplx<T> v = row[padk(k)];
+                if (swap) { T u = v.x; v.x = v.y; v.y = u; }
+                gl[(int64_t)k * os2] = v;
+            }
+        }
+    } else {
+        const int t = tid % tpb, step = nthreads / tpb;
+        if (s.b0[t] < 0) return;
+        cplx<T> *gl = g + s.boff_out[t] / 2;
+        const cplx<T> *row = src + (size_t)t * s.pitch;
+        for (int k = tid / tpb; k < n; k += step) {
+            cplx<T> v = row[padk(k)];
+            if (swap) { T u = v.x; v.x = v.y; v.y = u; }
+            gl[(int64_t)k * os2] = v;
+        }
+    }
+}
+
 // phase 1: global -> shared (buffer a)
 template <typename T>
 B2_HD void phase_load(const b2d_fft_pass &p, const Smem<T> &s, int tid, int nthreads)
@@ -308,8 +386,8 @@ B2_HD void phase_store(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx &c
 }
 
 #ifdef __CUDACC__
-template <typename T>
-__global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
+template <typename T, bool PLAIN>
+__global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -319,7 +397,8 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
     phase_twiddles<T>(p, s, tid, nthreads);
     const cplx<T> *twp = s.tw ? s.tw : (const cplx<T> *)p.tw;
     __syncthreads();
-    phase_load<T>(p, s, tid, nthreads);
+    if (PLAIN) phase_load_plain<T>(p, s, tid, nthreads, swap_in);
+    else phase_load<T>(p, s, tid, nthreads);
     __syncthreads();
     cplx<T> *src = s.a, *dst = s.b;
     const int reps = p.bluestein ? 2 : 1;
@@ -336,7 +415,8 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p)
             __syncthreads();
         }
     }
-    phase_store<T>(p, s, c, src, tid, nthreads);
+    if (PLAIN) phase_store_plain<T>(p, s, src, tid, nthreads, swap_out);
+    else phase_store<T>(p, s, c, src, tid, nthreads);
 }
 #endif
 

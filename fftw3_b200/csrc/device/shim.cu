@@ -44,10 +44,10 @@ int ensure_init()
     strncpy(g_name, prop.name, sizeof g_name - 1);
     g_sms = prop.multiProcessorCount;
     g_max_smem = prop.sharedMemPerBlockOptin;
-    cudaFuncSetAttribute(b2::fft_generic_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)g_max_smem);
-    cudaFuncSetAttribute(b2::fft_generic_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)g_max_smem);
+    cudaFuncSetAttribute(b2::fft_generic_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+    cudaFuncSetAttribute(b2::fft_generic_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+    cudaFuncSetAttribute(b2::fft_generic_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+    cudaFuncSetAttribute(b2::fft_generic_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
     b2fast::init((int)g_max_smem);
     return 0;
 }
@@ -211,10 +211,15 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     int threads = p->tpb * p->tpx;
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
-    if (p->prec == B2D_F32)
-        b2::fft_generic_kernel<float><<<(unsigned)blocks, threads, smem, g_stream>>>(*p);
-    else
-        b2::fft_generic_kernel<double><<<(unsigned)blocks, threads, smem, g_stream>>>(*p);
+    int swi = 0, swo = 0;
+    const bool plain = b2::plain_ok(*p, &swi, &swo);
+    if (p->prec == B2D_F32) {
+        if (plain) b2::fft_generic_kernel<float, true><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, swi, swo);
+        else b2::fft_generic_kernel<float, false><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, 0, 0);
+    } else {
+        if (plain) b2::fft_generic_kernel<double, true><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, swi, swo);
+        else b2::fft_generic_kernel<double, false><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, 0, 0);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(e, "fft_generic_kernel launch");
     g_launches++;

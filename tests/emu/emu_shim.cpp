@@ -41,7 +41,11 @@ static void run_fft_pass(const b2d_fft_pass &p)
         for (int t = 0; t < nthreads; ++t) phase_offsets<T>(p, s, c, t);
         for (int t = 0; t < nthreads; ++t) phase_twiddles<T>(p, s, t, nthreads);
         const cplx<T> *twp = s.tw ? s.tw : (const cplx<T> *)p.tw;
-        for (int t = 0; t < nthreads; ++t) phase_load<T>(p, s, t, nthreads);
+        int swi = 0, swo = 0;
+        const bool plain = plain_ok(p, &swi, &swo);     // same per-launch decision as shim.cu
+        for (int t = 0; t < nthreads; ++t) {
+            if (plain) phase_load_plain<T>(p, s, t, nthreads, swi); else phase_load<T>(p, s, t, nthreads);
+        }
         cplx<T> *src = s.a, *dst = s.b;
         int reps = p.bluestein ? 2 : 1;
         for (int rep = 0; rep < reps; ++rep) {
@@ -54,7 +58,9 @@ static void run_fft_pass(const b2d_fft_pass &p)
             if (p.bluestein && rep == 0)
                 for (int t = 0; t < nthreads; ++t) phase_pointwise<T>(p, src, s.pitch, t, nthreads);
         }
-        for (int t = 0; t < nthreads; ++t) phase_store<T>(p, s, c, src, t, nthreads);
+        for (int t = 0; t < nthreads; ++t) {
+            if (plain) phase_store_plain<T>(p, s, src, t, nthreads, swo); else phase_store<T>(p, s, c, src, t, nthreads);
+        }
     }
 }
 
