@@ -270,3 +270,59 @@ def test_rank0_transposes(gpu_lib):
         gpu_lib.execute(prec, p)
         gpu_lib.destroy_plan(prec, p)
         assert np.array_equal(y, x.transpose(0, 2, 1))
+
+
+def _random_problems(seed, count):
+    """Random problem strings in the reference harness' mini-language
+    (libbench2/problem.c:229-318): rank 1-3, sizes built from factors <= 13 plus the odd
+    prime, interleaved ('v') and external ('*') batches, c2c / r2c / c2r / r2r with random kinds."""
+    rng = np.random.default_rng(seed)
+    kinds = ["f", "b", "h", "e00", "e01", "e10", "e11", "o00", "o01", "o10", "o11"]
+    out = []
+    for _ in range(count):
+        rank = int(rng.integers(1, 4))
+        budget = 20000 ** (1.0 / rank)
+        dims = []
+        for _ in range(rank):
+            n = 1
+            while True:
+                f = int(rng.choice([2, 2, 2, 3, 3, 4, 5, 7, 8, 11, 13, 16]))
+                if n * f > budget:
+                    break
+                n *= f
+                if rng.random() < 0.25:
+                    break
+            if rng.random() < 0.08:
+                n = int(rng.choice([17, 19, 23, 31, 37, 101, 127]))
+            dims.append(max(n, 2))
+        fam = str(rng.choice(["c", "c", "r", "k"]))
+        s = ("i" if rng.random() < 0.5 else "o") + fam
+        if fam != "k":
+            s += "f" if rng.random() < 0.5 else "b"
+            body = "x".join(str(d) for d in dims)
+        else:
+            body = "x".join("%d%s" % (max(d, 3), rng.choice(kinds)) for d in dims)
+        s += body
+        r = rng.random()
+        if r < 0.3:
+            s += "v%d" % int(rng.integers(2, 9))
+        elif r < 0.6:
+            s += "*%d" % int(rng.integers(2, 9))
+        out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_reference_verifier_random_problems(gpu_lib, prec):
+    """The reference's self-checker on seeded random problems (what its tests/check.pl -r does),
+    against the product library on the real GPU."""
+    exe = _bench(prec)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bench_b200 not prebuilt")
+    probs = _random_problems(20261017 if prec == "d" else 7, 120)
+    for i in range(0, len(probs), 30):
+        args = [exe, "-oestimate"]
+        for pr in probs[i:i + 30]:
+            args += ["--verify", pr]
+        r = subprocess.run(args, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (probs[i:i + 30], r.stdout[-1500:], r.stderr[-1500:])
