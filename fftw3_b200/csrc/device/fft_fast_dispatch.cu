@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include "fft_fast.cuh"
 #include "fft_pipe.cuh"
+#include "fft_tma.cuh"
 
 namespace b2pipe {
 extern const PipeEntry pipe_table[];
@@ -20,7 +21,7 @@ static int g_sms = 148;
 // persistent pipelined COL kernels (fft_pipe.cuh): kernel code 5000 + tile width
 static const b2pipe::PipeEntry *pipe_entry_for(const b2d_fft_pass &p)
 {
-    if (p.kernel < 5000) return nullptr;
+    if (p.kernel < 5000 || p.kernel >= 6000) return nullptr;
     if (p.pre_op || p.post_op || p.bluestein || p.npeer) return nullptr;
     if (!p.load_col || !p.store_col || p.bis[0] != 2 || p.bos[0] != 2) return nullptr;
     if ((p.is & 1) || (p.os & 1)) return nullptr;
@@ -47,6 +48,7 @@ static const FastEntry *find(int prec, int n, int col, int code)
 void init(int max_smem)
 {
     g_max_smem = max_smem;
+    b2tma::init(max_smem);
     {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
@@ -99,12 +101,14 @@ int available(const b2d_fft_pass &p, int code)
 {
     b2d_fft_pass q = p;
     q.kernel = code;
+    if (code >= 6000) return b2tma::entry_for(q) != nullptr;
     if (code >= 5000) return pipe_entry_for(q) != nullptr;
     return entry_for(q) != nullptr;
 }
 
 size_t smem_bytes(const b2d_fft_pass &p)
 {
+    if (p.kernel >= 6000) { const b2tma::TmaEntry *te = b2tma::entry_for(p); return te ? te->smem : 0; }
     if (p.kernel >= 5000) { const b2pipe::PipeEntry *pe = pipe_entry_for(p); return pe ? pe->smem : 0; }
     const FastEntry *e = entry_for(p);
     return e ? e->smem : 0;
@@ -112,6 +116,7 @@ size_t smem_bytes(const b2d_fft_pass &p)
 
 int try_launch(const b2d_fft_pass &p, cudaStream_t st)
 {
+    if (p.kernel >= 6000) return b2tma::try_launch(p, st);
     if (p.kernel >= 5000) {
         const b2pipe::PipeEntry *pe = pipe_entry_for(p);
         if (!pe) return 1;

@@ -180,6 +180,7 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
 #define NPIPE 3               /* persistent pipelined strided kernels (fft_pipe.cuh), widest tiles first */
+#define NTMA 12               /* TMA-fed persistent strided kernels (fft_tma.cuh): 2 tile widths x (3 L2-promotion sizes x tiles single/paired) */
 #define NFAST 42              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor 0..6
                                  (flavor 0 plain, 1 register-capped, 4-6 L2 prefetch-size loads for narrow COL tiles) */
 
@@ -187,6 +188,25 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
+    if (variant >= NVARIANTS + NFAST + NPIPE) {
+        /* TMA-fed persistent strided kernels: k / 6 = which of the table's tile widths (widest first),
+           k % 6 = L2 promotion of the tensor map (none, 128 B, 256 B), +3 when a CTA takes tiles in adjacent pairs */
+        int k = variant - (NVARIANTS + NFAST + NPIPE), tpb, seen = 0;
+        if (k >= NTMA) return -1;
+        for (tpb = 32; tpb >= 2; --tpb) {
+            int code = 6000 + 100 * (k % 6) + tpb;
+            if (!b2d_fast_available(f, code)) continue;
+            if (seen++ == k / 6) {
+                ns = b2_factorize(f->n, f->prec, 0, f->radix);
+                if (ns == 0) return -1;
+                f->nstages = ns < 0 ? 0 : ns;
+                fill_geometry(f, 0);
+                f->kernel = code;
+                return 0;
+            }
+        }
+        return -1;
+    }
     if (variant >= NVARIANTS + NFAST) {
         /* persistent cp.async-pipelined strided kernels: tile widths are whatever the table holds;
            variant k tries the k-th widest */
@@ -381,6 +401,8 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         if (!have && b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
         if (!have && pat >= 1) {
+            /* the TMA-fed kernels (variants >= NVARIANTS + NFAST + NPIPE) are not searched: measured no
+               faster than the register-resident ones -- FFTW3_B200_FORCE_VARIANT only */
             int v, nv = NVARIANTS + NFAST + NPIPE, bestv = -1;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
@@ -402,7 +424,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
                             f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
                             (long long)f->bn[1], (long long)f->bn[2], v,
-                            trial.kernel >= 5000 ? "pipelined" : (trial.kernel ? "codelet" : "generic"),
+                            trial.kernel >= 6000 ? "tma" : trial.kernel >= 5000 ? "pipelined" : (trial.kernel ? "codelet" : "generic"),
                             trial.kernel ? trial.kernel % 100 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
                 }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
@@ -1311,7 +1333,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel >= 5000) fprintf(f, "pipelined-tile=%d", q->kernel - 5000);
+            if (q->kernel >= 6000) fprintf(f, "tma-tile=%d/l2p%d", q->kernel % 100, (q->kernel / 100) % 10);
+            else if (q->kernel >= 5000) fprintf(f, "pipelined-tile=%d", q->kernel - 5000);
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",

@@ -234,10 +234,10 @@ def test_inplace_transpose_and_stride_change(gpu_lib):
     assert O.rel_l2(x.T, O.dft(x0)) <= F.tol_for("d", (96, 96))
 
 
-@pytest.mark.parametrize("variant", list(range(12, 24)) + list(range(36, 57)))
+@pytest.mark.parametrize("variant", list(range(12, 24)) + list(range(36, 69)))
 def test_every_specialised_kernel_variant(gpu_lib, variant, monkeypatch):
     """Pin each specialised-kernel variant of the planner (tile widths x flavours of
-    fft_fast.cuh, pipelined kernels of fft_pipe.cuh) and check parity on shapes that exercise
+    fft_fast.cuh, pipelined kernels of fft_pipe.cuh, TMA-fed kernels of fft_tma.cuh) and check parity on shapes that exercise
     ROW, COL, four-step (fused twiddle store, transposed store) and partial tiles."""
     monkeypatch.setenv("FFTW3_B200_FORCE_VARIANT", str(variant))
     for prec in PRECS:
