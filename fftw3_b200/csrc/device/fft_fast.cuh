@@ -181,7 +181,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     const int64_t b0 = c.tile0 * TPB + t;
     const bool valid = b0 < p.bn[0];
     const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
-    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
+    const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + ((p.npeer && FLAVOR != 8) ? 0 : c.b2 * p.bos[2]);
     // interleaved data: vector pointer at the lower of (re, im)
     const cplx<T> *gin = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re) + boff_in / 2;
     // peer scatter: batch dim 2 selects the destination buffer (a peer GPU's exchange
@@ -196,6 +196,8 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     //   FLAVOR 2: four-step twiddle W_big^(kout * b0) fused into the store (two-level table)
     //   FLAVOR 3: ROW tile stored in COL order: park the result in shared memory (same
     //             position the thread just read), the CTA streams it out below
+    //   FLAVOR 8: COL kernel whose output ROWS are split over peer GPUs (row k -> peer k / peer_rows):
+    //             the second exchange of a distributed transform fused into its last pass
     //   FLAVOR 7: Bluestein in one CTA (dft/bluestein.c:82-128): the stages run twice; the first
     //             run's outputs are multiplied by B = FFT(filter), conjugated and kept in registers
     //             -- output b + r*Ns of the last stage IS input j + q*TPX of the next first stage,
@@ -233,6 +235,12 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         if (FLAVOR == 3) {
             o.x = vr; o.y = vi;
             sm[sidx(kout)] = o;
+        } else if (FLAVOR == 8) {
+            o.x = swap_out ? vi : vr;
+            o.y = swap_out ? vr : vi;
+            const int peer = p.tw4_shift >= 0 ? (kout >> p.tw4_shift) : kout / p.peer_rows;
+            const int krow = kout - peer * p.peer_rows;
+            if (valid) st_stream(reinterpret_cast<cplx<T> *>(p.peer_out[peer]) + boff_out / 2 + (int64_t)krow * os2, o);
         } else {
             o.x = swap_out ? vi : vr;
             o.y = swap_out ? vr : vi;

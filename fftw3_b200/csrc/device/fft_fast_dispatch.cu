@@ -81,8 +81,10 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
     } else if (p.pre_op || p.bluestein) return nullptr;
     if (flavor == 7) { /* ops checked above */ }
     else if (flavor == 2) { if (p.post_op != B2D_STORE_TWIDDLE4 || !p.load_col || !p.store_col) return nullptr; }
+    else if (flavor == 8) { if (p.post_op || !p.npeer || p.peer_rows <= 0 || !p.load_col || !p.store_col) return nullptr; }
     else if (p.post_op) return nullptr;
     if (flavor >= 4 && flavor <= 6 && !col) return nullptr;                          // L2-prefetch flavours: COL kernels only
+    if ((flavor == 8) != (p.npeer && p.peer_rows > 0)) return nullptr;               // row-split stores: flavour 8 only
     if (flavor == 3) { if (p.load_col || !p.store_col || p.npeer) return nullptr; }
     else if (p.load_col != p.store_col || col != p.load_col) return nullptr;
     if ((p.is & 1) || (p.os & 1)) return nullptr;

@@ -105,7 +105,8 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
 {
     T *re = (T *)p.out_re;
     T *im = (T *)p.out_im;
-    if (p.npeer) {            // batch dim 2 selects the destination buffer (peer GPU), interleaved
+    if (p.npeer) {            // batch dim 2 (or the output row) selects the destination buffer (peer GPU), interleaved
+        if (p.peer_rows) { peer = k / p.peer_rows; k -= (int)(peer * p.peer_rows); }
         T *base = (T *)p.peer_out[peer];
         if ((const char *)p.out_im < (const char *)p.out_re) { im = base; re = base + 1; }   // backward: swapped
         else { re = base; im = base + 1; }
@@ -177,7 +178,7 @@ B2_HD void phase_offsets(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx 
         int64_t b0 = c.tile0 * p.tpb + tid;
         s.b0[tid] = (b0 < p.bn[0]) ? b0 : -1;
         s.boff_in[tid] = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
-        s.boff_out[tid] = b0 * p.bos[0] + c.b1 * p.bos[1] + (p.npeer ? 0 : c.b2 * p.bos[2]);
+        s.boff_out[tid] = b0 * p.bos[0] + c.b1 * p.bos[1] + ((p.npeer && !p.peer_rows) ? 0 : c.b2 * p.bos[2]);
     }
 }
 

@@ -166,6 +166,24 @@ void *b2d_ipc_import(const unsigned char handle[64])
     return p;
 }
 void b2d_ipc_close(void *devptr) { if (devptr) cudaIpcCloseMemHandle(devptr); }
+int64_t b2d_alloc_offset(const void *devptr)
+{
+    // cuMemGetAddressRange through the runtime's driver entry point (the library does not link libcuda)
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static range_fn fn = nullptr;
+    if (ensure_init()) return -1;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return -1; }
+        fn = (range_fn)f;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)devptr) != 0) return -1;
+    return (int64_t)((unsigned long long)(uintptr_t)devptr - base);
+}
 
 int b2d_timer_start(void)
 {

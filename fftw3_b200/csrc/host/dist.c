@@ -18,6 +18,9 @@
  *   stage 1  Z: FFT along n0 reading the received blocks, which already form
  *               [n0][local_n1][n2]; written in place (natural order follows) or
  *               as [local_n1][n0][n2] into `local` (TRANSPOSED_OUT)
+ *            or (push plans) with its output ROWS stored straight into the owners' slabs:
+ *               row k0 belongs to rank k0 / block, so the second exchange is fused into
+ *               the stores of this pass as well and there is no stage 2
  *   stage 2     gather the blocks back into [local_n0][n1][n2] (peer loads).
  *               Stages 1 and 2 are cut into chunks of columns so that the
  *               gather of chunk c overlaps Z of chunk c+1; the caller puts a
@@ -122,9 +125,9 @@ static int chunks_for(int64_t n)
     return c;
 }
 
-dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
-                                 C *local, C *zbuf, void *const *push_targets, void *const *pull_sources,
-                                 int sign, unsigned flags)
+static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                    C *local, C *zbuf, void *const *push_targets, void *const *pull_sources,
+                    void *const *out_targets, int sign, unsigned flags)
 {
     dplan p;
     b2_problem q;
@@ -139,6 +142,7 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
     p = (dplan)calloc(1, sizeof *p);
     if (!p) return NULL;
     p->nranks = nranks; p->rank = rank;
+    if (out_targets && (pull_sources || nranks > B2D_MAX_PEERS || b2d_pointer_is_device(zbuf) != 1)) { free(p); return NULL; }
     p->nstages = pull_sources ? 3 : 2;
     p->c0 = ln0 > 0 ? chunks_for(ln0) : 1;
     p->c1 = pull_sources ? chunks_for(b1) : 1;     /* from the block size: identical on every rank */
@@ -191,8 +195,8 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
         /* columns (k1', k2) of this chunk: k1' in [lo, lo + cnt) */
         int64_t lo = ln1 * c / p->c1, cnt = ln1 * (c + 1) / p->c1 - lo;
         init_problem(&q, flags);
-        if (pull_sources) {
-            /* Z in place on zbuf = [n0][ln1][n2] */
+        if (pull_sources || out_targets) {
+            /* Z in place on zbuf = [n0][ln1][n2] (push plans: planned like this, stores redirected below) */
             dim(&q.sz, n0, 2 * ln1 * n2, 2 * ln1 * n2);
             dim(&q.vecsz, cnt * n2, 2, 2);
             set_ptrs(&q, (double *)zbuf + 2 * lo * n2, (double *)zbuf + 2 * lo * n2, sign);
@@ -205,6 +209,25 @@ dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int r
         }
         p->z[c] = b2_mkplan(&q);
         if (!p->z[c]) goto fail;
+        if (out_targets && !p->z[c]->is_nop) {
+            /* push: row k0 of every column goes to its owner rank k0 / b0, into that rank's
+               slab [ln0(owner)][n1][n2] at (k0 % b0, my first column + k1', k2) */
+            b2_plan *zp = p->z[c];
+            b2d_fft_pass *f;
+            int64_t b0 = blk(n0, nranks), s1 = b1 * rank;
+            int k, tile;
+            if (zp->nsteps != 1 || zp->steps[0].kind != STEP_FFT) goto fail;     /* multi-pass n0: use the gather plan */
+            f = &zp->steps[0].u.fft;
+            if (f->pre_op || f->post_op || f->bluestein || f->bn[1] != 1 || f->bn[2] != 1 || f->bos[0] != 2) goto fail;
+            f->npeer = nranks;
+            f->peer_rows = (int)b0;
+            for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)out_targets[k] + 2 * (s1 + lo) * n2;
+            f->os = 2 * n1 * n2;
+            f->tw4_shift = -1;
+            if ((b0 & (b0 - 1)) == 0) { int sh = 0; while (((int64_t)1 << sh) < b0) ++sh; f->tw4_shift = sh; }
+            tile = f->kernel >= 1000 && f->kernel < 5000 ? f->kernel % 100 : 0;
+            f->kernel = (tile && b2d_fast_available(f, 1800 + tile)) ? 1800 + tile : 0;
+        }
     }
     if (pull_sources) {
         /* gather back: block from rank s = [ln0][l1(s)][n2] -> local[i0][s*b1 + k1'][k2];
@@ -229,6 +252,26 @@ fail:
     fftw_b200_dist_destroy_plan(p);
     return NULL;
 }
+
+dplan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                 C *local, C *zbuf, void *const *push_targets, void *const *pull_sources,
+                                 int sign, unsigned flags)
+{
+    return mkdist(n0, n1, n2, rank, nranks, local, zbuf, push_targets, pull_sources, NULL, sign, flags);
+}
+
+/* natural-order output with BOTH exchanges fused into pass stores (no gather stage):
+   out_targets[d] = rank d's slab `local` (peer-mapped).  NULL when the dim-0 transform
+   needs more than one pass; the caller then uses the gather plan. */
+dplan fftw_b200_dist_plan_dft_3d_push(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                      C *local, C *zbuf, void *const *push_targets, void *const *out_targets,
+                                      int sign, unsigned flags)
+{
+    if (!out_targets) return NULL;
+    return mkdist(n0, n1, n2, rank, nranks, local, zbuf, push_targets, NULL, out_targets, sign, flags);
+}
+
+ptrdiff_t fftw_b200_ipc_offset(void *devptr) { return (ptrdiff_t)b2d_alloc_offset(devptr); }
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
 int fftw_b200_dist_num_chunks(const dplan p, int stage) { return stage == 0 ? p->c0 : p->c1; }

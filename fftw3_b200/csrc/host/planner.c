@@ -230,6 +230,8 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         int flavor = (variant - NVARIANTS) / 6;
         int code;
         if (flavor == 2 || flavor == 3) return -1;        /* derived from the pass shape below, not selectable */
+        if (f->npeer && f->peer_rows > 0) { if (flavor) return -1; flavor = 8; }      /* row-split peer stores */
+        else
         /* pass shapes with their own specialised flavour (see device/fft_fast.cuh) */
         if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }

@@ -17,6 +17,7 @@ Exchange paths
                     the CPU unit tests).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -37,6 +38,10 @@ def _declare(lib):
     L.fftw_b200_dist_local_size_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, SP, SP, SP, SP]
     L.fftw_b200_dist_plan_dft_3d.restype = P
     L.fftw_b200_dist_plan_dft_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
+    L.fftw_b200_dist_plan_dft_3d_push.restype = P
+    L.fftw_b200_dist_plan_dft_3d_push.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
+    L.fftw_b200_ipc_offset.restype = C.c_ssize_t
+    L.fftw_b200_ipc_offset.argtypes = [P]
     L.fftw_b200_dist_num_stages.argtypes = [P]
     L.fftw_b200_dist_execute_stage.argtypes = [P, I]
     L.fftw_b200_dist_num_chunks.argtypes = [P, I]
@@ -99,22 +104,44 @@ class SlabPlan3D:
         b0, b1 = _blk(n0, P), _blk(n1, P)
         self._owned = []
         self._opened = []
+        self.push = False
+        out_arr = None
         # chunk (src s -> dst d) = [ln0(s)][ln1(d)][n2]
         if exchange == "peer":
             self.zptr = self._dev_alloc(alloc * 16)
             handles = [None] * P
             h = C.create_string_buffer(64)
             assert self.L.fftw_b200_ipc_export(self.zptr, h) == 0, "cudaIpcGetMemHandle failed"
-            dist.all_gather_object(handles, bytes(h.raw), group=group)
+            # natural order without a gather stage: the dim-0 pass stores its rows straight into the
+            # owners' slabs, so every rank also maps every other rank's `local` (FFTW3_B200_DIST_PUSH=0
+            # keeps the gather plan)
+            lh, loff = None, -1
+            if not transposed_out and os.environ.get("FFTW3_B200_DIST_PUSH", "1") != "0":
+                loff = int(self.L.fftw_b200_ipc_offset(local.data_ptr()))
+                if loff >= 0:
+                    lb = C.create_string_buffer(64)
+                    if self.L.fftw_b200_ipc_export(local.data_ptr() - loff, lb) == 0:
+                        lh = bytes(lb.raw)
+            dist.all_gather_object(handles, (bytes(h.raw), lh, loff), group=group)
+            want_push = not transposed_out and all(x[1] is not None for x in handles)
             self.peer = []
+            peer_local = []
             for s in range(P):
                 if s == r:
                     self.peer.append(self.zptr)
+                    peer_local.append(local.data_ptr())
                 else:
-                    ptr = self.L.fftw_b200_ipc_import(handles[s])
+                    ptr = self.L.fftw_b200_ipc_import(handles[s][0])
                     assert ptr, "cudaIpcOpenMemHandle failed for rank %d" % s
                     self._opened.append(ptr)
                     self.peer.append(ptr)
+                    if want_push:
+                        lp = self.L.fftw_b200_ipc_import(handles[s][1])
+                        assert lp, "cudaIpcOpenMemHandle (slab) failed for rank %d" % s
+                        self._opened.append(lp)
+                        peer_local.append(lp + handles[s][2])
+            if want_push:
+                out_arr = (C.c_void_p * P)(*peer_local)
             # my rows start at r*b0 inside every peer's [n0][ln1(d)][n2]
             push = [self.peer[d] + 16 * (r * b0) * _share(n1, P, d) * n2 for d in range(P)]
             pull = [self.peer[s] + 16 * (r * b0) * _share(n1, P, s) * n2 for s in range(P)]
@@ -137,8 +164,21 @@ class SlabPlan3D:
         VP = C.c_void_p * P
         push_arr = VP(*push)
         pull_arr = None if transposed_out else VP(*pull)
-        self.plan = self.L.fftw_b200_dist_plan_dft_3d(n0, n1, n2, r, P, local.data_ptr(), zbuf, push_arr, pull_arr,
-                                                     int(sign), int(flags))
+        self.plan = None
+        if out_arr is not None:
+            self.plan = self.L.fftw_b200_dist_plan_dft_3d_push(n0, n1, n2, r, P, local.data_ptr(), zbuf, push_arr,
+                                                              out_arr, int(sign), int(flags))
+            ok = torch.tensor([1 if self.plan else 0])
+            if P > 1:                                   # all ranks must agree on the stage structure
+                ok = ok.to(local.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and self.plan:
+                self.L.fftw_b200_dist_destroy_plan(self.plan)
+                self.plan = None
+            self.push = bool(self.plan)
+        if not self.plan:
+            self.plan = self.L.fftw_b200_dist_plan_dft_3d(n0, n1, n2, r, P, local.data_ptr(), zbuf, push_arr,
+                                                         pull_arr, int(sign), int(flags))
         assert self.plan, "fftw_b200_dist_plan_dft_3d returned NULL"
         self.nstages = self.L.fftw_b200_dist_num_stages(self.plan)
         self._token = torch.zeros(1, device=local.device)
@@ -191,7 +231,14 @@ class SlabPlan3D:
     # ---- execution -------------------------------------------------------
     def execute(self):
         L = self.L
-        if self.exchange == "peer":
+        if self.exchange == "peer" and self.push:
+            # both exchanges ride on pass stores; the closing barrier of the previous call already
+            # ordered the peers' reads of their buffers before this call's first remote store
+            L.fftw_b200_dist_execute_stage(self.plan, 0)
+            self._barrier()                         # all blocks have landed
+            L.fftw_b200_dist_execute_stage(self.plan, 1)
+            self._barrier()                         # every rank's rows have landed in my slab
+        elif self.exchange == "peer":
             self._barrier()                         # peers are done reading their zbuf from the last call
             L.fftw_b200_dist_execute_stage(self.plan, 0)
             self._barrier()                         # all blocks have landed

@@ -77,6 +77,10 @@ typedef struct b2d_fft_pass {
        complex buffer that may live on another GPU (CUDA IPC / NVLink peer mapping) */
     int npeer;
     void *peer_out[B2D_MAX_PEERS];
+    /* peer split by output row (second exchange fused into the last pass): when npeer > 0
+       and peer_rows > 0, output row k of every transform goes to peer_out[k / peer_rows] at
+       row k % peer_rows, and batch dim 2 strides the output as usual */
+    int peer_rows;
     /* 0: one CTA per tile.  > 0: launch at most this many CTAs, which loop over the
        tiles -- used to keep an NVLink-bound pass from occupying every SM */
     int grid_limit;
@@ -156,6 +160,7 @@ size_t b2d_max_smem_per_block(void);
 int  b2d_ipc_export(void *devptr, unsigned char handle[64]);
 void *b2d_ipc_import(const unsigned char handle[64]);
 void b2d_ipc_close(void *devptr);
+int64_t b2d_alloc_offset(const void *devptr);   /* byte offset inside its allocation, -1 on failure */
 
 /* timing on the launch stream (planner measurements) */
 int  b2d_timer_start(void);

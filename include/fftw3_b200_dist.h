@@ -53,6 +53,16 @@ fftw_b200_dist_plan fftw_b200_dist_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdi
                                                fftw_complex *local, fftw_complex *zbuf,
                                                void *const *push_targets, void *const *pull_sources,
                                                int sign, unsigned flags);
+/* Natural-order output with BOTH exchanges fused into pass stores: the dim-0 pass of
+ * stage 1 writes output row k0 straight into the slab of its owner (rank k0 / block),
+ * so there is no gather stage (2 stages; the caller ends with a barrier: a rank's slab
+ * is complete once EVERY rank has finished stage 1).
+ *   out_targets   nranks pointers: rank d's `local` slab (peer-mapped, e.g. CUDA IPC)
+ * Returns NULL when the dim-0 transform needs more than one pass (use the plan above). */
+fftw_b200_dist_plan fftw_b200_dist_plan_dft_3d_push(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                                    fftw_complex *local, fftw_complex *zbuf,
+                                                    void *const *push_targets, void *const *out_targets,
+                                                    int sign, unsigned flags);
 int  fftw_b200_dist_num_stages(const fftw_b200_dist_plan p);
 void fftw_b200_dist_execute_stage(const fftw_b200_dist_plan p, int stage);
 /* Finer control for overlapping the exchange with compute: every stage is cut
@@ -72,6 +82,9 @@ void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);
 void *fftw_b200_device_malloc(size_t bytes);
 void  fftw_b200_device_free(void *p);
 int   fftw_b200_ipc_export(void *devptr, unsigned char handle[64]);
+/* The handle names the whole allocation devptr lives in; this is devptr's byte offset inside
+ * it (add it to what fftw_b200_ipc_import returns on the other side), or -1 on failure. */
+ptrdiff_t fftw_b200_ipc_offset(void *devptr);
 void *fftw_b200_ipc_import(const unsigned char handle[64]);
 void  fftw_b200_ipc_close(void *devptr);
 

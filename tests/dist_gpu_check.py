@@ -31,14 +31,18 @@ def main():
         rng = np.random.default_rng(5)
         full = rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)
         ref = O.dft(full) if rank == 0 else None
-        for exchange in ("peer", "collective"):
+        for exchange in ("peer", "peer-gather", "collective"):
             for transposed in (False, True):
                 alloc, ln0, s0, ln1, s1 = D.local_size_3d(lib, n0, n1, n2, rank, world)
                 local = torch.zeros(max(alloc, 1), dtype=torch.complex128, device="cuda")
                 if ln0:
                     local[:ln0 * n1 * n2] = torch.from_numpy(full[s0:s0 + ln0].reshape(-1).copy()).cuda()
+                # "peer": both exchanges fused into pass stores (push plan); "peer-gather": the older
+                # plan whose second exchange is a gather stage
+                os.environ["FFTW3_B200_DIST_PUSH"] = "0" if exchange == "peer-gather" else "1"
                 pl = D.SlabPlan3D(lib, n0, n1, n2, local, flags=B.FFTW_ESTIMATE, transposed_out=transposed,
-                                  exchange=exchange)
+                                  exchange="peer" if exchange == "peer-gather" else exchange)
+                pushed = pl.push
                 pl.execute()
                 pl.execute() if False else None
                 torch.cuda.synchronize()
@@ -59,8 +63,8 @@ def main():
                     err = O.rel_l2(got, ref)
                     good = err < 5e-15
                     ok &= good
-                    print("dist check %s P=%d %-10s transposed=%d rel L2 %.2e %s"
-                          % (shape, world, exchange, transposed, err, "OK" if good else "FAIL"), flush=True)
+                    print("dist check %s P=%d %-11s transposed=%d push=%d rel L2 %.2e %s"
+                          % (shape, world, exchange, transposed, pushed, err, "OK" if good else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

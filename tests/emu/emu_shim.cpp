@@ -109,6 +109,7 @@ int b2d_stream_wait_stream(void *, void *) { return 0; }
 int b2d_ipc_export(void *, unsigned char *) { return -1; }     /* no IPC in the unit-test double */
 void *b2d_ipc_import(const unsigned char *) { return NULL; }
 void b2d_ipc_close(void *) {}
+int64_t b2d_alloc_offset(const void *) { return 0; }
 int b2d_timer_start(void) { g_t0 = std::chrono::steady_clock::now(); return 0; }
 int b2d_timer_stop(float *ms)
 {

@@ -1,0 +1,86 @@
+"""Peer-exchange plans of the distributed transform, all ranks simulated in ONE process.
+
+The peer path (exchange fused into pass stores through peer-mapped pointers) needs CUDA IPC
+between processes, which the CPU test double cannot provide -- but inside one process every
+"rank" can simply be handed the other ranks' buffers.  That exercises dist.c's plan
+construction (scatter targets, row-split push stores, gather sources, uneven and idle ranks)
+and the kernels' peer addressing on the emulated device layer, stage by stage with the same
+barrier structure the real launcher uses (fftw3_b200/dist.py: SlabPlan3D.execute).
+Reference behaviour: mpi/dft-rank-geq2.c:40-59, mpi/dft-rank-geq2-transposed.c:47-70."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fftw3_b200 import binding as B
+from fftw3_b200 import dist as D
+from oracle import oracle as O
+
+
+def _run(lib, shape, P, mode, sign):
+    D._declare(lib)
+    L = lib.lib
+    n0, n1, n2 = shape
+    rng = np.random.default_rng(11)
+    full = rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)
+    info = [D.local_size_3d(lib, n0, n1, n2, r, P) for r in range(P)]
+    b0 = (n0 + P - 1) // P
+    nbytes = [16 * max(i[0], 1) for i in info]
+    loc = [L.fftw_b200_device_malloc(nb) for nb in nbytes]
+    zb = [L.fftw_b200_device_malloc(nb) for nb in nbytes]
+    assert all(loc) and all(zb)
+
+    def view(ptr, count):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(2 * count,)).view(np.complex128)
+
+    for r, (alloc, ln0, s0, ln1, s1) in enumerate(info):
+        view(loc[r], max(alloc, 1))[:] = 0
+        if ln0:
+            view(loc[r], alloc)[:ln0 * n1 * n2] = full[s0:s0 + ln0].reshape(-1)
+    plans = []
+    VP = C.c_void_p * P
+    for r in range(P):
+        share1 = [info[d][3] for d in range(P)]
+        push = VP(*[zb[d] + 16 * (r * b0) * share1[d] * n2 for d in range(P)])
+        if mode == "push":
+            p = L.fftw_b200_dist_plan_dft_3d_push(n0, n1, n2, r, P, loc[r], zb[r], push, VP(*loc), sign, B.FFTW_ESTIMATE)
+        elif mode == "gather":
+            pull = VP(*[zb[s] + 16 * (r * b0) * share1[s] * n2 for s in range(P)])
+            p = L.fftw_b200_dist_plan_dft_3d(n0, n1, n2, r, P, loc[r], zb[r], push, pull, sign, B.FFTW_ESTIMATE)
+        else:
+            p = L.fftw_b200_dist_plan_dft_3d(n0, n1, n2, r, P, loc[r], zb[r], push, None, sign, B.FFTW_ESTIMATE)
+        assert p, (mode, r)
+        plans.append(p)
+    nst = L.fftw_b200_dist_num_stages(plans[0])
+    assert nst == (3 if mode == "gather" else 2)
+    for st in range(nst):                     # a barrier between stages = finish the stage on every rank
+        for r in range(P):
+            L.fftw_b200_dist_execute_stage(plans[r], st)
+    want = O.dft(full, sign=sign) if sign < 0 else O.dft(full, sign=+1)
+    err = 0.0
+    for r, (alloc, ln0, s0, ln1, s1) in enumerate(info):
+        if mode == "transposed":
+            if ln1:
+                got = view(loc[r], alloc)[:ln1 * n0 * n2].reshape(ln1, n0, n2)
+                err = max(err, O.rel_l2(got, np.transpose(want, (1, 0, 2))[s1:s1 + ln1]))
+        elif ln0:
+            got = view(loc[r], alloc)[:ln0 * n1 * n2].reshape(ln0, n1, n2)
+            err = max(err, O.rel_l2(got, want[s0:s0 + ln0]))
+    for p in plans:
+        L.fftw_b200_dist_destroy_plan(p)
+    for q in loc + zb:
+        L.fftw_b200_device_free(q)
+    return err
+
+
+@pytest.mark.parametrize("mode", ["push", "gather", "transposed"])
+@pytest.mark.parametrize("shape,P,sign", [
+    ((8, 6, 10), 2, -1),
+    ((12, 10, 8), 3, +1),       # uneven column blocks (4, 4, 2)
+    ((6, 5, 4), 4, -1),         # block 2: the last rank owns no planes
+    ((16, 16, 16), 4, -1),      # power-of-two block: shift path of the row split
+    ((5, 3, 7), 1, -1),
+])
+def test_peer_plans_all_ranks_in_one_process(emu_lib, mode, shape, P, sign):
+    err = _run(emu_lib, shape, P, mode, sign)
+    assert err <= 1e-14, (mode, shape, P, err)
