@@ -55,6 +55,15 @@ B2_HD TileCtx decode_block(const b2d_fft_pass &p, int64_t block)
 {
     TileCtx c;
     int64_t tiles0 = (p.bn[0] + p.tpb - 1) / p.tpb;
+    if (p.npeer && !p.peer_rows) {
+        // peer scatter: the destination (batch dim 2) varies fastest and starts at this rank's
+        // successor -- all NVLink ports busy, no receiver hot-spot
+        c.b2 = (block % p.bn[2] + p.peer_rot) % p.bn[2];
+        int64_t rest = block / p.bn[2];
+        c.tile0 = rest % tiles0;
+        c.b1 = rest / tiles0;
+        return c;
+    }
     c.tile0 = block % tiles0;
     int64_t rest = block / tiles0;
     c.b1 = rest % p.bn[1];

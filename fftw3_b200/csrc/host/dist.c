@@ -184,6 +184,7 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
                 int k;
                 f->bn[2] = nranks; f->bis[2] = 2 * b1 * n2; f->bos[2] = 0;
                 f->npeer = nranks;
+                f->peer_rot = rank + 1;
                 for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)push_targets[k] + 2 * lo * l1 * n2;
                 p->x_fused[c] = 1;
                 break;

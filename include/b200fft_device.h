@@ -81,6 +81,10 @@ typedef struct b2d_fft_pass {
        and peer_rows > 0, output row k of every transform goes to peer_out[k / peer_rows] at
        row k % peer_rows, and batch dim 2 strides the output as usual */
     int peer_rows;
+    /* peer scatter (peer_rows == 0): consecutive CTAs walk the destinations first, starting
+       at peer (peer_rot % npeer), so that every GPU feeds all its peers at once and no
+       destination is hit by all senders at the same time */
+    int peer_rot;
     /* 0: one CTA per tile.  > 0: launch at most this many CTAs, which loop over the
        tiles -- used to keep an NVLink-bound pass from occupying every SM */
     int grid_limit;
