@@ -348,6 +348,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                "ms_per_step": float(dt.item()) * 1e3, "steps": steps,
                "api": "fftw3_b200.dist.SlabPlan3D.execute on pinned host slabs (one per rank)"}
     lib.lib.fftw_b200_set_async(0)
+    pushed = plan.push
     plan.destroy()
     plan_t.destroy()
     if rank != 0:
@@ -360,7 +361,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     slab_bytes = 16 * ln0 * n * n
-    passes = 4                                  # Y, X(+scatter), Z, gather
+    passes = 3 if pushed else 4                 # Y, X(+scatter), Z(+row push)  |  Y, X(+scatter), Z, gather
     achieved = passes * 2 * slab_bytes / (ms * 1e-3) / 1e9
     nv_bytes = 2 * slab_bytes * (world - 1) / world      # two exchanges, sent per GPU
     line = {
@@ -369,7 +370,8 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d^3 c2c double in place, forward, slab-decomposed over %d GPUs, natural-order "
                                "output (two exchanges)" % (n, world),
-                   "exchange": exchange, "l2": "slabs are larger than L2, no flush needed",
+                   "exchange": exchange + (", both exchanges fused into pass stores (no gather stage)" if pushed
+                                           else ", second exchange = gather stage"), "l2": "slabs are larger than L2, no flush needed",
                    "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
                    "transposed_out_ms_per_step": ms_t,
                    "transposed_out_gflops": flops_c2c((n, n, n)) / (ms_t * 1e-3) / 1e9},

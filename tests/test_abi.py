@@ -50,3 +50,26 @@ def test_product_library_does_not_reference_oracle():
     from fftw3_b200 import binding
     data = open(binding.default_library_path(), "rb").read()
     assert b"oracle_dft" not in data and b"liboracle" not in data and b"_ref.so" not in data
+
+
+def test_wisdom_tool_command_line():
+    """tools/fftw_wisdom.c (the reference's tools/fftw-wisdom.c:73-131 command line): help text,
+    size-syntax errors, and -- with no GPU -- a loud failure instead of empty wisdom."""
+    import subprocess
+    libdir = os.path.join(ROOT, "fftw3_b200", "lib")
+    for tool in ("fftw-wisdom", "fftwf-wisdom"):
+        exe = os.path.join(libdir, tool)
+        assert os.path.exists(exe), "run __graft_entry__.build()"
+        r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+        assert r.returncode == 0 and "Size syntax" in r.stdout and "--canonical" in r.stdout
+        r = subprocess.run([exe, "-V"], capture_output=True, text=True)
+        assert r.returncode == 0 and "FFTW 3.3" in r.stdout
+        r = subprocess.run([exe, "-e", "cof12q"], capture_output=True, text=True)
+        assert r.returncode != 0 and "cannot parse" in r.stderr
+        r = subprocess.run([exe, "--bogus"], capture_output=True, text=True)
+        assert r.returncode != 0
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([os.path.join(libdir, "fftw-wisdom"), "-e", "cof64", "ki10e10x8e01v3", "rib16x6"],
+                           capture_output=True, text=True)
+        assert r.returncode != 0 and r.stderr.count("could not plan") == 3

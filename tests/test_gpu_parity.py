@@ -326,3 +326,29 @@ def test_reference_verifier_random_problems(gpu_lib, prec):
             args += ["--verify", pr]
         r = subprocess.run(args, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (probs[i:i + 30], r.stdout[-1500:], r.stderr[-1500:])
+
+
+@pytest.mark.gpu
+def test_wisdom_tool_produces_importable_wisdom(gpu_lib, tmp_path):
+    """fftw-wisdom / fftwf-wisdom (tools/fftw_wisdom.c; reference tools/fftw-wisdom.c) plan the
+    requested sizes in MEASURE mode; the file they write lets a FFTW_WISDOM_ONLY plan succeed."""
+    import subprocess
+    libdir = os.path.join(ROOT, "fftw3_b200", "lib")
+    for prec, tool in (("d", "fftw-wisdom"), ("f", "fftwf-wisdom")):
+        out = tmp_path / (tool + ".txt")
+        r = subprocess.run([os.path.join(libdir, tool), "-v", "-m", "-n", "-o", str(out), "cof1024v64", "rif256",
+                            "ki10e10x8e01", "cib32x32"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.count("Planning transform") == 4
+        text = out.read_text()
+        assert text.count("(b200_fft_pass") >= 4, text
+        gpu_lib.fn(prec, "forget_wisdom")()
+        x = np.zeros((64, 1024), dtype=np.complex128 if prec == "d" else np.complex64)
+        y = np.zeros_like(x)
+        args = ([1024], 64, x.ctypes.data, None, 1, 1024, y.ctypes.data, None, 1, 1024, B.FFTW_FORWARD)
+        assert not gpu_lib.plan_many_dft(prec, *args, B.FFTW_MEASURE | B.FFTW_WISDOM_ONLY)
+        assert gpu_lib.fn(prec, "import_wisdom_from_filename")(str(out).encode()) == 1
+        p = gpu_lib.plan_many_dft(prec, *args, B.FFTW_MEASURE | B.FFTW_WISDOM_ONLY)
+        assert p, "wisdom written by the tool was not usable"
+        gpu_lib.destroy_plan(prec, p)
+        gpu_lib.fn(prec, "forget_wisdom")()
