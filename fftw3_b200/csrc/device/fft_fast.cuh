@@ -198,6 +198,8 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     //             position the thread just read), the CTA streams it out below
     //   FLAVOR 8: COL kernel whose output ROWS are split over peer GPUs (row k -> peer k / peer_rows):
     //             the second exchange of a distributed transform fused into its last pass
+    //   FLAVOR 9: real-to-real kinds: the PRE map gathers the first stage's inputs from the real line,
+    //             the POST map scatters the last stage's outputs into it (r2r_maps.cuh)
     //   FLAVOR 7: Bluestein in one CTA (dft/bluestein.c:82-128): the stages run twice; the first
     //             run's outputs are multiplied by B = FFT(filter), conjugated and kept in registers
     //             -- output b + r*Ns of the last stage IS input j + q*TPX of the next first stage,
@@ -205,6 +207,14 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     T bre[FLAVOR == 7 ? E : 1], bim[FLAVOR == 7 ? E : 1];
     int rep = 0;
     auto emit = [&](int kout, int q, T vr, T vi) {
+        if (FLAVOR == 9) {
+            if (valid) {
+                b2::RealLineOut<T> y = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
+                cplx<T> v; v.x = vr; v.y = vi;
+                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, kout, v, reinterpret_cast<const cplx<T> *>(p.aux0), y);
+            }
+            return;
+        }
         if (FLAVOR == 7) {
             cplx<T> v; v.x = vr; v.y = vi;
             if (rep == 0) {
@@ -271,7 +281,12 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = T(0); v.y = T(0);
-        if (FLAVOR == 7) {
+        if (FLAVOR == 9) {
+            if (valid) {
+                b2::RealLineIn<T> x = { reinterpret_cast<const T *>(p.in_re) + boff_in, p.is };
+                v = b2::r2r_pre_value<T>(p.r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x);
+            }
+        } else if (FLAVOR == 7) {
             const int k = j + r * TPX;
             if (valid && k < p.n_in) v = ld_stream(gin + (int64_t)k * is2);
         } else if (valid) {

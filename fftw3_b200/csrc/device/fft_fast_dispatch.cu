@@ -74,6 +74,16 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
     if (!p.kernel) return nullptr;
     const int col = p.kernel >= 1000;
     const int flavor = (p.kernel / 100) % 10;
+    if (flavor == 9) {
+        // r2r kinds fused into the pass: real lines, so strides are in single reals
+        if (p.pre_op != B2D_LOAD_R2R || p.post_op != B2D_STORE_R2R || p.bluestein || p.npeer) return nullptr;
+        if (p.load_col != p.store_col || col != p.load_col) return nullptr;
+        if (col ? (p.bis[0] != 1 || p.bos[0] != 1) : (p.is != 1 || p.os != 1)) return nullptr;
+        const FastEntry *e9 = find(p.prec, p.n, col, p.kernel);
+        if (e9 && (int)e9->smem > g_max_smem && g_max_smem) return nullptr;
+        return e9;
+    }
+    if ((p.pre_op & B2D_LOAD_R2R) || (p.post_op & B2D_STORE_R2R)) return nullptr;
     if (flavor == 7) {
         if (!p.bluestein || p.pre_op != (B2D_LOAD_PAD | B2D_LOAD_CHIRP) ||
             p.post_op != (B2D_STORE_TRUNC | B2D_STORE_CHIRP_SCALE) || p.load_col || p.store_col || col || p.npeer)
@@ -140,8 +150,9 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     const FastEntry *e = entry_for(p);
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;
-    const intptr_t din = (const char *)p.in_im - (const char *)p.in_re;
-    const intptr_t dout = (char *)p.out_im - (char *)p.out_re;   /* also tells the peer path whether to swap */
+    const bool reals = ((p.kernel / 100) % 10) == 9;            // r2r: scalar accesses, no re/im pairing
+    const intptr_t din = reals ? (intptr_t)rs : (const char *)p.in_im - (const char *)p.in_re;
+    const intptr_t dout = reals ? (intptr_t)rs : (char *)p.out_im - (char *)p.out_re;   /* also tells the peer path whether to swap */
     // interleaved (im = re +- 1 scalar) and vector-aligned, else the generic kernel handles it
     if ((din != (intptr_t)rs && din != -(intptr_t)rs) || (dout != (intptr_t)rs && dout != -(intptr_t)rs)) return 1;
     const int swap_in = din < 0, swap_out = dout < 0;
@@ -151,7 +162,7 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
         lo_out = 0;
         for (int i = 0; i < p.npeer; ++i) lo_out |= (uintptr_t)p.peer_out[i];
     }
-    if ((lo_in % (2 * rs)) || (lo_out % (2 * rs))) return 1;
+    if (!reals && ((lo_in % (2 * rs)) || (lo_out % (2 * rs)))) return 1;
     const int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
     const int64_t blocks = tiles0 * p.bn[1] * p.bn[2];
     if (blocks <= 0) return 0;

@@ -36,6 +36,10 @@ template <typename T> B2_HD cplx<T> cmul(cplx<T> a, cplx<T> b)
     return r;
 }
 
+}  // namespace b2
+#include "r2r_maps.cuh"
+namespace b2 {
+
 // padded position of element k inside one transform's shared-memory row
 B2_HD int padk(int k) { return k + (k >> 4); }
 // row pitch (complex elements): padded length forced to 1 mod 8 so that COL-mode
@@ -84,6 +88,10 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
     const T *re = (const T *)p.in_re;
     const T *im = (const T *)p.in_im;
     const int op = p.pre_op;
+    if (op & B2D_LOAD_R2R) {        // real line -> work sequence of the r2r kind (r2r_maps.cuh)
+        RealLineIn<T> x = { (const T *)p.in_re + boff, p.is };
+        return r2r_pre_value<T>(p.r2r_kind, p.n_in, k, (const cplx<T> *)p.aux0, x);
+    }
     cplx<T> z;
     if ((op & B2D_LOAD_PAD) && k >= p.n_in) { z.x = T(0); z.y = T(0); return z; }
     if (op & B2D_LOAD_REAL) {
@@ -121,6 +129,11 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
         else { re = base; im = base + 1; }
     }
     const int op = p.post_op;
+    if (op & B2D_STORE_R2R) {       // FFT output k scattered to the real output line
+        RealLineOut<T> y = { (T *)p.out_re + boff, p.os };
+        r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, z, (const cplx<T> *)p.aux0, y);
+        return;
+    }
     if ((op & B2D_STORE_TRUNC) && k >= p.n_out) return;
     if (op & B2D_STORE_TWIDDLE4) {
         // exponent e = k * b0 < big_n ; W^e = hi[e / L] * lo[e % L]

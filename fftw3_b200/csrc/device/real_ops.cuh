@@ -16,9 +16,6 @@
 
 namespace b2 {
 
-enum { K_R2HC = 0, K_HC2R, K_DHT, K_REDFT00, K_REDFT01, K_REDFT10, K_REDFT11,
-       K_RODFT00, K_RODFT01, K_RODFT10, K_RODFT11 };
-
 B2_HD int64_t realop_user_offset(const b2d_realop &r, int64_t b)
 {
     int64_t b0 = b % r.bn[0];
@@ -26,17 +23,6 @@ B2_HD int64_t realop_user_offset(const b2d_realop &r, int64_t b)
     int64_t b1 = rest % r.bn[1];
     int64_t b2 = rest / r.bn[1];
     return b0 * r.bxs[0] + b1 * r.bxs[1] + b2 * r.bxs[2];
-}
-
-// complex work length M for an r2r kind of physical size n
-B2_HD int r2r_work_len(int kind, int n)
-{
-    switch (kind) {
-    case K_REDFT00: return 2 * (n - 1);
-    case K_RODFT00: return 2 * (n + 1);
-    case K_REDFT11: case K_RODFT11: return 2 * n;
-    default: return n;
-    }
 }
 
 // PRE: one work element i of batch line b

@@ -146,6 +146,7 @@ typedef struct {
     int n_in, n_out;          /* 0 = n */
     int64_t big_n, tw4_split; /* STORE_TWIDDLE4: enclosing size and lo-table length */
     int cache;                /* L2 residency hints (b2d_fft_pass.cache) */
+    int r2r_kind;             /* LOAD_R2R / STORE_R2R */
 } b2_ops;
 
 static void fill_geometry(b2d_fft_pass *f, int variant)
@@ -236,6 +237,7 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
         else if (f->bluestein) { if (flavor) return -1; flavor = 7; }
+        else if (f->pre_op == B2D_LOAD_R2R && f->post_op == B2D_STORE_R2R) { if (flavor) return -1; flavor = 9; }
         code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
@@ -375,6 +377,14 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         f->aux1 = plan_table(p, prec, TAB_BLUE_B, n, bluestein_m);
         if (!f->aux0 || !f->aux1) return -1;
     }
+    if (f->pre_op & B2D_LOAD_R2R) {
+        int k = ops.r2r_kind;
+        f->r2r_kind = k;
+        if (k == 4 || k == 5 || k == 6 || k == 8 || k == 9 || k == 10) {     /* types 2, 3, 4: quarter-wave table */
+            f->aux0 = plan_table(p, prec, TAB_QUARTER, f->n_in, 0);
+            if (!f->aux0) return -1;
+        }
+    }
     if (f->post_op & B2D_STORE_TWIDDLE4) {
         f->big_n = ops.big_n; f->aux_split = ops.tw4_split;
         f->tw4_shift = -1;
@@ -409,8 +419,8 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
-            if (f->pre_op & B2D_LOAD_REAL) dri = 0;
-            if (f->post_op & B2D_STORE_REALPART) dro = 0;
+            if (f->pre_op & (B2D_LOAD_REAL | B2D_LOAD_R2R)) dri = 0;
+            if (f->post_op & (B2D_STORE_REALPART | B2D_STORE_R2R)) dro = 0;
             /* split arrays living in different buffers: time as interleaved-adjacent */
             if (llabs(dri) > 64) dri = 1;
             if (llabs(dro) > 64) dro = 1;
@@ -1153,6 +1163,60 @@ static int plan_r2r(b2_plan *p)
         int i;
         if (kind < 0 || kind > 10) return -1;
         if (r2r_work_len(kind, n, &m)) return -1;
+        /* work transform fits one CTA: PRE and POST maps ride in the load and the store of ONE pass
+           over the user's arrays (device/r2r_maps.cuh) -- one read and one write per dimension */
+        {
+            int radix[64];
+            if (m >= 2 && b2_factorize(m, q->prec, 0, radix) != 0 && single_pass_fits(m, q->prec) &&
+                !getenv("FFTW3_B200_R2R_UNFUSED")) {
+                b2_view vin, vout;
+                b2_ops ops;
+                memset(&ops, 0, sizeof ops);
+                ops.pre_op = B2D_LOAD_R2R; ops.post_op = B2D_STORE_R2R;
+                ops.n_in = (int)n; ops.n_out = (int)n; ops.r2r_kind = kind;
+                vin.re = vin.im = first ? mkref(BUF_IN0, 0) : mkref(BUF_OUT0, 0);
+                vin.stride = first ? q->sz.d[d].is : q->sz.d[d].os;
+                vout.re = vout.im = mkref(BUF_OUT0, 0);
+                vout.stride = q->sz.d[d].os;
+                other_dims(q, d, !first, &ub);
+                {
+                    int col = 0;
+                    for (i = 0; i < ub.rnk; ++i)
+                        if (ub.d[i].n > 1 && llabs(ub.d[i].is) < llabs(vin.stride)) col = 1;
+                    if (!col || (size_t)m * 4 * esz <= 131072) {
+                        rc = emit_fft1d(p, q->prec, m, vin, vout, &ub, ops, 1, "r2r (maps fused)");
+                    } else {
+                        /* strided lines too long for a tile of them to share a CTA: make them contiguous
+                           with a tiled transpose, run the fused pass there, transpose back
+                           (the reference's dft/indirect-transpose.c:38-59 strategy) */
+                        b2_tensor srt = ub, tin, tout, tb;
+                        b2_view sv;
+                        int64_t dense = n;
+                        b2_tensor_drop_unit(&srt);
+                        if (srt.rnk > 1) qsort(srt.d, (size_t)srt.rnk, sizeof(b2_dim), cmp_is);
+                        b2_tensor_init(&tin, 0); b2_tensor_init(&tout, 0); b2_tensor_init(&tb, 0);
+                        tin.d[0].n = n; tin.d[0].is = vin.stride; tin.d[0].os = 1;
+                        tout.d[0].n = n; tout.d[0].is = 1; tout.d[0].os = vout.stride;
+                        tin.rnk = tout.rnk = 1;
+                        for (i = 0; i < srt.rnk; ++i) {
+                            tin.d[tin.rnk].n = srt.d[i].n; tin.d[tin.rnk].is = srt.d[i].is; tin.d[tin.rnk].os = dense;
+                            tout.d[tout.rnk].n = srt.d[i].n; tout.d[tout.rnk].is = dense; tout.d[tout.rnk].os = srt.d[i].os;
+                            tb.d[tb.rnk].n = srt.d[i].n; tb.d[tb.rnk].is = dense; tb.d[tb.rnk].os = dense;
+                            tin.rnk++; tout.rnk++; tb.rnk++;
+                            dense *= srt.d[i].n;
+                        }
+                        need_scratch(p, 0, (size_t)dense * real_size(q->prec));
+                        sv.re = sv.im = mkref(BUF_SCRATCH0, 0); sv.stride = 1;
+                        rc = emit_copy(p, q->prec, vin.re, mkref(BUF_SCRATCH0, 0), &tin, 1);
+                        if (!rc) rc = emit_fft1d(p, q->prec, m, sv, sv, &tb, ops, 1, "r2r (maps fused, lines transposed)");
+                        if (!rc) rc = emit_copy(p, q->prec, mkref(BUF_SCRATCH0, 0), vout.re, &tout, 1);
+                    }
+                }
+                if (rc) return rc;
+                first = 0;
+                continue;
+            }
+        }
         /* user batch for this dim: input side strides for PRE, output side for POST */
         other_dims(q, d, !first, &ub);      /* .is = source strides, .os = out strides */
         wb_in = ub;

@@ -31,7 +31,9 @@ enum {
                                n_in given by its non-redundant half (c2r): k > n_in/2
                                reads in[n_in-k]; imag of self-mirrored bins ignored   */
     B2D_LOAD_PAD = 4,       /* k >= n_in reads as zero                               */
-    B2D_LOAD_CHIRP = 8      /* multiply by aux0[k] (Bluestein chirp)                 */
+    B2D_LOAD_CHIRP = 8,     /* multiply by aux0[k] (Bluestein chirp)                 */
+    B2D_LOAD_R2R = 16       /* real line of n_in elements -> complex work sequence of length n by
+                               the PRE map of r2r_kind (aux0 = quarter-wave table)     */
 };
 
 /* element-wise operations fused into the store side of an FFT pass (bit mask) */
@@ -39,7 +41,9 @@ enum {
     B2D_STORE_REALPART = 1,    /* store Re only (c2r)                                 */
     B2D_STORE_TRUNC = 2,       /* store only k < n_out                                */
     B2D_STORE_CHIRP_SCALE = 4, /* Bluestein: z * aux0[k] * scale                      */
-    B2D_STORE_TWIDDLE4 = 8     /* four-step: z *= W_big^(k * b0) (two-level tables)   */
+    B2D_STORE_TWIDDLE4 = 8,    /* four-step: z *= W_big^(k * b0) (two-level tables)   */
+    B2D_STORE_R2R = 16         /* output k scattered into the real line of n_out elements by the
+                                  POST map of r2r_kind                                 */
 };
 
 /* One batched strided 1-D complex FFT pass.  All strides/offsets are in units
@@ -61,6 +65,8 @@ typedef struct b2d_fft_pass {
     int kernel;               /* 0: generic runtime-radix kernel; else code of a
                                  specialised kernel: tile width + 1000 for COL      */
     int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
+    int r2r_kind;             /* LOAD_R2R / STORE_R2R: 0..10 = R2HC HC2R DHT REDFT00 REDFT01 REDFT10 REDFT11
+                                 RODFT00 RODFT01 RODFT10 RODFT11 (the fftw_r2r_kind values)          */
     int64_t is, os;           /* element stride along the transform                  */
     int64_t bn[B2D_MAX_BATCH_DIMS], bis[B2D_MAX_BATCH_DIMS], bos[B2D_MAX_BATCH_DIMS];
     /* buffers: re/im pointers (im == re +- 1 means interleaved; sign swap = -1)    */

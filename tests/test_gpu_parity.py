@@ -352,3 +352,23 @@ def test_wisdom_tool_produces_importable_wisdom(gpu_lib, tmp_path):
         assert p, "wisdom written by the tool was not usable"
         gpu_lib.destroy_plan(prec, p)
         gpu_lib.fn(prec, "forget_wisdom")()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("shape,kinds,inplace", [
+    ((4096, 64), ("REDFT10", "RODFT01"), False),     # strided 4096-lines: transposed scratch lines
+    ((3000, 40), ("REDFT01", "R2HC"), True),
+    ((2, 2500, 33), ("DHT", "RODFT11", "HC2R"), False),
+    ((2049, 20), ("REDFT00", "REDFT11"), True),
+    ((512, 512), ("REDFT10", "REDFT10"), True),      # both dims fused, COL tile kernel on dim 0
+    ((256, 100, 64), ("RODFT10", "REDFT01", "DHT"), False),
+    ((1024, 1024), ("RODFT11", "RODFT00"), False),
+])
+def test_r2r_fused_maps_and_long_strided_lines(gpu_lib, prec, shape, kinds, inplace):
+    """The r2r PRE/POST maps ride in the load/store of one FFT pass per dimension
+    (device/r2r_maps.cuh; specialised kernels flavour 9 and the generic kernel); strided lines
+    too long for a tile go through transposed scratch lines.  Same oracle and bound as the
+    other r2r tests."""
+    err, tol = F.r2r(gpu_lib, prec, shape, list(kinds), inplace=inplace)
+    assert err <= tol, (prec, shape, kinds, err, tol)

@@ -244,3 +244,17 @@ def test_inplace_with_different_strides(emu_lib):
     emu_lib.destroy_plan("d", p)
     for k in range(2):
         assert O.rel_l2(y[16 * k:16 * k + 16:2], O.dft(y0[8 * k:8 * k + 8])) < 1e-15
+
+
+@pytest.mark.parametrize("shape,kinds,inplace", [
+    ((4096, 6), ("REDFT10", "RODFT01"), False),
+    ((3000, 5), ("REDFT01", "R2HC"), True),
+    ((2, 2500, 3), ("DHT", "RODFT11", "HC2R"), False),
+    ((2049, 4), ("REDFT00", "REDFT11"), True),
+])
+def test_r2r_long_strided_lines(emu_lib, shape, kinds, inplace):
+    """r2r dimensions whose strided lines are too long for a tile of them to share a CTA go
+    through transposed scratch lines (dft/indirect-transpose.c strategy) around the fused pass;
+    the other dimensions run the PRE/POST maps inside one pass (device/r2r_maps.cuh)."""
+    err, tol = F.r2r(emu_lib, "d", shape, list(kinds), inplace=inplace)
+    assert err <= tol, (shape, kinds, err)
