@@ -89,6 +89,7 @@ __device__ __forceinline__ cplx<T> unit_root(int m)
     cplx<T> c;
     if (E == 4) unit_root4<T>(m, c.x, c.y);
     else if (E == 8) unit_root8<T>(m, c.x, c.y);
+    else if (E == 10) unit_root10<T>(m, c.x, c.y);
     else if (E == 16) unit_root16<T>(m, c.x, c.y);
     else unit_root32<T>(m, c.x, c.y);
     return c;
@@ -106,10 +107,10 @@ __device__ __forceinline__ void load_twiddles(const cplx<T> *tw, int step, cplx<
 #pragma unroll
         for (int c = 1; c < 4; ++c) w[c] = ldg_c(&tw[step * c]);
 #pragma unroll
-        for (int a = 1; a < R / 4; ++a) {
+        for (int a = 1; a < (R + 3) / 4; ++a) {
             w[4 * a] = ldg_c(&tw[step * 4 * a]);
 #pragma unroll
-            for (int c = 1; c < 4; ++c) w[4 * a + c] = cmul(w[4 * a], w[c]);
+            for (int c = 1; c < 4; ++c) if (4 * a + c < R) w[4 * a + c] = cmul(w[4 * a], w[c]);
         }
     }
 }
@@ -117,7 +118,7 @@ __device__ __forceinline__ void load_twiddles(const cplx<T> *tw, int step, cplx<
 // Stage twiddles staged in shared memory once per CTA: the table entries a thread needs are
 // W^(m*k) for the multipliers m in {1,2,3} (and {4,8,..} for radices > 4); reading them with LDS
 // (~30 cycles) instead of LDG through L1/L2 (up to ~300 cycles) removes most long-scoreboard stalls.
-__host__ __device__ constexpr int tw_nmult(int R) { return R <= 1 ? 0 : (R <= 4 ? R - 1 : 3 + (R / 4 - 1)); }
+__host__ __device__ constexpr int tw_nmult(int R) { return R <= 1 ? 0 : (R <= 4 ? R - 1 : 3 + ((R + 3) / 4 - 1)); }
 __host__ __device__ constexpr int tw_mult(int mi) { return mi < 3 ? mi + 1 : 4 * (mi - 2); }
 
 // w[r] for r = 1..R-1 from a shared table laid out [mi][count] (count entries per multiplier)
@@ -131,10 +132,10 @@ __device__ __forceinline__ void smem_twiddles(const cplx<T> *tab, int count, int
 #pragma unroll
         for (int c = 1; c < 4; ++c) w[c] = tab[(c - 1) * count + k];
 #pragma unroll
-        for (int a = 1; a < R / 4; ++a) {
+        for (int a = 1; a < (R + 3) / 4; ++a) {
             w[4 * a] = tab[(2 + a) * count + k];
 #pragma unroll
-            for (int c = 1; c < 4; ++c) w[4 * a + c] = cmul(w[4 * a], w[c]);
+            for (int c = 1; c < 4; ++c) if (4 * a + c < R) w[4 * a + c] = cmul(w[4 * a], w[c]);
         }
     }
 }

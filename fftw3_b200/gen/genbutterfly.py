@@ -393,7 +393,7 @@ def main():
         parts.append(src)
     # compile-time roots of unity W_E^m = exp(-2 pi i m / E), used by the specialised
     # kernels to derive per-butterfly twiddles from one loaded base twiddle
-    for e in (4, 8, 16, 32):
+    for e in (4, 8, 10, 16, 32):
         cs = [root(m, e) for m in range(e)]
         cases = "\n".join("    case %d: re = T(%s); im = T(%s); break;" % (m, repr(c[0]), repr(c[1]))
                           for m, c in enumerate(cs))

@@ -242,7 +242,10 @@ def test_every_specialised_kernel_variant(gpu_lib, variant, monkeypatch):
     monkeypatch.setenv("FFTW3_B200_FORCE_VARIANT", str(variant))
     for prec in PRECS:
         for shape, hm, inplace in (((1024,), 37, False), ((512, 30), 3, True), ((13, 1024, 20), 1, True),
-                                   ((1 << 19,), 2, False), ((256, 64, 36), 1, False)):
+                                   ((1 << 19,), 2, False), ((256, 64, 36), 1, False),
+                                   # powers of ten: radix-10 specialised kernels, four-step with non-binary twiddle split
+                                   ((1000,), 37, False), ((100, 30), 3, True), ((13, 1000, 20), 1, True),
+                                   ((1000000,), 1, False)):
             err, tol = F.c2c(gpu_lib, prec, shape, howmany=hm, inplace=inplace, sign=-1 if variant % 2 else 1)
             assert err <= tol, (variant, prec, shape)
 
