@@ -40,6 +40,7 @@ struct fftw_b200_dist_plan_s {
     b2_plan **x;             /* [c0] fused or [c0 * nranks] */
     b2_plan **z;             /* [c1] */
     b2_plan **g;             /* [c1 * nranks] */
+    b2_plan *pre, *post;     /* real-data plans: local r2c rows before stage 0 / local c2r rows as the last stage */
 };
 typedef struct fftw_b200_dist_plan_s *dplan;
 
@@ -90,6 +91,8 @@ void fftw_b200_dist_destroy_plan(dplan p)
     for (i = 0; p->x && i < p->c0 * p->nranks; ++i) b2_plan_destroy(p->x[i]);
     for (i = 0; p->z && i < p->c1; ++i) b2_plan_destroy(p->z[i]);
     for (i = 0; p->g && i < p->c1 * p->nranks; ++i) b2_plan_destroy(p->g[i]);
+    b2_plan_destroy(p->pre);
+    b2_plan_destroy(p->post);
     free(p->y); free(p->x); free(p->z); free(p->g);
     free(p);
 }
@@ -123,6 +126,27 @@ static int chunks_for(int64_t n)
     if (c > 64) c = 64;
     while (c > 1 && n / c < 2) c /= 2;
     return c;
+}
+
+/* Redirect the stores of a planned single-pass strided (COL) transform so that output row k
+   goes to targets[k / rows] at row k % rows (row stride `os` reals): the exchange rides on the
+   pass.  0 on success. */
+static int rowsplit(b2_plan *pl, int nranks, int64_t rows, void *const *targets, int64_t target_off, int64_t os)
+{
+    b2d_fft_pass *f;
+    int k, tile;
+    if (pl->nsteps != 1 || pl->steps[0].kind != STEP_FFT) return -1;
+    f = &pl->steps[0].u.fft;
+    if (f->pre_op || f->post_op || f->bluestein || f->bn[2] != 1 || f->bos[0] != 2 || !f->store_col) return -1;
+    f->npeer = nranks;
+    f->peer_rows = (int)rows;
+    for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)targets[k] + target_off;
+    f->os = os;
+    f->tw4_shift = -1;
+    if ((rows & (rows - 1)) == 0) { int sh = 0; while (((int64_t)1 << sh) < rows) ++sh; f->tw4_shift = sh; }
+    tile = f->kernel >= 1000 && f->kernel < 5000 ? f->kernel % 100 : 0;
+    f->kernel = (tile && b2d_fast_available(f, 1800 + tile)) ? 1800 + tile : 0;
+    return 0;
 }
 
 static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
@@ -213,21 +237,9 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
         if (out_targets && !p->z[c]->is_nop) {
             /* push: row k0 of every column goes to its owner rank k0 / b0, into that rank's
                slab [ln0(owner)][n1][n2] at (k0 % b0, my first column + k1', k2) */
-            b2_plan *zp = p->z[c];
-            b2d_fft_pass *f;
             int64_t b0 = blk(n0, nranks), s1 = b1 * rank;
-            int k, tile;
-            if (zp->nsteps != 1 || zp->steps[0].kind != STEP_FFT) goto fail;     /* multi-pass n0: use the gather plan */
-            f = &zp->steps[0].u.fft;
-            if (f->pre_op || f->post_op || f->bluestein || f->bn[1] != 1 || f->bn[2] != 1 || f->bos[0] != 2) goto fail;
-            f->npeer = nranks;
-            f->peer_rows = (int)b0;
-            for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)out_targets[k] + 2 * (s1 + lo) * n2;
-            f->os = 2 * n1 * n2;
-            f->tw4_shift = -1;
-            if ((b0 & (b0 - 1)) == 0) { int sh = 0; while (((int64_t)1 << sh) < b0) ++sh; f->tw4_shift = sh; }
-            tile = f->kernel >= 1000 && f->kernel < 5000 ? f->kernel % 100 : 0;
-            f->kernel = (tile && b2d_fast_available(f, 1800 + tile)) ? 1800 + tile : 0;
+            if (p->z[c]->nsteps != 1 || p->z[c]->steps[0].u.fft.bn[1] != 1) goto fail;   /* multi-pass n0: use the gather plan */
+            if (rowsplit(p->z[c], nranks, b0, out_targets, 2 * (s1 + lo) * n2, 2 * n1 * n2)) goto fail;
         }
     }
     if (pull_sources) {
@@ -272,6 +284,87 @@ dplan fftw_b200_dist_plan_dft_3d_push(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, 
     return mkdist(n0, n1, n2, rank, nranks, local, zbuf, push_targets, NULL, out_targets, sign, flags);
 }
 
+/* ---- real data: r2c / c2r of an n0 x n1 x n2 real array (mpi/rdft2-rank-geq2(-transposed).c,
+   mpi/api.c:650-760).  Layout as fftw_mpi: the real slab is [local_n0][n1][2*(n2/2+1)] (padded
+   rows, so it may alias the complex slab [local_n0][n1][n2/2+1]).
+     r2c  stage 0: local r2c of the rows (n2), then c2c along n1 whose output ROWS are stored
+                   straight into the peers' exchange buffers [n0][n1/P][h] (row-split stores)
+          stage 1: c2c along n0, rows stored straight into the owners' complex slabs
+     c2r  stages 0/1 the same with backward c2c passes, stage 2: local c2r of the rows.
+   Equal column blocks only (n1 % nranks == 0); NULL otherwise. */
+static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                         double *real, C *cplx, C *zbuf, void *const *push_targets, void *const *out_targets,
+                         unsigned flags)
+{
+    dplan p;
+    b2_problem q;
+    int64_t h = n2 / 2 + 1, b0 = blk(n0, nranks), b1 = blk(n1, nranks);
+    int64_t ln0 = share(n0, nranks, rank);
+    int sign = c2r ? +1 : -1;
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0 || nranks < 1 || rank < 0 || rank >= nranks || nranks > B2D_MAX_PEERS) return NULL;
+    if (n1 % nranks || !push_targets || !out_targets) return NULL;
+    if (b2d_pointer_is_device(zbuf) != 1 || b2d_pointer_is_device(cplx) != 1) return NULL;
+    p = (dplan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->nranks = nranks; p->rank = rank; p->c0 = p->c1 = 1;
+    p->nstages = c2r ? 3 : 2;
+    p->y = (b2_plan **)calloc(1, sizeof(b2_plan *));
+    p->x = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));
+    p->z = (b2_plan **)calloc(1, sizeof(b2_plan *));
+    p->g = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));
+    if (!p->y || !p->x || !p->z || !p->g) goto fail;
+    if (ln0 > 0) {
+        /* the local real pass over the rows */
+        init_problem(&q, flags | (c2r ? B2F_DESTROY_INPUT : 0));
+        q.kind = c2r ? B2_C2R : B2_R2C;
+        dim(&q.sz, n2, c2r ? 2 : 1, c2r ? 1 : 2);
+        dim(&q.vecsz, ln0 * n1, 2 * h, 2 * h);
+        if (c2r) { q.in0 = (double *)cplx; q.in1 = (double *)cplx + 1; q.out0 = real; }
+        else { q.in0 = real; q.out0 = (double *)cplx; q.out1 = (double *)cplx + 1; }
+        if (c2r) p->post = b2_mkplan(&q); else p->pre = b2_mkplan(&q);
+        if (!(c2r ? p->post : p->pre)) goto fail;
+        /* c2c along n1 on [ln0][n1][h], rows k1 -> peer k1 / b1: [n0][b1][h] at (my first plane + i0, k1 % b1, k2) */
+        init_problem(&q, flags);
+        dim(&q.sz, n1, 2 * h, 2 * h);
+        dim(&q.vecsz, ln0, 2 * n1 * h, 2 * b1 * h);
+        dim(&q.vecsz, h, 2, 2);
+        set_ptrs(&q, (double *)cplx, (double *)zbuf, sign);       /* zbuf only stands in while planning */
+        p->x[0] = b2_mkplan(&q);
+        if (!p->x[0]) goto fail;
+        if (p->x[0]->nsteps != 1 || rowsplit(p->x[0], nranks, b1, push_targets, 0, 2 * h)) goto fail;
+        p->x_fused[0] = 1;
+    }
+    {
+        /* c2c along n0 on zbuf = [n0][b1][h], rows k0 -> owner k0 / b0: [ln0][n1][h] at (k0 % b0, my first column + k1', k2) */
+        init_problem(&q, flags);
+        dim(&q.sz, n0, 2 * b1 * h, 2 * b1 * h);
+        dim(&q.vecsz, b1 * h, 2, 2);
+        set_ptrs(&q, (double *)zbuf, (double *)zbuf, sign);
+        p->z[0] = b2_mkplan(&q);
+        if (!p->z[0]) goto fail;
+        if (p->z[0]->nsteps != 1 || p->z[0]->steps[0].u.fft.bn[1] != 1 ||
+            rowsplit(p->z[0], nranks, b0, out_targets, 2 * (b1 * rank) * h, 2 * n1 * h)) goto fail;
+    }
+    return p;
+fail:
+    fftw_b200_dist_destroy_plan(p);
+    return NULL;
+}
+
+dplan fftw_b200_dist_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                     double *real_in, C *cplx_out, C *zbuf, void *const *push_targets,
+                                     void *const *out_targets, unsigned flags)
+{
+    return mkdist_real(0, n0, n1, n2, rank, nranks, real_in, cplx_out, zbuf, push_targets, out_targets, flags);
+}
+
+dplan fftw_b200_dist_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                     C *cplx_in, double *real_out, C *zbuf, void *const *push_targets,
+                                     void *const *out_targets, unsigned flags)
+{
+    return mkdist_real(1, n0, n1, n2, rank, nranks, real_out, cplx_in, zbuf, push_targets, out_targets, flags);
+}
+
 ptrdiff_t fftw_b200_ipc_offset(void *devptr) { return (ptrdiff_t)b2d_alloc_offset(devptr); }
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
@@ -290,8 +383,11 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
     int d, saved = b2_async_mode;
     void *mainst = b2d_get_stream();
     b2_async_mode = 1;
-    if (stage == 0 && c < p->c0) {
+    if (stage == 2 && p->post) {
+        if (c == 0) run(p->post);
+    } else if (stage == 0 && c < p->c0) {
         void *aux = b2d_aux_stream(0);
+        if (c == 0) run(p->pre);
         run(p->y[c]);
         if (aux) { b2d_stream_wait_stream(aux, mainst); b2d_set_stream(aux); }
         if (p->x_fused[c]) run(p->x[c * p->nranks]);

@@ -40,6 +40,9 @@ def _declare(lib):
     L.fftw_b200_dist_plan_dft_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
     L.fftw_b200_dist_plan_dft_3d_push.restype = P
     L.fftw_b200_dist_plan_dft_3d_push.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, I, C.c_uint]
+    for name in ("fftw_b200_dist_plan_dft_r2c_3d", "fftw_b200_dist_plan_dft_c2r_3d"):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, P, C.c_uint]
     L.fftw_b200_ipc_offset.restype = C.c_ssize_t
     L.fftw_b200_ipc_offset.argtypes = [P]
     L.fftw_b200_dist_num_stages.argtypes = [P]
@@ -259,6 +262,98 @@ class SlabPlan3D:
             if self.nstages == 3:
                 self._alltoall(self.recv2, self.recv2_counts, self.recv, self.send2_counts)
                 L.fftw_b200_dist_execute_stage(self.plan, 2)
+
+    def destroy(self):
+        if self.plan:
+            self.L.fftw_b200_dist_destroy_plan(self.plan)
+            self.plan = None
+        if self.P > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.L.fftw_b200_ipc_close(p)
+        for p in self._owned:
+            self.L.fftw_b200_device_free(p)
+        self._opened, self._owned = [], []
+
+
+def _map_peers(L, group, rank, P, ptr):
+    """Every rank exports the allocation `ptr` lives in (CUDA IPC) and maps all the others;
+    returns (list of P device pointers addressing each rank's `ptr`, list of mappings to close)."""
+    off = int(L.fftw_b200_ipc_offset(ptr))
+    assert off >= 0, "cannot locate the allocation of a device pointer"
+    hb = C.create_string_buffer(64)
+    assert L.fftw_b200_ipc_export(ptr - off, hb) == 0, "cudaIpcGetMemHandle failed"
+    got = [None] * P
+    dist.all_gather_object(got, (bytes(hb.raw), off), group=group)
+    ptrs, opened = [], []
+    for s in range(P):
+        if s == rank:
+            ptrs.append(ptr)
+        else:
+            base = L.fftw_b200_ipc_import(got[s][0])
+            assert base, "cudaIpcOpenMemHandle failed for rank %d" % s
+            opened.append(base)
+            ptrs.append(base + got[s][1])
+    return ptrs, opened
+
+
+class SlabPlanReal3D:
+    """Distributed r2c / c2r of an n0 x n1 x n2 real array (fftw_mpi_plan_dft_r2c_3d / _c2r_3d;
+    C-ABI: fftw_b200_dist_plan_dft_r2c_3d / _c2r_3d in include/fftw3_b200_dist.h).
+
+    ``real``  float64 CUDA tensor holding this rank's slab [local_n0][n1][2*(n2//2+1)] (padded rows),
+    ``cplx``  complex128 CUDA tensor [local_n0][n1][n2//2+1]; pass ``real.view(torch.complex128)``
+              for an in-place transform.  Peer exchange only (both exchanges are stores of FFT
+              passes into peer memory); needs n1 % world_size == 0.
+    """
+
+    def __init__(self, lib, n0, n1, n2, real, cplx, direction="r2c", group=None, flags=B.FFTW_MEASURE):
+        _declare(lib)
+        self.lib, self.L = lib, lib.lib
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.direction = direction
+        P, r = self.P, self.rank
+        assert n1 % P == 0, "distributed real transforms need n1 divisible by the number of ranks"
+        h = n2 // 2 + 1
+        b0, b1 = _blk(n0, P), n1 // P
+        self.ln0, self.s0 = _share(n0, P, r), min(b0 * r, n0)
+        assert real.is_cuda and cplx.is_cuda and real.dtype == torch.float64 and cplx.dtype == torch.complex128
+        assert real.numel() >= self.ln0 * n1 * 2 * h and cplx.numel() >= self.ln0 * n1 * h
+        self.real, self.cplx = real, cplx
+        self._owned, self._opened = [], []
+        zbytes = 16 * max(P * b0 * b1 * h, 1)
+        self.zptr = self.L.fftw_b200_device_malloc(zbytes)
+        assert self.zptr, "device allocation of %d bytes failed" % zbytes
+        self._owned.append(self.zptr)
+        if P > 1:
+            zpeers, o1 = _map_peers(self.L, group, r, P, self.zptr)
+            cpeers, o2 = _map_peers(self.L, group, r, P, cplx.data_ptr())
+            self._opened += o1 + o2
+        else:
+            zpeers, cpeers = [self.zptr], [cplx.data_ptr()]
+        VP = C.c_void_p * P
+        push = VP(*[zpeers[d] + 16 * (r * b0) * b1 * h for d in range(P)])
+        out = VP(*cpeers)
+        fn = self.L.fftw_b200_dist_plan_dft_r2c_3d if direction == "r2c" else self.L.fftw_b200_dist_plan_dft_c2r_3d
+        a, b = (real.data_ptr(), cplx.data_ptr()) if direction == "r2c" else (cplx.data_ptr(), real.data_ptr())
+        self.plan = fn(n0, n1, n2, r, P, a, b, self.zptr, push, out, int(flags))
+        assert self.plan, "distributed %s plan returned NULL" % direction
+        self._token = torch.zeros(1, device=real.device)
+
+    def _barrier(self):
+        if self.P > 1:
+            dist.all_reduce(self._token, group=self.group)
+
+    def execute(self):
+        L = self.L
+        L.fftw_b200_dist_execute_stage(self.plan, 0)
+        self._barrier()                     # exchange buffers complete
+        L.fftw_b200_dist_execute_stage(self.plan, 1)
+        self._barrier()                     # every rank's rows have landed in my complex slab
+        if self.direction == "c2r":
+            L.fftw_b200_dist_execute_stage(self.plan, 2)
 
     def destroy(self):
         if self.plan:

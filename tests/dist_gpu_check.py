@@ -65,6 +65,46 @@ def main():
                     ok &= good
                     print("dist check %s P=%d %-11s transposed=%d push=%d rel L2 %.2e %s"
                           % (shape, world, exchange, transposed, pushed, err, "OK" if good else "FAIL"), flush=True)
+    # real data: r2c then c2r (round trip) of padded slabs; needs n1 % world == 0
+    for shape in [(64, 16 * world, 50), (24, 8 * world, 33), (128, 128, 128)]:
+        n0, n1, n2 = shape
+        h = n2 // 2 + 1
+        rng = np.random.default_rng(7)
+        full = rng.uniform(-0.5, 0.5, shape)
+        ref = O.r2c(full, rank=3) if rank == 0 else None
+        for inplace in (False, True):
+            alloc, ln0, s0, ln1, s1 = D.local_size_3d(lib, n0, n1, n2, rank, world)
+            real = torch.zeros(max(ln0, 1) * n1 * 2 * h, dtype=torch.float64, device="cuda")
+            if ln0:
+                pad = np.zeros((ln0, n1, 2 * h))
+                pad[:, :, :n2] = full[s0:s0 + ln0]
+                real[:pad.size] = torch.from_numpy(pad.reshape(-1)).cuda()
+            cplx = real.view(torch.complex128) if inplace else torch.zeros(max(ln0, 1) * n1 * h, dtype=torch.complex128,
+                                                                          device="cuda")
+            fw = D.SlabPlanReal3D(lib, n0, n1, n2, real, cplx, "r2c", flags=B.FFTW_ESTIMATE)
+            fw.execute()
+            torch.cuda.synchronize()
+            spec = cplx[:ln0 * n1 * h].cpu().numpy().copy()
+            fw.destroy()
+            bw = D.SlabPlanReal3D(lib, n0, n1, n2, real, cplx, "c2r", flags=B.FFTW_ESTIMATE)
+            bw.execute()
+            torch.cuda.synchronize()
+            back = real[:ln0 * n1 * 2 * h].cpu().numpy().reshape(ln0, n1, 2 * h)[:, :, :n2] / (n0 * n1 * n2) if ln0 else None
+            bw.destroy()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (s0, ln0, spec, back))
+            if rank == 0:
+                got = np.zeros((n0, n1, h), dtype=np.complex128)
+                rt = np.zeros(shape)
+                for start, c, sp, bk in gathered:
+                    if c:
+                        got[start:start + c] = sp.reshape(c, n1, h)
+                        rt[start:start + c] = bk
+                e1, e2 = O.rel_l2(got, ref), O.rel_l2(rt, full)
+                good = e1 < 5e-15 and e2 < 5e-15
+                ok &= good
+                print("dist check %s P=%d r2c/c2r inplace=%d rel L2 fwd %.2e roundtrip %.2e %s"
+                      % (shape, world, inplace, e1, e2, "OK" if good else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
