@@ -93,6 +93,7 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
         return r2r_pre_value<T>(p.r2r_kind, p.n_in, k, (const cplx<T> *)p.aux0, x);
     }
     cplx<T> z;
+    if (op & B2D_LOAD_RADER) k = ((const int *)p.aux0)[k];          // a_q = x[g^q mod n]
     if ((op & B2D_LOAD_PAD) && k >= p.n_in) { z.x = T(0); z.y = T(0); return z; }
     if (op & B2D_LOAD_REAL) {
         z.x = re[boff + (int64_t)k * p.is]; z.y = T(0);
@@ -141,6 +142,10 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
         int64_t eh = e / p.aux_split, el = e - eh * p.aux_split;
         cplx<T> w = cmul(((const cplx<T> *)p.aux1)[eh], ((const cplx<T> *)p.aux0)[el]);
         z = cmul(z, w);
+    }
+    if (op & B2D_STORE_RADER) {     // X[g^-m mod n] = x_0 + conv_m (x_0 was folded into bin 0 before the inverse)
+        k = ((const int *)p.aux0)[p.n + k];
+        z.x *= (T)p.scale; z.y *= (T)p.scale;
     }
     if (op & B2D_STORE_CHIRP_SCALE) {
         z = cmul(z, ((const cplx<T> *)p.aux0)[k]);
@@ -376,15 +381,27 @@ B2_HD void phase_stage(const b2d_fft_pass &p, int stage, int ns, const cplx<T> *
 // Bluestein mid-phase: z[k] = conj(z[k] * B[k])  (the conj turns the second
 // forward run into an inverse transform; undone in phase_store)
 template <typename T>
-B2_HD void phase_pointwise(const b2d_fft_pass &p, cplx<T> *buf, int pitch, int tid, int nthreads)
+B2_HD void phase_pointwise(const b2d_fft_pass &p, const Smem<T> &s, cplx<T> *buf, int pitch, int tid, int nthreads)
 {
     const int n = p.n;
     const int total = n * p.tpb;
     const cplx<T> *B = (const cplx<T> *)p.aux1;
     for (int idx = tid; idx < total; idx += nthreads) {
         int t = idx / n, k = idx - t * n;
+        if (s.b0[t] < 0) continue;
         cplx<T> *q = buf + (size_t)t * pitch + padk(k);
-        cplx<T> v = cmul(*q, B[k]);
+        cplx<T> a = *q;
+        cplx<T> v = cmul(a, B[k]);
+        if (p.bluestein == 2 && k == 0) {
+            // Rader (dft/rader.c:95-165): bin 0 of the permuted input's transform is the sum of x_1..x_{n-1}:
+            // X_0 = x_0 + A_0 goes straight out; x_0 is added to every convolution output by adding
+            // x_0 * M to bin 0 before the inverse (the store scales by 1/M)
+            const T *re = (const T *)p.in_re, *im = (const T *)p.in_im;
+            T *ore = (T *)p.out_re, *oim = (T *)p.out_im;
+            cplx<T> x0; x0.x = re[s.boff_in[t]]; x0.y = im[s.boff_in[t]];
+            ore[s.boff_out[t]] = x0.x + a.x; oim[s.boff_out[t]] = x0.y + a.y;
+            v.x += x0.x * (T)n; v.y += x0.y * (T)n;
+        }
         v.y = -v.y;
         *q = v;
     }
@@ -434,7 +451,7 @@ __global__ void fft_generic_kernel(const __grid_constant__ b2d_fft_pass p, int s
             cplx<T> *tmp = src; src = dst; dst = tmp;
         }
         if (p.bluestein && rep == 0) {
-            phase_pointwise<T>(p, src, s.pitch, tid, nthreads);
+            phase_pointwise<T>(p, s, src, s.pitch, tid, nthreads);
             __syncthreads();
         }
     }

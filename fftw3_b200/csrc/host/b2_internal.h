@@ -114,11 +114,15 @@ enum { TAB_TWIDDLE = 1,      /* n entries exp(-2 pi i k / n)                    
        TAB_R2C,              /* n/2+1 entries exp(-2 pi i k / n)  (half-size split)  */
        TAB_TW4_LO, TAB_TW4_HI, /* two-level tables for exp(-2 pi i e / n), aux = L  */
        TAB_QUARTER,          /* 2n entries: exp(-pi i k/(2n)) then exp(-pi i (2k+1)/(4n)) */
+       TAB_RADER_PERM,       /* prime n: int32 perm_in[q] = g^q mod n, then perm_out[m] = g^-m mod n (n-1 each) */
+       TAB_RADER_B,          /* prime n: FFT_{n-1} of b_q = exp(-2 pi i g^-q / n)        */
        TAB_COUNT };
 b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux);
 void b2_table_release(b2_table *t);
 void b2_tables_cleanup(void);
 void b2_unit_root_ld(int64_t m, int64_t n, long double *c, long double *s); /* exp(-2 pi i m/n) */
+int  b2_is_prime(int64_t n);
+int64_t b2_primitive_root(int64_t p);     /* smallest generator of (Z/p)^*, p prime (kernel/primes.c:81-122 role) */
 
 /* planner.c */
 b2_plan *b2_mkplan(const b2_problem *prob);

@@ -355,7 +355,8 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     if (!s) return -1;
     f = &s->u.fft;
     f->prec = prec;
-    f->n = (int)(bluestein_m ? bluestein_m : n);
+    /* bluestein_m > 0: Bluestein with padded length M; bluestein_m < 0: Rader (work length n - 1) */
+    f->n = (int)(bluestein_m > 0 ? bluestein_m : (bluestein_m < 0 ? n - 1 : n));
     f->pre_op = ops.pre_op; f->post_op = ops.post_op;
     f->cache = ops.cache;
     f->n_in = ops.n_in ? ops.n_in : (int)n;
@@ -368,7 +369,17 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     f->scale = 1.0;
     f->tw = plan_table(p, prec, TAB_TWIDDLE, f->n, 0);
     if (!f->tw) return -1;
-    if (bluestein_m) {
+    if (bluestein_m < 0) {
+        /* Rader (dft/rader.c:95-165): x permuted by generator powers, cyclic convolution of length n - 1 with
+           the permuted roots of unity (two FFTs of that length in the same CTA), outputs permuted back */
+        f->bluestein = 2;
+        f->pre_op |= B2D_LOAD_RADER;
+        f->post_op |= B2D_STORE_RADER;
+        f->scale = 1.0 / (double)(n - 1);
+        f->aux0 = plan_table(p, prec, TAB_RADER_PERM, n, 0);
+        f->aux1 = plan_table(p, prec, TAB_RADER_B, n, 0);
+        if (!f->aux0 || !f->aux1) return -1;
+    } else if (bluestein_m) {
         f->bluestein = 1;
         f->pre_op |= B2D_LOAD_PAD | B2D_LOAD_CHIRP;
         f->post_op |= B2D_STORE_TRUNC | B2D_STORE_CHIRP_SCALE;
@@ -524,6 +535,27 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
     if (!smooth) {
         /* Bluestein (dft/bluestein.c:82-128): one CTA does chirp, FFT_M, x B, IFFT_M, chirp */
         int64_t m = next_pow2(2 * n - 1);
+        /* Rader for primes whose n - 1 is smooth and fits one CTA: half the transform length of
+           Bluestein.  Taken when no register-resident Bluestein kernel exists for M (those beat the
+           generic kernel by more than the length ratio); FFTW3_B200_PRIME=rader|bluestein overrides. */
+        {
+            const char *force = getenv("FFTW3_B200_PRIME");
+            int rr[64];
+            int can = !c->ops.pre_op && !c->ops.post_op && n >= 5 && n < 2000000000 && b2_is_prime(n) &&
+                      b2_factorize(n - 1, c->prec, 0, rr) != 0 && single_pass_fits(n - 1, c->prec);
+            int want = can;
+            if (can && !(force && !strcmp(force, "rader"))) {
+                b2d_fft_pass probe;
+                memset(&probe, 0, sizeof probe);
+                probe.prec = c->prec; probe.n = (int)m; probe.bluestein = 1;
+                probe.pre_op = B2D_LOAD_PAD | B2D_LOAD_CHIRP; probe.post_op = B2D_STORE_TRUNC | B2D_STORE_CHIRP_SCALE;
+                probe.is = in.stride; probe.os = out.stride;
+                if (single_pass_fits(m, c->prec) && in.stride == 2 && out.stride == 2 &&
+                    (b2d_fast_available(&probe, 701) || b2d_fast_available(&probe, 702))) want = 0;
+            }
+            if (force && !strcmp(force, "bluestein")) want = 0;
+            if (want) return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, -1, "rader");
+        }
         if (single_pass_fits(m, c->prec))
             return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, (int)m, "bluestein");
         /* padded length too long for one CTA: chirp.pad kernel, FFT_M (four-step), x B, FFT_M,
@@ -1404,7 +1436,7 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
-                    q->bluestein ? " bluestein" : "");
+                    q->bluestein == 2 ? " rader" : (q->bluestein ? " bluestein" : ""));
         } else if (s->kind == STEP_COPY) {
             fprintf(f, "\n  (copy %lldx%lldx%lldx%lld)", (long long)s->u.copy.n[0], (long long)s->u.copy.n[1],
                     (long long)s->u.copy.n[2], (long long)s->u.copy.n[3]);

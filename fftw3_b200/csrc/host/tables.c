@@ -33,6 +33,36 @@ void b2_unit_root_ld(int64_t m, int64_t n, long double *c, long double *s)
     *s = -ss;
 }
 
+int b2_is_prime(int64_t n)
+{
+    int64_t d;
+    if (n < 2) return 0;
+    for (d = 2; d * d <= n; ++d) if (n % d == 0) return 0;
+    return 1;
+}
+
+static int64_t powmod(int64_t b, int64_t e, int64_t m)
+{
+    __int128 r = 1, x = b % m;
+    while (e > 0) { if (e & 1) r = r * x % m; x = x * x % m; e >>= 1; }
+    return (int64_t)r;
+}
+
+int64_t b2_primitive_root(int64_t p)
+{
+    int64_t fac[64], nf = 0, m = p - 1, d, g;
+    for (d = 2; d * d <= m; ++d)
+        if (m % d == 0) { fac[nf++] = d; while (m % d == 0) m /= d; }
+    if (m > 1) fac[nf++] = m;
+    for (g = 2; g < p; ++g) {
+        int ok = 1;
+        int64_t i;
+        for (i = 0; i < nf && ok; ++i) if (powmod(g, (p - 1) / fac[i], p) == 1) ok = 0;
+        if (ok) return g;
+    }
+    return p == 2 ? 1 : 0;
+}
+
 static void put(void *host, int prec, int64_t i, long double re, long double im)
 {
     if (prec == B2D_F32) { ((float *)host)[2 * i] = (float)re; ((float *)host)[2 * i + 1] = (float)im; }
@@ -58,6 +88,8 @@ b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux)
     case TAB_TW4_LO: count = aux; break;
     case TAB_TW4_HI: count = (n + aux - 1) / aux; break;
     case TAB_QUARTER: count = 2 * n; break;
+    case TAB_RADER_PERM: count = (int64_t)((2 * (size_t)(n - 1) * sizeof(int) + esz - 1) / esz); break;
+    case TAB_RADER_B: count = n - 1; break;
     default: return NULL;
     }
     host = malloc((size_t)(count ? count : 1) * esz);
@@ -84,6 +116,18 @@ b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux)
             if (i > 0) put(host, prec, aux - i, c, -s);
         }
         break;
+    case TAB_RADER_PERM: case TAB_RADER_B: {
+        /* generator powers: perm_in[q] = g^q, perm_out[m] = g^-m = perm_in[(M - m) % M]  (dft/rader.c:95-165) */
+        int64_t M = n - 1, g = b2_primitive_root(n), v = 1;
+        int *pin = (int *)malloc((size_t)(2 * M) * sizeof(int)), *pout = pin + M;
+        if (!pin || g <= 0) { free(pin); free(host); return NULL; }
+        for (i = 0; i < M; ++i) { pin[i] = (int)v; v = (int64_t)((__int128)v * g % n); }
+        for (i = 0; i < M; ++i) pout[i] = pin[(M - i) % M];
+        if (kind == TAB_RADER_PERM) memcpy(host, pin, (size_t)(2 * M) * sizeof(int));
+        else for (i = 0; i < M; ++i) { b2_unit_root_ld(pout[i], n, &c, &s); put(host, prec, i, c, s); }
+        free(pin);
+        break;
+    }
     case TAB_QUARTER:
         for (i = 0; i < n; ++i) {
             b2_unit_root_ld(i, 4 * n, &c, &s); put(host, prec, i, c, s);              /* exp(-pi i k/(2n)) */
@@ -101,6 +145,10 @@ b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux)
         return NULL;
     }
     free(host);
+    if (kind == TAB_RADER_B && b2_run_contig_fft(prec, n - 1, t->dev)) {
+        b2d_free(t->dev); free(t);
+        return NULL;
+    }
     if (kind == TAB_BLUE_B && b2_run_contig_fft(prec, aux, t->dev)) {
         b2d_free(t->dev); free(t);
         return NULL;

@@ -32,6 +32,8 @@ enum {
                                reads in[n_in-k]; imag of self-mirrored bins ignored   */
     B2D_LOAD_PAD = 4,       /* k >= n_in reads as zero                               */
     B2D_LOAD_CHIRP = 8,     /* multiply by aux0[k] (Bluestein chirp)                 */
+    B2D_LOAD_RADER = 32,    /* element k comes from input index perm[k] (aux0: int32 perm_in[n], perm_out[n]);
+                               Rader's prime-size algorithm, bluestein == 2            */
     B2D_LOAD_R2R = 16       /* real line of n_in elements -> complex work sequence of length n by
                                the PRE map of r2r_kind (aux0 = quarter-wave table)     */
 };
@@ -42,6 +44,7 @@ enum {
     B2D_STORE_TRUNC = 2,       /* store only k < n_out                                */
     B2D_STORE_CHIRP_SCALE = 4, /* Bluestein: z * aux0[k] * scale                      */
     B2D_STORE_TWIDDLE4 = 8,    /* four-step: z *= W_big^(k * b0) (two-level tables)   */
+    B2D_STORE_RADER = 32,      /* element k goes to output index perm_out[k], times scale */
     B2D_STORE_R2R = 16         /* output k scattered into the real line of n_out elements by the
                                   POST map of r2r_kind                                 */
 };

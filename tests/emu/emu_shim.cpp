@@ -56,7 +56,7 @@ static void run_fft_pass(const b2d_fft_pass &p)
                 cplx<T> *tmp = src; src = dst; dst = tmp;
             }
             if (p.bluestein && rep == 0)
-                for (int t = 0; t < nthreads; ++t) phase_pointwise<T>(p, src, s.pitch, t, nthreads);
+                for (int t = 0; t < nthreads; ++t) phase_pointwise<T>(p, s, src, s.pitch, t, nthreads);
         }
         for (int t = 0; t < nthreads; ++t) {
             if (plain) phase_store_plain<T>(p, s, src, t, nthreads, swo); else phase_store<T>(p, s, c, src, t, nthreads);

@@ -406,3 +406,20 @@ def test_r2r_fused_maps_and_long_strided_lines(gpu_lib, prec, shape, kinds, inpl
     other r2r tests."""
     err, tol = F.r2r(gpu_lib, prec, shape, list(kinds), inplace=inplace)
     assert err <= tol, (prec, shape, kinds, err, tol)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("mode", ["rader", "bluestein"])
+def test_prime_sizes_rader_and_bluestein(gpu_lib, prec, mode, monkeypatch):
+    """Prime sizes through both algorithms (dft/rader.c:95-165, dft/bluestein.c:82-128): forced
+    Rader (n - 1 smooth, one CTA), forced Bluestein, 1-d batches, both signs, and as a dimension
+    of a 2-d in-place transform."""
+    monkeypatch.setenv("FFTW3_B200_PRIME", mode)
+    for n in (5, 7, 13, 17, 31, 101, 257, 1009, 2017, 4099):
+        for sign in (-1, 1):
+            err, tol = F.c2c(gpu_lib, prec, (n,), howmany=33, sign=sign)
+            assert err <= 4 * tol, (mode, n, sign, err, tol)
+    err, tol = F.c2c(gpu_lib, prec, (40, 1009), howmany=1, inplace=True)
+    assert err <= 4 * tol
+    err, tol = F.c2c(gpu_lib, prec, (1009, 24), howmany=2, inplace=False)
+    assert err <= 4 * tol

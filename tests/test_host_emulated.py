@@ -258,3 +258,20 @@ def test_r2r_long_strided_lines(emu_lib, shape, kinds, inplace):
     the other dimensions run the PRE/POST maps inside one pass (device/r2r_maps.cuh)."""
     err, tol = F.r2r(emu_lib, "d", shape, list(kinds), inplace=inplace)
     assert err <= tol, (shape, kinds, err)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("n", [5, 7, 11, 13, 17, 31, 101, 1009, 2017])
+def test_rader_primes(emu_lib, prec, n, monkeypatch):
+    """Primes whose n - 1 is smooth: Rader's algorithm in one pass (dft/rader.c:95-165) --
+    generator-power permutation, length n-1 cyclic convolution, inverse permutation."""
+    monkeypatch.setenv("FFTW3_B200_PRIME", "rader")
+    for sign in (-1, 1):
+        err, tol = F.c2c(emu_lib, prec, (n,), howmany=3, sign=sign)
+        assert err <= 4 * tol, (n, sign, err, tol)
+    err, tol = F.c2c(emu_lib, prec, (6, n), howmany=1, inplace=True)
+    assert err <= 4 * tol
+    x = np.zeros(n, dtype=np.complex128 if prec == "d" else np.complex64)
+    p = emu_lib.plan_many_dft(prec, [n], 1, x.ctypes.data, None, 1, n, x.ctypes.data, None, 1, n, -1, B.FFTW_ESTIMATE)
+    assert ("rader" in emu_lib.sprint_plan(prec, p)) == (n > 13)      # radices up to 13 are direct butterflies
+    emu_lib.destroy_plan(prec, p)
