@@ -276,6 +276,47 @@ class SlabPlan3D:
         self._opened, self._owned = [], []
 
 
+def batch_share(howmany, rank, nranks):
+    """(count, first) of the transforms rank `rank` owns when a batch of `howmany` independent
+    transforms is block-distributed (mpi/block.c:37-50 applied to the batch index)."""
+    b = _blk(howmany, nranks)
+    first = min(b * rank, howmany)
+    return max(0, min(b, howmany - first)), first
+
+
+class ShardedBatchPlan:
+    """Batched 1-D c2c over several GPUs: the batch index is block-distributed and every rank
+    transforms its own share with an ordinary single-GPU plan -- independent units, NO collective
+    on the data path (the reference's counterpart is the `howmany` loop of
+    dft/vrank-geq1.c:54-65 spread over MPI ranks by the caller).
+
+    ``local`` holds this rank's transforms contiguously: [count][n] complex (device or host)."""
+
+    def __init__(self, lib, n, howmany, local_in, local_out=None, prec="d", sign=B.FFTW_FORWARD,
+                 flags=B.FFTW_MEASURE, group=None):
+        self.lib = lib
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.count, self.first = batch_share(howmany, self.rank, self.P)
+        self.prec = prec
+        self.plan = None
+        if self.count:
+            pin = local_in.data_ptr() if hasattr(local_in, "data_ptr") else local_in.ctypes.data
+            out = local_in if local_out is None else local_out
+            pout = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+            self.plan = lib.plan_many_dft(prec, [n], self.count, pin, None, 1, n, pout, None, 1, n, sign, flags)
+            assert self.plan, "plan_many_dft returned NULL"
+
+    def execute(self):
+        if self.plan:
+            self.lib.execute(self.prec, self.plan)
+
+    def destroy(self):
+        if self.plan:
+            self.lib.destroy_plan(self.prec, self.plan)
+            self.plan = None
+
+
 def _map_peers(L, group, rank, P, ptr):
     """Every rank exports the allocation `ptr` lives in (CUDA IPC) and maps all the others;
     returns (list of P device pointers addressing each rank's `ptr`, list of mappings to close)."""

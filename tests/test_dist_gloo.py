@@ -86,3 +86,50 @@ def test_slab_3d_matches_oracle(emu_lib, world, shape, transposed, sign):
         else:
             got[start:start + cnt] = out
     assert O.rel_l2(got, ref) < 1e-14
+
+
+def _batch_worker(rank, world, port, n, howmany, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fftw3_b200 import binding as B
+        from fftw3_b200 import dist as D
+        lib = B.Lib(os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
+        rng = np.random.default_rng(9)
+        full = rng.uniform(-0.5, 0.5, (howmany, n)) + 1j * rng.uniform(-0.5, 0.5, (howmany, n))
+        count, first = D.batch_share(howmany, rank, world)
+        local = np.ascontiguousarray(full[first:first + count]) if count else np.zeros((1, n), dtype=np.complex128)
+        plan = D.ShardedBatchPlan(lib, n, howmany, local, flags=B.FFTW_ESTIMATE)
+        plan.execute()
+        plan.destroy()
+        q.put((rank, first, count, local[:count].copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,howmany", [(2, 64, 10), (3, 30, 7), (4, 16, 3)])
+def test_batched_1d_shards_without_collective(emu_lib, world, n, howmany):
+    """Independent transforms are block-distributed over the ranks and need no exchange
+    (SURVEY.md section 8e): every rank plans its share; the union equals the oracle."""
+    from oracle import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, n, howmany, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    parts = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(9)
+    full = rng.uniform(-0.5, 0.5, (howmany, n)) + 1j * rng.uniform(-0.5, 0.5, (howmany, n))
+    got = np.zeros_like(full)
+    seen = 0
+    for rank, first, count, arr in parts:
+        got[first:first + count] = arr
+        seen += count
+    assert seen == howmany
+    assert O.rel_l2(got, O.dft(full, rank=1)) < 1e-14
