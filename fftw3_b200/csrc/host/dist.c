@@ -291,7 +291,7 @@ dplan fftw_b200_dist_plan_dft_3d_push(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, 
                    straight into the peers' exchange buffers [n0][n1/P][h] (row-split stores)
           stage 1: c2c along n0, rows stored straight into the owners' complex slabs
      c2r  stages 0/1 the same with backward c2c passes, stage 2: local c2r of the rows.
-   Equal column blocks only (n1 % nranks == 0); NULL otherwise. */
+   Uneven blocks: every exchange buffer uses the row pitch b1 = ceil(n1 / nranks). */
 static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
                          double *real, C *cplx, C *zbuf, void *const *push_targets, void *const *out_targets,
                          unsigned flags)
@@ -299,10 +299,10 @@ static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int 
     dplan p;
     b2_problem q;
     int64_t h = n2 / 2 + 1, b0 = blk(n0, nranks), b1 = blk(n1, nranks);
-    int64_t ln0 = share(n0, nranks, rank);
+    int64_t ln0 = share(n0, nranks, rank), ln1 = share(n1, nranks, rank);
     int sign = c2r ? +1 : -1;
     if (n0 <= 0 || n1 <= 0 || n2 <= 0 || nranks < 1 || rank < 0 || rank >= nranks || nranks > B2D_MAX_PEERS) return NULL;
-    if (n1 % nranks || !push_targets || !out_targets) return NULL;
+    if (!push_targets || !out_targets) return NULL;
     if (b2d_pointer_is_device(zbuf) != 1 || b2d_pointer_is_device(cplx) != 1) return NULL;
     p = (dplan)calloc(1, sizeof *p);
     if (!p) return NULL;
@@ -334,11 +334,12 @@ static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int 
         if (p->x[0]->nsteps != 1 || rowsplit(p->x[0], nranks, b1, push_targets, 0, 2 * h)) goto fail;
         p->x_fused[0] = 1;
     }
-    {
-        /* c2c along n0 on zbuf = [n0][b1][h], rows k0 -> owner k0 / b0: [ln0][n1][h] at (k0 % b0, my first column + k1', k2) */
+    if (ln1 > 0) {
+        /* c2c along n0 on zbuf = [n0][b1][h] (row pitch b1 = the block size on every rank; this rank fills
+           ln1 <= b1 of them), rows k0 -> owner k0 / b0: [ln0][n1][h] at (k0 % b0, my first column + k1', k2) */
         init_problem(&q, flags);
         dim(&q.sz, n0, 2 * b1 * h, 2 * b1 * h);
-        dim(&q.vecsz, b1 * h, 2, 2);
+        dim(&q.vecsz, ln1 * h, 2, 2);
         set_ptrs(&q, (double *)zbuf, (double *)zbuf, sign);
         p->z[0] = b2_mkplan(&q);
         if (!p->z[0]) goto fail;

@@ -345,7 +345,7 @@ class SlabPlanReal3D:
     ``real``  float64 CUDA tensor holding this rank's slab [local_n0][n1][2*(n2//2+1)] (padded rows),
     ``cplx``  complex128 CUDA tensor [local_n0][n1][n2//2+1]; pass ``real.view(torch.complex128)``
               for an in-place transform.  Peer exchange only (both exchanges are stores of FFT
-              passes into peer memory); needs n1 % world_size == 0.
+              passes into peer memory).
     """
 
     def __init__(self, lib, n0, n1, n2, real, cplx, direction="r2c", group=None, flags=B.FFTW_MEASURE):
@@ -356,9 +356,8 @@ class SlabPlanReal3D:
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.direction = direction
         P, r = self.P, self.rank
-        assert n1 % P == 0, "distributed real transforms need n1 divisible by the number of ranks"
         h = n2 // 2 + 1
-        b0, b1 = _blk(n0, P), n1 // P
+        b0, b1 = _blk(n0, P), _blk(n1, P)
         self.ln0, self.s0 = _share(n0, P, r), min(b0 * r, n0)
         assert real.is_cuda and cplx.is_cuda and real.dtype == torch.float64 and cplx.dtype == torch.complex128
         assert real.numel() >= self.ln0 * n1 * 2 * h and cplx.numel() >= self.ln0 * n1 * h

@@ -65,12 +65,13 @@ fftw_b200_dist_plan fftw_b200_dist_plan_dft_3d_push(ptrdiff_t n0, ptrdiff_t n1, 
                                                     int sign, unsigned flags);
 /* Real data (fftw_mpi_plan_dft_r2c_3d / _c2r_3d, mpi/api.c:650-760): the real slab is
  * [local_n0][n1][2*(n2/2+1)] (padded rows; it may alias the complex slab), the complex slab
- * [local_n0][n1][n2/2+1]; zbuf holds [n0][n1/nranks][n2/2+1].  Both exchanges ride on pass stores:
- *   push_targets[d] = rank d's zbuf + 2*(first plane of this rank)*(n1/nranks)*(n2/2+1) doubles,
+ * [local_n0][n1][n2/2+1]; zbuf holds [n0][b1][n2/2+1] with b1 = ceil(n1/nranks) on every rank.
+ * Both exchanges ride on pass stores:
+ *   push_targets[d] = rank d's zbuf + 2*(first plane of this rank)*b1*(n2/2+1) doubles,
  *   out_targets[d]  = rank d's complex slab.
  * r2c: 2 stages (local r2c rows + dim-1 pass scattering rows | dim-0 pass pushing rows), then a
  * barrier.  c2r: the same two stages backward, a barrier, then stage 2 = local c2r of the rows.
- * Requires n1 % nranks == 0 and single-pass n0, n1; NULL otherwise. */
+ * Requires single-pass n0 and n1; NULL otherwise. */
 fftw_b200_dist_plan fftw_b200_dist_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
                                                    double *real_in, fftw_complex *cplx_out, fftw_complex *zbuf,
                                                    void *const *push_targets, void *const *out_targets,

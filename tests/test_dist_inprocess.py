@@ -94,7 +94,7 @@ def _run_real(lib, shape, P, inplace):
     h = n2 // 2 + 1
     rng = np.random.default_rng(3)
     full = rng.uniform(-0.5, 0.5, shape)
-    b0, b1 = (n0 + P - 1) // P, n1 // P
+    b0, b1 = (n0 + P - 1) // P, (n1 + P - 1) // P
     ln0 = [max(0, min(b0, n0 - b0 * r)) for r in range(P)]
     slab_c = max(b0 * n1 * h, 1)                      # complex elements of a slab / of zbuf ([n0][b1][h] <= P*b0*b1*h)
     zb_c = max(P * b0 * b1 * h, 1)
@@ -152,6 +152,8 @@ def _run_real(lib, shape, P, inplace):
 @pytest.mark.parametrize("shape,P", [
     ((8, 6, 10), 2),
     ((12, 9, 7), 3),        # odd last dimension
+    ((12, 10, 7), 3),       # uneven column blocks (4, 4, 2)
+    ((6, 5, 4), 4),         # column blocks (2, 2, 1, 0) and the last rank owns no planes
     ((6, 8, 16), 4),        # block 2: the last rank owns no planes
     ((5, 3, 8), 1),
 ])
