@@ -209,6 +209,11 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     int rep = 0;
     auto emit = [&](int kout, int q, T vr, T vi) {
         if (FLAVOR == 9) {
+            if (p.r2r_pair) {       // two real lines per transform: park, the spectra are separated in flush_col()
+                cplx<T> o; o.x = vr; o.y = vi;
+                sm[sidx(kout)] = o;
+                return;
+            }
             if (valid) {
                 b2::RealLineOut<T> y = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
                 cplx<T> v; v.x = vr; v.y = vi;
@@ -262,6 +267,23 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         }
     };
     auto flush_col = [&]() {
+        if (FLAVOR == 9) {
+            if (!p.r2r_pair) return;
+            __syncthreads();
+            if (!valid) return;
+            const cplx<T> *qt = reinterpret_cast<const cplx<T> *>(p.aux0);
+            b2::RealLineOut<T> ya = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
+            b2::RealLineOut<T> yb = { reinterpret_cast<T *>(p.out_re) + boff_out + p.pair_os, p.os };
+#pragma unroll 4
+            for (int r = 0; r < E; ++r) {
+                const int k = j + r * TPX;
+                cplx<T> u, v;
+                b2::r2r_unpack_pair<T>(sm[sidx(k)], sm[sidx(k ? N - k : 0)], u, v);
+                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, u, qt, ya);
+                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, v, qt, yb);
+            }
+            return;
+        }
         if (FLAVOR != 3) return;
         __syncthreads();
         cplx<T> *gbase = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re);
@@ -286,6 +308,10 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             if (valid) {
                 b2::RealLineIn<T> x = { reinterpret_cast<const T *>(p.in_re) + boff_in, p.is };
                 v = b2::r2r_pre_value<T>(p.r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x);
+                if (p.r2r_pair) {
+                    b2::RealLineIn<T> x2 = { reinterpret_cast<const T *>(p.in_re) + boff_in + p.pair_is, p.is };
+                    v.y = b2::r2r_pre_value<T>(p.r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x2).x;
+                }
             }
         } else if (FLAVOR == 7) {
             const int k = j + r * TPX;

@@ -90,7 +90,12 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
     const int op = p.pre_op;
     if (op & B2D_LOAD_R2R) {        // real line -> work sequence of the r2r kind (r2r_maps.cuh)
         RealLineIn<T> x = { (const T *)p.in_re + boff, p.is };
-        return r2r_pre_value<T>(p.r2r_kind, p.n_in, k, (const cplx<T> *)p.aux0, x);
+        cplx<T> u = r2r_pre_value<T>(p.r2r_kind, p.n_in, k, (const cplx<T> *)p.aux0, x);
+        if (p.r2r_pair) {           // second line of the pair rides in the imaginary part
+            RealLineIn<T> x2 = { (const T *)p.in_re + boff + p.pair_is, p.is };
+            u.y = r2r_pre_value<T>(p.r2r_kind, p.n_in, k, (const cplx<T> *)p.aux0, x2).x;
+        }
+        return u;
     }
     cplx<T> z;
     if (op & B2D_LOAD_RADER) k = ((const int *)p.aux0)[k];          // a_q = x[g^q mod n]
@@ -421,6 +426,15 @@ B2_HD void phase_store(const b2d_fft_pass &p, const Smem<T> &s, const TileCtx &c
         if (s.b0[t] < 0) continue;
         cplx<T> z = src[(size_t)t * s.pitch + padk(k)];
         if (p.bluestein) z.y = -z.y;
+        if (p.r2r_pair) {           // two real lines per transform: separate their spectra, POST each
+            cplx<T> zm = src[(size_t)t * s.pitch + padk(k ? n - k : 0)], u, v;
+            r2r_unpack_pair<T>(z, zm, u, v);
+            RealLineOut<T> ya = { (T *)p.out_re + s.boff_out[t], p.os };
+            RealLineOut<T> yb = { (T *)p.out_re + s.boff_out[t] + p.pair_os, p.os };
+            r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, u, (const cplx<T> *)p.aux0, ya);
+            r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, v, (const cplx<T> *)p.aux0, yb);
+            continue;
+        }
         store_elem<T>(p, s.boff_out[t], s.b0[t], c.b2, k, z);
     }
 }

@@ -41,6 +41,21 @@ B2_HD int r2r_work_len(int kind, int n)
     }
 }
 
+// kinds whose PRE sequence is purely real: two lines can share one complex transform
+B2_HD bool r2r_pairable(int kind)
+{
+    return kind == K_R2HC || kind == K_DHT || kind == K_REDFT00 || kind == K_RODFT00 || kind == K_REDFT10 ||
+           kind == K_RODFT10;
+}
+
+// spectra of the two real sequences packed as u + i v, from Z_k and Z_{M-k}
+template <typename T>
+B2_HD void r2r_unpack_pair(cplx<T> zk, cplx<T> zm, cplx<T> &u, cplx<T> &v)
+{
+    u.x = T(0.5) * (zk.x + zm.x); u.y = T(0.5) * (zk.y - zm.y);      // (Z_k + conj Z_{M-k}) / 2
+    v.x = T(0.5) * (zk.y + zm.y); v.y = T(0.5) * (zm.x - zk.x);      // (Z_k - conj Z_{M-k}) / (2 i)
+}
+
 // PRE: work element i (0 <= i < M).  tw = quarter-wave table (TAB_QUARTER of n), used by types 3 and 4.
 template <typename T, typename In>
 B2_HD cplx<T> r2r_pre_value(int kind, int n, int i, const cplx<T> *tw, const In &x)

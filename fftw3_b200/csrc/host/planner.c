@@ -286,6 +286,7 @@ static void pass_span(const b2d_fft_pass *f, int out, int64_t *lo, int64_t *hi)
     int64_t len = out ? (f->n_out ? f->n_out : f->n) : (f->n_in ? f->n_in : f->n);
     int64_t e = (len - 1) * s;
     if (e < 0) mn += e; else mx += e;
+    if (f->r2r_pair) { e = out ? f->pair_os : f->pair_is; if (e < 0) mn += e; else mx += e; }
     for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) {
         int64_t bs = out ? f->bos[i] : f->bis[i];
         e = (f->bn[i] - 1) * bs;
@@ -391,6 +392,14 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     if (f->pre_op & B2D_LOAD_R2R) {
         int k = ops.r2r_kind;
         f->r2r_kind = k;
+        /* kinds with a real PRE sequence (R2HC DHT REDFT00 RODFT00 REDFT10 RODFT10): two neighbouring lines
+           share one complex transform -- half the arithmetic */
+        if ((k == 0 || k == 2 || k == 3 || k == 7 || k == 5 || k == 9) && brank >= 1 && bd[0].n >= 2 &&
+            bd[0].n % 2 == 0 && !getenv("FFTW3_B200_R2R_UNPAIRED")) {
+            f->r2r_pair = 1;
+            f->pair_is = bd[0].is; f->pair_os = bd[0].os;
+            f->bn[0] = bd[0].n / 2; f->bis[0] = 2 * bd[0].is; f->bos[0] = 2 * bd[0].os;
+        }
         if (k == 4 || k == 5 || k == 6 || k == 8 || k == 9 || k == 10) {     /* types 2, 3, 4: quarter-wave table */
             f->aux0 = plan_table(p, prec, TAB_QUARTER, f->n_in, 0);
             if (!f->aux0) return -1;
@@ -1436,7 +1445,7 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
-                    q->bluestein == 2 ? " rader" : (q->bluestein ? " bluestein" : ""));
+                    q->bluestein == 2 ? " rader" : (q->bluestein ? " bluestein" : (q->r2r_pair ? " paired-lines" : "")));
         } else if (s->kind == STEP_COPY) {
             fprintf(f, "\n  (copy %lldx%lldx%lldx%lld)", (long long)s->u.copy.n[0], (long long)s->u.copy.n[1],
                     (long long)s->u.copy.n[2], (long long)s->u.copy.n[3]);

@@ -45,7 +45,7 @@ b2_sig b2_sig_of_pass(const b2d_fft_pass *p, int inplace)
     int k = 0, i;
     v[k++] = p->prec; v[k++] = p->n; v[k++] = p->pre_op; v[k++] = p->post_op;
     v[k++] = p->bluestein; v[k++] = p->n_in; v[k++] = p->n_out;
-    v[k++] = (p->pre_op & B2D_LOAD_R2R) ? p->r2r_kind : -1;
+    v[k++] = (p->pre_op & B2D_LOAD_R2R) ? p->r2r_kind + 16 * p->r2r_pair : -1;
     v[k++] = p->is; v[k++] = p->os; v[k++] = inplace;
     v[k++] = p->load_col; v[k++] = p->store_col;
     for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) { v[k++] = p->bn[i]; v[k++] = p->bis[i]; v[k++] = p->bos[i]; }

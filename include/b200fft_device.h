@@ -68,6 +68,11 @@ typedef struct b2d_fft_pass {
     int kernel;               /* 0: generic runtime-radix kernel; else code of a
                                  specialised kernel: tile width + 1000 for COL      */
     int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
+    /* LOAD_R2R / STORE_R2R, kinds whose PRE sequence is real: r2r_pair != 0 packs TWO lines into one
+       complex transform (line A -> real part, line B = A + pair_is -> imaginary part; the spectra are
+       separated as (Z_k +- conj Z_{n-k}) / 2 before the POST map).  Batch dim 0 then counts pairs. */
+    int r2r_pair;
+    int64_t pair_is, pair_os;
     int r2r_kind;             /* LOAD_R2R / STORE_R2R: 0..10 = R2HC HC2R DHT REDFT00 REDFT01 REDFT10 REDFT11
                                  RODFT00 RODFT01 RODFT10 RODFT11 (the fftw_r2r_kind values)          */
     int64_t is, os;           /* element stride along the transform                  */
