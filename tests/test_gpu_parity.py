@@ -258,7 +258,7 @@ def test_tma_fed_kernel_variants_in_a_child_process():
         "    for prec in ('d', 'f'):\n"
         "        for shape, hm, inplace in (((512, 30), 3, True), ((13, 1024, 20), 1, True), ((1024, 64), 2, True),\n"
         "                                   ((512, 512), 1, False)):\n"
-        "            err, tol = F.c2c(lib, prec, shape, howmany=hm, inplace=inplace, sign=-1 if variant % 2 else 1)\n"
+        "            err, tol = F.c2c(lib, prec, shape, howmany=hm, inplace=inplace, sign=-1 if variant %% 2 else 1)\n"
         "            assert err <= tol, (variant, prec, shape, err, tol)\n"
         "print('tma variants ok')\n" % (ROOT, ROOT))
     last = None
