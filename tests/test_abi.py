@@ -73,3 +73,23 @@ def test_wisdom_tool_command_line():
         r = subprocess.run([os.path.join(libdir, "fftw-wisdom"), "-e", "cof64", "ki10e10x8e01v3", "rib16x6"],
                            capture_output=True, text=True)
         assert r.returncode != 0 and r.stderr.count("could not plan") == 3
+
+
+def _build_example(libdir, libname, out):
+    import subprocess
+    src = os.path.join(ROOT, "examples", "fftw_tutorial.c")
+    subprocess.run(["gcc", "-O1", "-Wall", src, "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-l" + libname, "-lm",
+                    "-Wl,-rpath," + libdir, "-o", out], check=True)
+    return subprocess.run([out], capture_output=True, text=True, timeout=300)
+
+
+def test_plain_fftw_program_links_and_runs(emu_lib, tmp_path):
+    """examples/fftw_tutorial.c uses nothing but fftw3.h (doc/tutorial.texi style).  Its logic is
+    checked here against the host layer on the emulated device; linked against the product
+    library on a box without a GPU it must fail loudly at planning (no CPU fallback)."""
+    r = _build_example(os.path.join(ROOT, "tests", "_emu"), "fftw3_b200_emu", str(tmp_path / "tut_emu"))
+    assert r.returncode == 0 and r.stdout.count(" ok") == 7 and "FAILED" not in r.stdout, r.stdout + r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = _build_example(os.path.join(ROOT, "fftw3_b200", "lib"), "fftw3_b200", str(tmp_path / "tut_gpu"))
+        assert r.returncode == 2 and "planning failed" in r.stderr

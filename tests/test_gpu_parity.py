@@ -423,3 +423,16 @@ def test_prime_sizes_rader_and_bluestein(gpu_lib, prec, mode, monkeypatch):
     assert err <= 4 * tol
     err, tol = F.c2c(gpu_lib, prec, (1009, 24), howmany=2, inplace=False)
     assert err <= 4 * tol
+
+
+def test_plain_fftw_program_on_the_gpu(gpu_lib, tmp_path):
+    """The drop-in claim end to end: examples/fftw_tutorial.c (plain fftw3.h code: c2c, in-place
+    2-d r2c/c2r, DCT-II/III, wisdom) compiled with gcc, linked against libfftw3_b200.so, run."""
+    import subprocess
+    libdir = os.path.join(ROOT, "fftw3_b200", "lib")
+    exe = str(tmp_path / "tutorial")
+    subprocess.run(["gcc", "-O1", "-Wall", os.path.join(ROOT, "examples", "fftw_tutorial.c"),
+                    "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lfftw3_b200", "-lm", "-Wl,-rpath," + libdir,
+                    "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count(" ok") == 7 and "FAILED" not in r.stdout, r.stdout + r.stderr
