@@ -40,6 +40,7 @@ struct fftw_b200_dist_plan_s {
     b2_plan **x;             /* [c0] fused or [c0 * nranks] */
     b2_plan **z;             /* [c1] */
     b2_plan **g;             /* [c1 * nranks] */
+    int real_gather;         /* r2r plan: x[] = stage-1 gathers (before z), g[] = stage-2 gathers */
     b2_plan *pre, *post;     /* real-data plans: local r2c rows before stage 0 / local c2r rows as the last stage */
 };
 typedef struct fftw_b200_dist_plan_s *dplan;
@@ -366,6 +367,89 @@ dplan fftw_b200_dist_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, i
     return mkdist_real(1, n0, n1, n2, rank, nranks, real_out, cplx_in, zbuf, push_targets, out_targets, flags);
 }
 
+/* ---- r2r (fftw_mpi_plan_r2r_3d, mpi/rdft-rank-geq2(-transposed).c, mpi/api.c:770-886): a real
+   n0 x n1 x n2 array, kind[i] along dimension i.  Built from validated pieces only:
+     stage 0  local r2r over (n1, n2) in place on [ln0][n1][n2]
+     stage 1  pull my column block from every rank's slab into zbuf = [n0][ln1][n2] (peer loads),
+              then r2r along n0 in place on zbuf
+     stage 2  pull my planes of every column block back from the peers' zbufs into the slab
+   (the global transposes of mpi/transpose-alltoall.c as gather copies; real rows are not yet
+   scattered by the passes themselves).  The caller puts a barrier before every stage. */
+dplan fftw_b200_dist_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                 double *local, double *zbuf, void *const *peer_locals, void *const *peer_zbufs,
+                                 const int *kinds, unsigned flags)
+{
+    dplan p;
+    b2_problem q;
+    int s;
+    int64_t b0 = blk(n0, nranks), b1 = blk(n1, nranks);
+    int64_t ln0 = share(n0, nranks, rank), ln1 = share(n1, nranks, rank);
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0 || nranks < 1 || rank < 0 || rank >= nranks || !kinds) return NULL;
+    if (!peer_locals || !peer_zbufs) return NULL;
+    p = (dplan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->nranks = nranks; p->rank = rank; p->c0 = p->c1 = 1;
+    p->nstages = 3;
+    p->y = (b2_plan **)calloc(1, sizeof(b2_plan *));
+    p->x = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));      /* stage 1 gathers, one per source */
+    p->z = (b2_plan **)calloc(1, sizeof(b2_plan *));
+    p->g = (b2_plan **)calloc((size_t)nranks, sizeof(b2_plan *));      /* stage 2 gathers */
+    if (!p->y || !p->x || !p->z || !p->g) goto fail;
+    p->real_gather = 1;
+    if (ln0 > 0) {
+        init_problem(&q, flags);
+        q.kind = B2_R2R;
+        dim(&q.sz, n1, n2, n2); dim(&q.sz, n2, 1, 1);
+        q.r2r_kind[0] = kinds[1]; q.r2r_kind[1] = kinds[2];
+        dim(&q.vecsz, ln0, n1 * n2, n1 * n2);
+        q.in0 = local; q.out0 = local;
+        p->y[0] = b2_mkplan(&q);
+        if (!p->y[0]) goto fail;
+    }
+    if (ln1 > 0) {
+        for (s = 0; s < nranks; ++s) {
+            /* block of rank s: [ln0(s)][ln1][n2] at column b1*rank of its slab -> zbuf planes b0*s ... */
+            int64_t l0 = share(n0, nranks, s);
+            if (!l0) continue;
+            init_problem(&q, flags | B2F_ESTIMATE);
+            q.kind = B2_R2R;                                           /* rank 0: a copy of reals */
+            dim(&q.vecsz, l0, n1 * n2, ln1 * n2);
+            dim(&q.vecsz, ln1 * n2, 1, 1);
+            q.in0 = (double *)peer_locals[s] + b1 * rank * n2;
+            q.out0 = zbuf + b0 * s * ln1 * n2;
+            p->x[s] = b2_mkplan(&q);
+            if (!p->x[s]) goto fail;
+        }
+        init_problem(&q, flags);
+        q.kind = B2_R2R;
+        dim(&q.sz, n0, ln1 * n2, ln1 * n2);
+        q.r2r_kind[0] = kinds[0];
+        dim(&q.vecsz, ln1 * n2, 1, 1);
+        q.in0 = zbuf; q.out0 = zbuf;
+        p->z[0] = b2_mkplan(&q);
+        if (!p->z[0]) goto fail;
+    }
+    if (ln0 > 0) {
+        for (s = 0; s < nranks; ++s) {
+            /* my planes of column block s: rank s's zbuf [n0][l1(s)][n2] planes b0*rank ... -> slab column b1*s */
+            int64_t l1 = share(n1, nranks, s);
+            if (!l1) continue;
+            init_problem(&q, flags | B2F_ESTIMATE);
+            q.kind = B2_R2R;
+            dim(&q.vecsz, ln0, l1 * n2, n1 * n2);
+            dim(&q.vecsz, l1 * n2, 1, 1);
+            q.in0 = (double *)peer_zbufs[s] + b0 * rank * l1 * n2;
+            q.out0 = local + b1 * s * n2;
+            p->g[s] = b2_mkplan(&q);
+            if (!p->g[s]) goto fail;
+        }
+    }
+    return p;
+fail:
+    fftw_b200_dist_destroy_plan(p);
+    return NULL;
+}
+
 ptrdiff_t fftw_b200_ipc_offset(void *devptr) { return (ptrdiff_t)b2d_alloc_offset(devptr); }
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
@@ -384,7 +468,15 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
     int d, saved = b2_async_mode;
     void *mainst = b2d_get_stream();
     b2_async_mode = 1;
-    if (stage == 2 && p->post) {
+    if (p->real_gather) {
+        if (stage == 0) run(p->y[0]);
+        else if (stage == 1) {
+            for (d = 0; d < p->nranks; ++d) run(p->x[(p->rank + d) % p->nranks]);
+            run(p->z[0]);
+        } else if (stage == 2) {
+            for (d = 0; d < p->nranks; ++d) run(p->g[(p->rank + d) % p->nranks]);
+        }
+    } else if (stage == 2 && p->post) {
         if (c == 0) run(p->post);
     } else if (stage == 0 && c < p->c0) {
         void *aux = b2d_aux_stream(0);

@@ -43,6 +43,8 @@ def _declare(lib):
     for name in ("fftw_b200_dist_plan_dft_r2c_3d", "fftw_b200_dist_plan_dft_c2r_3d"):
         getattr(L, name).restype = P
         getattr(L, name).argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, P, C.c_uint]
+    L.fftw_b200_dist_plan_r2r_3d.restype = P
+    L.fftw_b200_dist_plan_r2r_3d.argtypes = [C.c_ssize_t] * 3 + [I, I, P, P, P, P, P, C.c_uint]
     L.fftw_b200_ipc_offset.restype = C.c_ssize_t
     L.fftw_b200_ipc_offset.argtypes = [P]
     L.fftw_b200_dist_num_stages.argtypes = [P]
@@ -394,6 +396,59 @@ class SlabPlanReal3D:
         self._barrier()                     # every rank's rows have landed in my complex slab
         if self.direction == "c2r":
             L.fftw_b200_dist_execute_stage(self.plan, 2)
+
+    def destroy(self):
+        if self.plan:
+            self.L.fftw_b200_dist_destroy_plan(self.plan)
+            self.plan = None
+        if self.P > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.L.fftw_b200_ipc_close(p)
+        for p in self._owned:
+            self.L.fftw_b200_device_free(p)
+        self._opened, self._owned = [], []
+
+
+class SlabPlanR2R3D:
+    """Distributed r2r of an n0 x n1 x n2 real array, kinds[i] along dimension i
+    (fftw_mpi_plan_r2r_3d; C-ABI fftw_b200_dist_plan_r2r_3d).  ``local`` = float64 CUDA tensor
+    [local_n0][n1][n2], transformed in place.  The two global transposes are gather copies with
+    peer loads; a barrier precedes every stage."""
+
+    def __init__(self, lib, n0, n1, n2, local, kinds, group=None, flags=B.FFTW_MEASURE):
+        _declare(lib)
+        self.lib, self.L = lib, lib.lib
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+        P, r = self.P, self.rank
+        b0, b1 = _blk(n0, P), _blk(n1, P)
+        self.ln0 = _share(n0, P, r)
+        assert local.is_cuda and local.dtype == torch.float64 and local.numel() >= self.ln0 * n1 * n2
+        self.local = local
+        self._owned, self._opened = [], []
+        self.zptr = self.L.fftw_b200_device_malloc(8 * max(n0 * b1 * n2, 1))
+        assert self.zptr, "device allocation failed"
+        self._owned.append(self.zptr)
+        if P > 1:
+            zpeers, o1 = _map_peers(self.L, group, r, P, self.zptr)
+            lpeers, o2 = _map_peers(self.L, group, r, P, local.data_ptr())
+            self._opened += o1 + o2
+        else:
+            zpeers, lpeers = [self.zptr], [local.data_ptr()]
+        VP = C.c_void_p * P
+        ks = (C.c_int * 3)(*[B.R2R_KINDS[k] if isinstance(k, str) else int(k) for k in kinds])
+        self.plan = self.L.fftw_b200_dist_plan_r2r_3d(n0, n1, n2, r, P, local.data_ptr(), self.zptr, VP(*lpeers),
+                                                     VP(*zpeers), ks, int(flags))
+        assert self.plan, "distributed r2r plan returned NULL"
+        self._token = torch.zeros(1, device=local.device)
+
+    def execute(self):
+        for st in range(3):
+            if self.P > 1:
+                dist.all_reduce(self._token, group=self.group)      # barrier before every stage
+            self.L.fftw_b200_dist_execute_stage(self.plan, st)
 
     def destroy(self):
         if self.plan:

@@ -80,6 +80,13 @@ fftw_b200_dist_plan fftw_b200_dist_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, p
                                                    fftw_complex *cplx_in, double *real_out, fftw_complex *zbuf,
                                                    void *const *push_targets, void *const *out_targets,
                                                    unsigned flags);
+/* r2r (fftw_mpi_plan_r2r_3d, mpi/api.c:770-886): real [local_n0][n1][n2] slab transformed in place, kinds[i]
+ * (fftw_r2r_kind values) along dimension i; zbuf holds [n0][local_n1][n2] reals.  Three stages (local
+ * 2-d r2r | gather columns + r2r along dim 0 | gather back) with a barrier BEFORE each of them;
+ *   peer_locals[s] = rank s's slab, peer_zbufs[s] = rank s's zbuf (peer-mapped). */
+fftw_b200_dist_plan fftw_b200_dist_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nranks,
+                                               double *local, double *zbuf, void *const *peer_locals,
+                                               void *const *peer_zbufs, const int *kinds, unsigned flags);
 int  fftw_b200_dist_num_stages(const fftw_b200_dist_plan p);
 void fftw_b200_dist_execute_stage(const fftw_b200_dist_plan p, int stage);
 /* Finer control for overlapping the exchange with compute: every stage is cut

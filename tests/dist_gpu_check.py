@@ -105,6 +105,32 @@ def main():
                 ok &= good
                 print("dist check %s P=%d r2c/c2r inplace=%d rel L2 fwd %.2e roundtrip %.2e %s"
                       % (shape, world, inplace, e1, e2, "OK" if good else "FAIL"), flush=True)
+    # r2r: kinds per dimension, uneven blocks included
+    for shape, kinds in [((64, 48, 32), ("REDFT10", "RODFT01", "R2HC")), ((30, 7 * world + 1, 25), ("DHT", "REDFT00", "RODFT11"))]:
+        n0, n1, n2 = shape
+        rng = np.random.default_rng(11)
+        full = rng.uniform(-0.5, 0.5, shape)
+        ref = O.r2r(full, list(kinds), rank=3) if rank == 0 else None
+        alloc, ln0, s0, ln1, s1 = D.local_size_3d(lib, n0, n1, n2, rank, world)
+        local = torch.zeros(max(ln0, 1) * n1 * n2, dtype=torch.float64, device="cuda")
+        if ln0:
+            local[:ln0 * n1 * n2] = torch.from_numpy(full[s0:s0 + ln0].reshape(-1).copy()).cuda()
+        pl = D.SlabPlanR2R3D(lib, n0, n1, n2, local, kinds, flags=B.FFTW_ESTIMATE)
+        pl.execute()
+        torch.cuda.synchronize()
+        pl.destroy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (s0, ln0, local[:ln0 * n1 * n2].cpu().numpy()))
+        if rank == 0:
+            got = np.zeros(shape)
+            for start, c, arr in gathered:
+                if c:
+                    got[start:start + c] = arr.reshape(c, n1, n2)
+            err = O.rel_l2(got, ref)
+            good = err < 2e-14
+            ok &= good
+            print("dist check %s P=%d r2r %s rel L2 %.2e %s" % (shape, world, "/".join(kinds), err, "OK" if good else "FAIL"),
+                  flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

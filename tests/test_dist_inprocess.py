@@ -163,3 +163,51 @@ def test_real_data_plans_all_ranks_in_one_process(emu_lib, shape, P, inplace):
     c2r of that result against the input (unnormalised: scaled by n0*n1*n2)."""
     err_f, err_b = _run_real(emu_lib, shape, P, inplace)
     assert err_f <= 1e-14 and err_b <= 1e-14, (shape, P, inplace, err_f, err_b)
+
+
+@pytest.mark.parametrize("shape,P,kinds", [
+    ((8, 6, 10), 2, ("REDFT10", "RODFT01", "R2HC")),
+    ((12, 10, 7), 3, ("DHT", "REDFT00", "RODFT11")),       # uneven column blocks
+    ((6, 5, 4), 4, ("RODFT00", "HC2R", "REDFT11")),        # idle last rank
+    ((5, 3, 8), 1, ("REDFT01", "REDFT10", "RODFT10")),
+])
+def test_r2r_plans_all_ranks_in_one_process(emu_lib, shape, P, kinds):
+    """Distributed r2r (mpi/api.c:770-886): local 2-d r2r, gather of the column blocks, r2r along
+    dim 0, gather back -- every rank simulated in one process, stage by stage."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    n0, n1, n2 = shape
+    rng = np.random.default_rng(21)
+    full = rng.uniform(-0.5, 0.5, shape)
+    b0, b1 = (n0 + P - 1) // P, (n1 + P - 1) // P
+    ln0 = [max(0, min(b0, n0 - b0 * r)) for r in range(P)]
+    ln1 = [max(0, min(b1, n1 - b1 * r)) for r in range(P)]
+    loc = [L.fftw_b200_device_malloc(8 * max(b0 * n1 * n2, 1)) for _ in range(P)]
+    zb = [L.fftw_b200_device_malloc(8 * max(n0 * b1 * n2, 1)) for _ in range(P)]
+
+    def rview(ptr, count):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(count,))
+
+    for r in range(P):
+        if ln0[r]:
+            rview(loc[r], b0 * n1 * n2)[:ln0[r] * n1 * n2] = full[r * b0:r * b0 + ln0[r]].reshape(-1)
+    VP = C.c_void_p * P
+    ks = (C.c_int * 3)(*[B.R2R_KINDS[k] for k in kinds])
+    plans = []
+    for r in range(P):
+        p = L.fftw_b200_dist_plan_r2r_3d(n0, n1, n2, r, P, loc[r], zb[r], VP(*loc), VP(*zb), ks, B.FFTW_ESTIMATE)
+        assert p, r
+        plans.append(p)
+    for st in range(3):
+        for r in range(P):
+            L.fftw_b200_dist_execute_stage(plans[r], st)
+    want = O.r2r(full, list(kinds), rank=3)
+    for r in range(P):
+        if ln0[r]:
+            got = rview(loc[r], b0 * n1 * n2)[:ln0[r] * n1 * n2].reshape(ln0[r], n1, n2)
+            assert O.rel_l2(got, want[r * b0:r * b0 + ln0[r]]) < 1e-13, (shape, P, kinds, r)
+    for p in plans:
+        L.fftw_b200_dist_destroy_plan(p)
+    for q in loc + zb:
+        L.fftw_b200_device_free(q)
