@@ -3,7 +3,7 @@
  * Turns a canonical problem into a flat list of device passes.  It plays the
  * role of the reference's planner + solvers (kernel/planner.c:518-747,
  * dft/ct.c, dft/rank-geq2.c:42-52, dft/vrank-geq1.c:54-65, dft/bluestein.c,
- * rdft/rank-geq2-rdft2.c:40-66, rdft/ct-hc2c.c:59-82, reodft/*.c) but the
+ * rdft/rank-geq2-rdft2.c:40-66, rdft/ct-hc2c.c:59-82, reodft/ *.c) but the
  * search space is the GPU one: per pass, the radix factorisation, how many
  * transforms a CTA stages, threads per transform and the specialised-vs-generic
  * kernel; candidates are timed with CUDA events (FFTW_MEASURE and above) or
