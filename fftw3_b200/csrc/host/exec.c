@@ -108,9 +108,11 @@ static int execute_host(b2_plan *p, void *const user[4])
         a = (char *)user[i] + lo * (int64_t)rs;
         b = (char *)user[i] + (hi + 1) * (int64_t)rs;
         if (i >= 2) written_reals += touched_count(q, i);
-        /* merge with an existing region if overlapping / adjacent */
+        /* merge with an existing region only if the two really overlap or touch: a gap between two user
+           arrays is not the user's memory (it may be allocator metadata) and must be neither read nor
+           written back */
         for (j = 0; j < nreg; ++j) {
-            if (a <= reg[j].hi + 64 && b + 64 >= reg[j].lo) {
+            if (a <= reg[j].hi && b >= reg[j].lo) {
                 if (a < reg[j].lo) reg[j].lo = a;
                 if (b > reg[j].hi) reg[j].hi = b;
                 break;
@@ -123,7 +125,7 @@ static int execute_host(b2_plan *p, void *const user[4])
     /* regions may have become overlapping after growth: merge again */
     for (i = 0; i < nreg; ++i)
         for (j = i + 1; j < nreg; ++j)
-            if (reg[j].lo <= reg[i].hi + 64 && reg[j].hi + 64 >= reg[i].lo) {
+            if (reg[j].lo <= reg[i].hi && reg[j].hi >= reg[i].lo) {
                 int k;
                 if (reg[j].lo < reg[i].lo) reg[i].lo = reg[j].lo;
                 if (reg[j].hi > reg[i].hi) reg[i].hi = reg[j].hi;

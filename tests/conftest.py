@@ -18,6 +18,9 @@ def emu_lib():
     """The REAL host layer linked against the unit-test double of the device shim
     (tests/emu/emu_shim.cpp).  Test infrastructure only; never the product."""
     from fftw3_b200 import binding
+    override = os.environ.get("FFTW3_B200_EMU_LIB")       # e.g. a sanitizer build of the same sources
+    if override:
+        return binding.Lib(override)
     subprocess.run(["sh", os.path.join(ROOT, "tests", "emu", "build_emu.sh")], check=True)
     return binding.Lib(os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
 
