@@ -452,6 +452,7 @@ int X(init_threads)(void) { return 1; }
 void X(plan_with_nthreads)(int n) { g_nthreads = n > 0 ? n : 1; }
 int X(planner_nthreads)(void) { return g_nthreads; }
 void X(cleanup_threads)(void) { X(cleanup)(); }
+/* planner entry points always serialise on b2_planner_lock(), so there is nothing to switch on */
 void X(make_planner_thread_safe)(void) {}
 void X(threads_set_callback)(void (*parallel_loop)(void *(*work)(char *), char *jobdata, size_t elsize,
                                                    int njobs, void *data), void *data)

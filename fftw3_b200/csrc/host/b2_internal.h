@@ -125,6 +125,12 @@ int  b2_is_prime(int64_t n);
 int64_t b2_primitive_root(int64_t p);     /* smallest generator of (Z/p)^*, p prime (kernel/primes.c:81-122 role) */
 
 /* planner.c */
+/* One process-wide recursive lock around everything that touches planner state (plan creation and
+   destruction, the shared table list, wisdom): the planner entry points may then be called from any
+   thread, which is what fftw_make_planner_thread_safe() asks for (doc/threads.texi:225-270,
+   api/apiplan.c:23-29).  Execution never takes it. */
+void b2_planner_lock(void);
+void b2_planner_unlock(void);
 b2_plan *b2_mkplan(const b2_problem *prob);
 void b2_plan_destroy(b2_plan *p);
 void b2_plan_print(const b2_plan *p, FILE *f);

@@ -10,7 +10,9 @@
  * chosen by a closed-form heuristic (FFTW_ESTIMATE), and the winner is
  * remembered as wisdom keyed on the pass signature.
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include "b2_internal.h"
@@ -1313,7 +1315,31 @@ static int tensor_valid(const b2_tensor *t, int allow_minfty)
     return 1;
 }
 
+static pthread_mutex_t g_planner_mu = PTHREAD_RECURSIVE_MUTEX_INITIALIZER_NP;
+void b2_planner_lock(void) { pthread_mutex_lock(&g_planner_mu); }
+void b2_planner_unlock(void) { pthread_mutex_unlock(&g_planner_mu); }
+
+static b2_plan *mkplan_locked(const b2_problem *prob);
+static void plan_destroy_locked(b2_plan *p);
+
 b2_plan *b2_mkplan(const b2_problem *prob)
+{
+    b2_plan *p;
+    b2_planner_lock();
+    p = mkplan_locked(prob);
+    b2_planner_unlock();
+    return p;
+}
+
+void b2_plan_destroy(b2_plan *p)
+{
+    if (!p) return;
+    b2_planner_lock();
+    plan_destroy_locked(p);
+    b2_planner_unlock();
+}
+
+static b2_plan *mkplan_locked(const b2_problem *prob)
 {
     b2_plan *p;
     int rc = 0, i;
@@ -1411,7 +1437,7 @@ b2_plan *b2_mkplan(const b2_problem *prob)
     return p;
 }
 
-void b2_plan_destroy(b2_plan *p)
+static void plan_destroy_locked(b2_plan *p)
 {
     int i;
     if (!p) return;

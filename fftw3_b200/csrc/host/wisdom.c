@@ -92,7 +92,7 @@ void b2_wisdom_store(b2_sig s, unsigned patience, int variant)
     store_prec(s, patience, variant, g_store_prec);
 }
 
-void b2_wisdom_forget(void)
+static void wisdom_forget_locked(void)
 {
     int i;
     for (i = 0; i < NBUCKET; ++i) {
@@ -107,7 +107,7 @@ static void emit_str(void (*emit)(char, void *), void *d, const char *s)
     while (*s) emit(*s++, d);
 }
 
-void b2_wisdom_export(void (*emit)(char c, void *), void *data, int prec)
+static void wisdom_export_locked(void (*emit)(char c, void *), void *data, int prec)
 {
     char buf[160];
     int i;
@@ -156,7 +156,7 @@ static int hexval(const char *t, unsigned long long *v)
     return *end == 0;
 }
 
-int b2_wisdom_import(int (*next)(void *), void *data, int prec)
+static int wisdom_import_locked(int (*next)(void *), void *data, int prec)
 {
     src s;
     char tok[128];
@@ -198,5 +198,29 @@ int b2_wisdom_import(int (*next)(void *), void *data, int prec)
         if (ok) store_prec(e->sig, e->patience, e->variant, e->prec);
         free(e);
     }
+    return ok;
+}
+
+/* public entry points: planner state is shared, see b2_planner_lock() */
+void b2_wisdom_forget(void)
+{
+    b2_planner_lock();
+    wisdom_forget_locked();
+    b2_planner_unlock();
+}
+
+void b2_wisdom_export(void (*emit)(char c, void *), void *data, int prec)
+{
+    b2_planner_lock();
+    wisdom_export_locked(emit, data, prec);
+    b2_planner_unlock();
+}
+
+int b2_wisdom_import(int (*next)(void *), void *data, int prec)
+{
+    int ok;
+    b2_planner_lock();
+    ok = wisdom_import_locked(next, data, prec);
+    b2_planner_unlock();
     return ok;
 }

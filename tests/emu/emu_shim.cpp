@@ -13,15 +13,18 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../fftw3_b200/csrc/device/fft_generic.cuh"
 #include "../../fftw3_b200/csrc/device/real_ops.cuh"
 
 static char g_err[256] = "";
-static uint64_t g_launches = 0;
+static std::atomic<uint64_t> g_launches{0};
 static std::map<char *, size_t> g_dev;          // "device" allocations: base -> bytes
+static std::mutex g_dev_mu;                     // execute is re-entrant: the registry must be too
 static std::chrono::steady_clock::time_point g_t0;
 
 template <typename T>
@@ -91,17 +94,29 @@ const char *b2d_device_name(void) { return "emulated-for-unit-tests"; }
 int b2d_sm_count(void) { return 148; }
 const char *b2d_last_error(void) { return g_err; }
 size_t b2d_max_smem_per_block(void) { return 232448; }
-uint64_t b2d_launch_count(void) { return g_launches; }
+uint64_t b2d_launch_count(void) { return g_launches.load(); }
 int b2d_pointer_is_device(const void *p)
 {
     // interior pointers count too (cudaPointerGetAttributes resolves them on the real device)
+    std::lock_guard<std::mutex> lk(g_dev_mu);
     auto it = g_dev.upper_bound((char *)p);
     if (it == g_dev.begin()) return 0;
     --it;
     return (const char *)p < it->first + it->second ? 1 : 0;
 }
-void *b2d_malloc(size_t n) { char *p = (char *)malloc(n ? n : 1); g_dev[p] = n ? n : 1; return p; }
-void b2d_free(void *p) { if (p) { g_dev.erase((char *)p); free(p); } }
+void *b2d_malloc(size_t n)
+{
+    char *p = (char *)malloc(n ? n : 1);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    g_dev[p] = n ? n : 1;
+    return p;
+}
+void b2d_free(void *p)
+{
+    if (!p) return;
+    { std::lock_guard<std::mutex> lk(g_dev_mu); g_dev.erase((char *)p); }
+    free(p);
+}
 void *b2d_malloc_host(size_t n) { void *p = NULL; if (posix_memalign(&p, 64, n ? n : 1)) return NULL; return p; }
 void b2d_free_host(void *p) { free(p); }
 int b2d_memcpy_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }

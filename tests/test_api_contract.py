@@ -184,3 +184,37 @@ def test_multidimensional_r2r_is_separable(emu_lib):
     a = np.stack([O.r2r(x[:, j].copy(), ["RODFT10"], rank=1) for j in range(10)], axis=1)
     b = np.stack([O.r2r(a[i].copy(), ["REDFT01"], rank=1) for i in range(6)], axis=0)
     assert O.rel_l2(y, b) < 1e-14
+
+
+def test_planner_entry_points_are_thread_safe(emu_lib):
+    """#18 doc/threads.texi:225-270, api/apiplan.c:23-29: after fftw_make_planner_thread_safe() plan
+    creation / destruction / wisdom calls may come from any thread (here they always serialise on one
+    process-wide lock; ThreadSanitizer runs of the same scenario are clean)."""
+    emu_lib.fn("d", "make_planner_thread_safe")()
+    errs = []
+
+    def work(i):
+        try:
+            rng = np.random.default_rng(i)
+            for it in range(6):
+                n = 48 + 16 * ((i + it) % 5)
+                x = (rng.uniform(-0.5, 0.5, n) + 1j * rng.uniform(-0.5, 0.5, n))
+                y = np.zeros_like(x)
+                flags = B.FFTW_ESTIMATE if it % 2 else B.FFTW_MEASURE
+                x0 = x.copy()
+                p = emu_lib.fn("d", "plan_dft_1d")(n, x.ctypes.data, y.ctypes.data, -1, flags)
+                assert p
+                x[:] = x0
+                emu_lib.execute("d", p)
+                assert O.rel_l2(y, np.fft.fft(x0)) < 1e-14
+                assert emu_lib.export_wisdom_to_string("d").startswith("(fftw3_b200-")
+                emu_lib.destroy_plan("d", p)
+        except Exception as e:      # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
