@@ -80,6 +80,7 @@ def _run(lib, shape, P, mode, sign):
     ((6, 5, 4), 4, -1),         # block 2: the last rank owns no planes
     ((16, 16, 16), 4, -1),      # power-of-two block: shift path of the row split
     ((5, 3, 7), 1, -1),
+    ((12, 10, 1), 3, -1),       # a 2-d array as n0 x n1 x 1 (fftw_mpi_plan_dft_2d)
 ])
 def test_peer_plans_all_ranks_in_one_process(emu_lib, mode, shape, P, sign):
     err = _run(emu_lib, shape, P, mode, sign)
