@@ -179,3 +179,41 @@ def test_random_guru_r2c_c2r(emu_lib, seed):
     emu_lib.destroy_plan("d", p)
     n = float(np.prod(shape[:rank]))
     assert np.abs(back[ridx] / n - x).max() <= 1e-12, (seed, "c2r", shape, rank, hrank)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_guru_c2c_single_precision(emu_lib, seed):
+    """the same random strided problems in single precision (fftwf_ entry points)"""
+    rng = np.random.default_rng(3000 + seed)
+    rank = int(rng.integers(1, 4))
+    hrank = int(rng.integers(0, 3))
+    shape = [int(rng.choice(SIZES)) for _ in range(rank + hrank)]
+    while int(np.prod(shape, dtype=np.int64)) > 20000:
+        shape[int(np.argmax(shape))] = 2
+    inplace = bool(rng.integers(0, 2))
+    sign = int(rng.choice([-1, 1]))
+    pad = bool(rng.integers(0, 2))
+    is_, isz = _layout(rng, shape, pad)
+    os_, osz = (is_, isz) if inplace else _layout(rng, shape, pad)
+    x = (rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)).astype(np.complex64)
+    dims = [(shape[i], is_[i], os_[i]) for i in range(rank)]
+    hows = [(shape[rank + i], is_[rank + i], os_[rank + i]) for i in range(hrank)]
+    x64 = x.astype(np.complex128)
+    want = np.fft.fftn(x64, axes=tuple(range(rank))) if sign < 0 else np.fft.ifftn(x64, axes=tuple(range(rank))) * np.prod(
+        shape[:rank])
+    _, iidx = _gather(np.zeros(isz), shape, is_)
+    _, oidx = _gather(np.zeros(osz), shape, os_)
+    a = np.full(isz, 7 + 7j, dtype=np.complex64)
+    a[iidx] = x
+    b = a if inplace else np.full(osz, 9 + 9j, dtype=np.complex64)
+    p = emu_lib.plan_guru_dft("f", dims, hows, a.ctypes.data, b.ctypes.data, sign, B.FFTW_ESTIMATE)
+    assert p, (shape, dims, hows)
+    emu_lib.execute("f", p)
+    emu_lib.destroy_plan("f", p)
+    got = b[oidx].astype(np.complex128)
+    n = max(2.0, float(np.prod(shape[:rank])))
+    assert np.linalg.norm(got - want) <= 4 * 1.2e-7 * np.log2(n) * max(np.linalg.norm(want), 1e-30), (seed, shape, rank, hrank)
+    if not inplace:
+        mask = np.ones(osz, dtype=bool)
+        mask[oidx.reshape(-1)] = False
+        assert np.all(b[mask] == np.complex64(9 + 9j))
