@@ -83,10 +83,11 @@ def test_random_guru_c2c(emu_lib, seed):
         emu_lib.execute("d", p)
         emu_lib.destroy_plan("d", p)
         got = b[oidx]
-        if not inplace:         # nothing outside the output tensor may be written
+        if not inplace:         # nothing outside the output tensor may be written, and the input is preserved
             mask = np.ones(osz, dtype=bool)
             mask[oidx.reshape(-1)] = False
             assert np.all(b[mask] == 9 + 9j)
+            assert np.array_equal(a[iidx], x) and np.all(np.delete(a, iidx.reshape(-1)) == 7 + 7j)
     scale = max(1.0, float(np.abs(want).max()))
     assert np.abs(got - want).max() <= 1e-12 * scale, (seed, shape, rank, hrank, inplace, split, sign, pad)
 
@@ -131,6 +132,12 @@ def test_random_guru_r2r(emu_lib, seed):
     got = b[oidx]
     scale = max(1.0, float(np.abs(want).max()))
     assert np.abs(got - want).max() <= 1e-11 * scale, (seed, shape, kinds, inplace, pad)
+    if not inplace:             # FFTW_PRESERVE_INPUT is the default for r2r, except HC2R (doc/reference.texi:511-527)
+        if "HC2R" not in kinds:
+            assert np.array_equal(a[iidx], x), (seed, shape, kinds)
+        mask = np.ones(osz, dtype=bool)
+        mask[oidx.reshape(-1)] = False
+        assert np.all(b[mask] == 9.0)
 
 
 @pytest.mark.parametrize("seed", range(40))
@@ -163,6 +170,7 @@ def test_random_guru_r2c_c2r(emu_lib, seed):
     want = np.fft.rfftn(x, axes=tuple(range(rank)))
     scale = max(1.0, float(np.abs(want).max()))
     assert np.abs(b[cidx] - want).max() <= 1e-12 * scale, (seed, "r2c", shape, rank, hrank)
+    assert np.array_equal(a[ridx], x), (seed, "r2c must preserve its input", shape)
     mask = np.ones(csz, dtype=bool)
     mask[cidx.reshape(-1)] = False
     assert np.all(b[mask] == 9 + 9j)
