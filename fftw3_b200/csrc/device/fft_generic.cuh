@@ -83,7 +83,7 @@ B2_HD int64_t grid_blocks(const b2d_fft_pass &p)
 
 // ---------------------------------------------------------------- load element
 template <typename T>
-B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
+B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int k)
 {
     const T *re = (const T *)p.in_re;
     const T *im = (const T *)p.in_im;
@@ -105,8 +105,14 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int k)
     } else if (op & B2D_LOAD_HERMCONJ) {
         // conj(H) of the Hermitian sequence of logical length n_in whose
         // non-redundant half is stored: Re(forward(conj H)) == backward(H)
-        const int n = p.n_in;
-        if (2 * k <= n) {
+        const int64_t n = p.n_in;
+        if (p.idx_mul) {
+            // half of a four-step line: logical index j = k * idx_mul + b0, the line advances by bis[0] per index
+            const int64_t j = (int64_t)k * p.idx_mul + b0;
+            const int64_t o = boff + (int64_t)k * p.is;
+            if (2 * j <= n) { z.x = re[o]; z.y = (j == 0 || 2 * j == n) ? T(0) : -im[o]; }
+            else { const int64_t om = o + (n - 2 * j) * p.bis[0]; z.x = re[om]; z.y = im[om]; }
+        } else if (2 * k <= n) {
             int64_t o = boff + (int64_t)k * p.is;
             z.x = re[o];
             z.y = (k == 0 || 2 * k == n) ? T(0) : -im[o];
@@ -140,7 +146,7 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
         r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, z, (const cplx<T> *)p.aux0, y);
         return;
     }
-    if ((op & B2D_STORE_TRUNC) && k >= p.n_out) return;
+    if ((op & B2D_STORE_TRUNC) && (p.idx_mul ? (int64_t)k * p.idx_mul + b0 : (int64_t)k) >= p.n_out) return;
     if (op & B2D_STORE_TWIDDLE4) {
         // exponent e = k * b0 < big_n ; W^e = hi[e / L] * lo[e % L]
         int64_t e = ((int64_t)k * b0) % p.big_n;
@@ -303,7 +309,7 @@ B2_HD void phase_load(const b2d_fft_pass &p, const Smem<T> &s, int tid, int nthr
         if (p.load_col) { k = idx / tpb; t = idx - k * tpb; }
         else            { t = idx / n;   k = idx - t * n; }
         if (s.b0[t] < 0) continue;
-        s.a[(size_t)t * s.pitch + padk(k)] = load_elem<T>(p, s.boff_in[t], k);
+        s.a[(size_t)t * s.pitch + padk(k)] = load_elem<T>(p, s.boff_in[t], s.b0[t], k);
     }
 }
 

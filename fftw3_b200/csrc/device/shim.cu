@@ -12,7 +12,12 @@
 
 namespace {
 char g_err[512] = "";
-cudaStream_t g_stream = 0;
+cudaStream_t g_user_stream = 0;               // set by fftw_b200_set_stream: process-wide
+// per-thread override (side streams of one execute: plan lanes, the distributed stages): another
+// thread that executes meanwhile keeps launching on the user's stream
+thread_local cudaStream_t t_stream = 0;
+thread_local int t_stream_depth = 0;
+#define g_stream (t_stream_depth > 0 ? t_stream : g_user_stream)
 int g_init = 0, g_ndev = 0, g_sms = 0;
 size_t g_max_smem = 0;
 char g_name[256] = "";
@@ -120,13 +125,25 @@ int b2d_sync(void)
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail(e, "kernel");
 }
-void b2d_set_stream(void *s) { g_stream = (cudaStream_t)s; }
+void b2d_set_stream(void *s) { g_user_stream = (cudaStream_t)s; }
 void *b2d_get_stream(void) { return (void *)g_stream; }
+void *b2d_push_stream(void *s)
+{
+    void *prev = (void *)g_stream;
+    t_stream = (cudaStream_t)s;
+    ++t_stream_depth;
+    return prev;
+}
+void b2d_pop_stream(void *prev)
+{
+    if (t_stream_depth > 0) --t_stream_depth;
+    t_stream = (cudaStream_t)prev;
+}
 
 void *b2d_aux_stream(int idx)
 {
-    static cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
-    if (ensure_init() || idx < 0 || idx >= 4) return nullptr;
+    static cudaStream_t aux[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    if (ensure_init() || idx < 0 || idx >= 8) return nullptr;
     if (!aux[idx]) {
         int lo = 0, hi = 0;                 /* hi = numerically lowest = greatest priority */
         cudaDeviceGetStreamPriorityRange(&lo, &hi);

@@ -200,7 +200,7 @@ X(plan) X(plan_many_dft_r2c)(int rank, const int *n, int howmany, R *in, const i
     int ni[B2_MAXRANK], no[B2_MAXRANK], i;
     int inplace = ((void *)in == (void *)out);
     memset(&q, 0, sizeof q);
-    if (rank < 1 || rank > B2_MAXRANK || howmany < 0) return NULL;
+    if (rank < 0 || rank > B2_MAXRANK || howmany < 0) return NULL;
     for (i = 0; i < rank; ++i) if (n[i] <= 0) return NULL;
     rdft2_pad(rank, n, inembed, inplace, 0, ni);
     rdft2_pad(rank, n, onembed, inplace, 1, no);
@@ -243,7 +243,7 @@ X(plan) X(plan_many_dft_c2r)(int rank, const int *n, int howmany, C *in, const i
     int ni[B2_MAXRANK], no[B2_MAXRANK], i;
     int inplace = ((void *)in == (void *)out);
     memset(&q, 0, sizeof q);
-    if (rank < 1 || rank > B2_MAXRANK || howmany < 0) return NULL;
+    if (rank < 0 || rank > B2_MAXRANK || howmany < 0) return NULL;
     for (i = 0; i < rank; ++i) if (n[i] <= 0) return NULL;
     if (!c2r_flags_ok(rank > 1, inplace, flags)) return NULL;
     rdft2_pad(rank, n, inembed, inplace, 1, ni);
@@ -278,7 +278,7 @@ X(plan) X(plan_dft_c2r_3d)(int n0, int n1, int n2, C *in, R *out, unsigned flags
     {                                                                                              \
         b2_problem q;                                                                              \
         memset(&q, 0, sizeof q);                                                                   \
-        if (rank < 1) return NULL;                                                                 \
+        if (rank < 0) return NULL;   /* rank 0 is a copy (rdft/rank0-rdft2.c) */                                                                 \
         if (MK(&q.sz, rank, dims, 1, 2, 0) || MK(&q.vecsz, howmany_rank, howmany_dims, 1, 2, 1))   \
             return NULL;                                                                           \
         q.kind = B2_R2C; q.flags = flags;                                                          \
@@ -294,7 +294,7 @@ GURU_R2C(plan_guru64_dft_r2c, iodim64, iodims64)
     {                                                                                              \
         b2_problem q;                                                                              \
         memset(&q, 0, sizeof q);                                                                   \
-        if (rank < 1) return NULL;                                                                 \
+        if (rank < 0) return NULL;   /* rank 0 is a copy (rdft/rank0-rdft2.c) */                                                                 \
         if ((void *)in == (void *)ro && rank > 1) return NULL; /* doc/reference.texi:1452-1459 */  \
         if (MK(&q.sz, rank, dims, 1, 1, 0) || MK(&q.vecsz, howmany_rank, howmany_dims, 1, 1, 1))   \
             return NULL;                                                                           \
@@ -311,7 +311,7 @@ GURU_SPLIT_R2C(plan_guru64_split_dft_r2c, iodim64, iodims64)
     {                                                                                              \
         b2_problem q;                                                                              \
         memset(&q, 0, sizeof q);                                                                   \
-        if (rank < 1) return NULL;                                                                 \
+        if (rank < 0) return NULL;   /* rank 0 is a copy (rdft/rank0-rdft2.c) */                                                                 \
         if (!c2r_flags_ok(rank > 1, (void *)in == (void *)out, flags)) return NULL;                \
         if (MK(&q.sz, rank, dims, 2, 1, 0) || MK(&q.vecsz, howmany_rank, howmany_dims, 2, 1, 1))   \
             return NULL;                                                                           \
@@ -328,7 +328,7 @@ GURU_C2R(plan_guru64_dft_c2r, iodim64, iodims64)
     {                                                                                              \
         b2_problem q;                                                                              \
         memset(&q, 0, sizeof q);                                                                   \
-        if (rank < 1) return NULL;                                                                 \
+        if (rank < 0) return NULL;   /* rank 0 is a copy (rdft/rank0-rdft2.c) */                                                                 \
         if ((void *)ri == (void *)out && rank > 1) return NULL;                                    \
         if (!c2r_flags_ok(rank > 1, (void *)ri == (void *)out, flags)) return NULL;                \
         if (MK(&q.sz, rank, dims, 1, 1, 0) || MK(&q.vecsz, howmany_rank, howmany_dims, 1, 1, 1))   \

@@ -54,7 +54,8 @@ typedef struct {
 } b2_problem;
 
 /* ---- plan ---- */
-enum { BUF_NONE = 0, BUF_IN0, BUF_IN1, BUF_OUT0, BUF_OUT1, BUF_SCRATCH0, BUF_SCRATCH1, BUF_SCRATCH2, BUF_SCRATCH3, BUF_TABLE, BUF_COUNT };
+enum { BUF_NONE = 0, BUF_IN0, BUF_IN1, BUF_OUT0, BUF_OUT1, BUF_SCRATCH0, BUF_SCRATCH1, BUF_SCRATCH2, BUF_SCRATCH3, BUF_SCRATCH4, BUF_SCRATCH5, BUF_TABLE, BUF_COUNT };
+#define B2_NSCRATCH 6
 
 typedef struct { int buf; int64_t off; /* in reals (scratch/table: in bytes) */ } b2_ref;
 
@@ -66,6 +67,7 @@ typedef struct {
     b2_ref r[6];              /* fft: in_re,in_im,out_re,out_im ; copy: in,out ;
                                  realop: x_re,x_im,y_re,y_im,work                     */
     char note[48];            /* for print_plan                                       */
+    int lane;                 /* 0: caller's stream; k > 0: side stream k - 1 (exec.c: run_steps) */
 } b2_step;
 
 typedef struct b2_table {     /* device-resident constant table, refcounted & shared */
@@ -82,8 +84,8 @@ typedef struct b2_plan {
     b2_problem prob;
     int nsteps, cap;
     b2_step *steps;
-    size_t scratch_bytes[4];
-    void *scratch[4];
+    size_t scratch_bytes[B2_NSCRATCH];
+    void *scratch[B2_NSCRATCH];
     int ntables, tcap;
     b2_table **tables;
     double est_flops_add, est_flops_mul, est_flops_fma;
@@ -151,6 +153,7 @@ int  b2_wisdom_import(int (*next)(void *), void *data, int prec);
 
 /* exec.c */
 void b2_execute(b2_plan *p, void *in0, void *in1, void *out0, void *out1);
+void b2_execute_ex(b2_plan *p, void *in0, void *in1, void *out0, void *out1, int nosync);
 void b2_plan_lock_init(b2_plan *p);
 void b2_plan_lock_destroy(b2_plan *p);
 void b2_wisdom_set_prec(int prec);

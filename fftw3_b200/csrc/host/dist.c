@@ -457,7 +457,7 @@ int fftw_b200_dist_num_chunks(const dplan p, int stage) { return stage == 0 ? p-
 
 static void run(b2_plan *pl)
 {
-    if (pl) b2_execute(pl, pl->prob.in0, pl->prob.in1, pl->prob.out0, pl->prob.out1);
+    if (pl) b2_execute_ex(pl, pl->prob.in0, pl->prob.in1, pl->prob.out0, pl->prob.out1, 1);   /* enqueue only */
 }
 
 /* one chunk of a stage.  Stage 0: Y_c on the caller's stream, X_c on side stream 0.
@@ -465,9 +465,8 @@ static void run(b2_plan *pl)
    everything the caller's stream holds so far (the caller's barrier included). */
 void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
 {
-    int d, saved = b2_async_mode;
-    void *mainst = b2d_get_stream();
-    b2_async_mode = 1;
+    int d;
+    void *mainst = b2d_get_stream(), *prev = NULL;
     if (p->real_gather) {
         if (stage == 0) run(p->y[0]);
         else if (stage == 1) {
@@ -482,19 +481,18 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
         void *aux = b2d_aux_stream(0);
         if (c == 0) run(p->pre);
         run(p->y[c]);
-        if (aux) { b2d_stream_wait_stream(aux, mainst); b2d_set_stream(aux); }
+        if (aux) { b2d_stream_wait_stream(aux, mainst); prev = b2d_push_stream(aux); }
         if (p->x_fused[c]) run(p->x[c * p->nranks]);
         else for (d = 0; d < p->nranks; ++d) run(p->x[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
-        b2d_set_stream(mainst);
+        if (aux) b2d_pop_stream(prev);
     } else if (stage == 1 && c < p->c1) {
         run(p->z[c]);
     } else if (stage == 2 && c < p->c1) {
         void *aux = b2d_aux_stream(1);
-        if (aux) { b2d_stream_wait_stream(aux, mainst); b2d_set_stream(aux); }
+        if (aux) { b2d_stream_wait_stream(aux, mainst); prev = b2d_push_stream(aux); }
         for (d = 0; d < p->nranks; ++d) run(p->g[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
-        b2d_set_stream(mainst);
+        if (aux) b2d_pop_stream(prev);
     }
-    b2_async_mode = saved;
 }
 
 /* make the caller's stream wait for the side streams */

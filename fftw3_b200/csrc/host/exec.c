@@ -22,20 +22,43 @@ static void *resolve(const b2_plan *p, b2_ref r, void *const user[4], size_t rs)
     switch (r.buf) {
     case BUF_IN0: case BUF_IN1: case BUF_OUT0: case BUF_OUT1:
         return user[r.buf - BUF_IN0] ? (char *)user[r.buf - BUF_IN0] + r.off * (int64_t)rs : NULL;
-    case BUF_SCRATCH0: case BUF_SCRATCH1: case BUF_SCRATCH2: case BUF_SCRATCH3:
+    case BUF_SCRATCH0: case BUF_SCRATCH1: case BUF_SCRATCH2: case BUF_SCRATCH3: case BUF_SCRATCH4: case BUF_SCRATCH5:
         return (char *)p->scratch[r.buf - BUF_SCRATCH0] + r.off * (int64_t)rs;
     default:
         return NULL;
     }
 }
 
+/* Steps carry a lane: lane 0 runs on the caller's stream, lane k > 0 on side stream k - 1.  Steps of
+   different lanes between two lane-0 steps are independent (the planner guarantees it: L2-resident
+   groups of a multi-dimensional transform), so their kernels overlap: one lane's tail is filled by
+   the next lane's head.  A lane is forked from the caller's stream the first time it is used after a
+   join and joined back before the next lane-0 step (and at the end). */
+#define B2_MAX_LANES 6      /* side streams 2..7 (0 and 1 belong to the distributed stages, dist.c) */
+
+static void join_lanes(void *mainst, unsigned *active)
+{
+    int k;
+    for (k = 1; k <= B2_MAX_LANES; ++k)
+        if (*active & (1u << k)) { void *aux = b2d_aux_stream(k + 1); if (aux) b2d_stream_wait_stream(mainst, aux); }
+    *active = 0;
+}
+
 static int run_steps(const b2_plan *p, void *const user[4])
 {
     int i;
     size_t rs = real_size(p->prob.prec);
+    void *mainst = b2d_get_stream();
+    unsigned active = 0;
     for (i = 0; i < p->nsteps; ++i) {
         const b2_step *s = &p->steps[i];
         int rc = 0;
+        void *aux = NULL, *prev = NULL;
+        if (s->lane > 0 && s->lane <= B2_MAX_LANES) aux = b2d_aux_stream(s->lane + 1);
+        if (aux) {
+            if (!(active & (1u << s->lane))) { b2d_stream_wait_stream(aux, mainst); active |= 1u << s->lane; }
+            prev = b2d_push_stream(aux);
+        } else if (active) join_lanes(mainst, &active);
         if (s->kind == STEP_FFT) {
             b2d_fft_pass f = s->u.fft;
             f.in_re = resolve(p, s->r[0], user, rs);
@@ -57,11 +80,14 @@ static int run_steps(const b2_plan *p, void *const user[4])
             r.work = resolve(p, s->r[4], user, rs);
             rc = b2d_launch_realop(&r);
         }
+        if (aux) b2d_pop_stream(prev);
         if (rc) {
             fprintf(stderr, "fftw3_b200: pass %d failed: %s\n", i, b2d_last_error());
+            if (active) join_lanes(mainst, &active);
             return rc;
         }
     }
+    if (active) join_lanes(mainst, &active);
     return 0;
 }
 
@@ -162,23 +188,40 @@ static int execute_host(b2_plan *p, void *const user[4])
     return rc;
 }
 
-void b2_execute(b2_plan *p, void *in0, void *in1, void *out0, void *out1)
+/* nosync: return after enqueueing (device pointers only).  fftw_execute* may be called from several
+   threads on the same plan (doc/threads.texi:225-270): a plan that keeps intermediate data in its own
+   scratch (or staging) buffers serialises its executes on the plan mutex -- held until the passes are
+   complete, or, when only enqueueing, until they are all in the stream (stream order then keeps two
+   executes of one plan apart). */
+void b2_execute_ex(b2_plan *p, void *in0, void *in1, void *out0, void *out1, int nosync)
 {
     void *user[4];
-    int dev;
+    int dev, rc, i, shared = 0;
+    pthread_mutex_t *m;
     if (!p || p->is_nop) return;
+    m = (pthread_mutex_t *)p->lock;
     user[0] = in0; user[1] = in1; user[2] = out0; user[3] = out1;
     dev = b2d_pointer_is_device(in0 ? in0 : out0);
     if (dev < 0) { fprintf(stderr, "fftw3_b200: no CUDA device: %s\n", b2d_last_error()); abort(); }
     if (dev == 1) {
-        if (run_steps(p, user)) abort();
-        if (!b2_async_mode && b2d_sync()) { fprintf(stderr, "fftw3_b200: %s\n", b2d_last_error()); abort(); }
+        for (i = 0; i < B2_NSCRATCH; ++i) if (p->scratch[i]) shared = 1;
+        for (i = 0; i < p->nsteps && !shared; ++i) if (p->steps[i].lane) shared = 1;   /* side streams are shared too */
+        if (shared && m) pthread_mutex_lock(m);
+        rc = run_steps(p, user);
+        if (!rc && !nosync) rc = b2d_sync();
+        if (shared && m) pthread_mutex_unlock(m);
+        if (rc) { fprintf(stderr, "fftw3_b200: %s\n", b2d_last_error()); abort(); }
     } else {
-        pthread_mutex_t *m = (pthread_mutex_t *)p->lock;
         if (m) pthread_mutex_lock(m);
-        if (execute_host(p, user)) { if (m) pthread_mutex_unlock(m); abort(); }
+        rc = execute_host(p, user);
         if (m) pthread_mutex_unlock(m);
+        if (rc) abort();
     }
+}
+
+void b2_execute(b2_plan *p, void *in0, void *in1, void *out0, void *out1)
+{
+    b2_execute_ex(p, in0, in1, out0, out1, b2_async_mode);
 }
 
 void b2_plan_lock_init(b2_plan *p)

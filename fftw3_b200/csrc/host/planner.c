@@ -149,6 +149,7 @@ typedef struct {
     int64_t big_n, tw4_split; /* STORE_TWIDDLE4: enclosing size and lo-table length */
     int cache;                /* L2 residency hints (b2d_fft_pass.cache) */
     int r2r_kind;             /* LOAD_R2R / STORE_R2R */
+    int64_t idx_mul;          /* four-step halves: logical index rule for HERMCONJ / TRUNC (b2d_fft_pass.idx_mul) */
 } b2_ops;
 
 static void fill_geometry(b2d_fft_pass *f, int variant)
@@ -286,6 +287,7 @@ static void pass_span(const b2d_fft_pass *f, int out, int64_t *lo, int64_t *hi)
     int i;
     int64_t mn = 0, mx = 0, s = out ? f->os : f->is;
     int64_t len = out ? (f->n_out ? f->n_out : f->n) : (f->n_in ? f->n_in : f->n);
+    if (f->idx_mul) len = f->n;      /* half of a four-step line: n_in / n_out are lengths of the whole line */
     int64_t e = (len - 1) * s;
     if (e < 0) mn += e; else mx += e;
     if (f->r2r_pair) { e = out ? f->pair_os : f->pair_is; if (e < 0) mn += e; else mx += e; }
@@ -362,6 +364,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     f->n = (int)(bluestein_m > 0 ? bluestein_m : (bluestein_m < 0 ? n - 1 : n));
     f->pre_op = ops.pre_op; f->post_op = ops.post_op;
     f->cache = ops.cache;
+    f->idx_mul = ops.idx_mul;
     f->n_in = ops.n_in ? ops.n_in : (int)n;
     f->n_out = ops.n_out ? ops.n_out : (int)n;
     f->is = in.stride; f->os = out.stride;
@@ -532,6 +535,23 @@ typedef struct {
 static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                       const b2_tensor *batch_in, b2_ops ops, int scratch_slot, const char *note);
 
+/* n = n1 * n2 with both halves smooth and one-pass sized: the n1 closest to sqrt(n) from below (or the one
+   FFTW3_B200_FOURSTEP_N1 pins), -1 if there is none */
+static int64_t two_factor_split(int64_t n, int prec)
+{
+    int64_t d, best = -1;
+    int tmp[64];
+    const char *fs = getenv("FFTW3_B200_FOURSTEP_N1");       /* tests / tuning: pin the split */
+    for (d = 2; d * d <= n; ++d) {
+        if (n % d) continue;
+        if (!single_pass_fits(n / d, prec) || !single_pass_fits(d, prec)) continue;
+        if (!b2_factorize(d, prec, 0, tmp) || !b2_factorize(n / d, prec, 0, tmp)) continue;
+        if (d > best) best = d;
+        if (fs && d == atol(fs)) return d;
+    }
+    return best;
+}
+
 static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int64_t ioff, int64_t ooff)
 {
     fft1d_ctx *c = (fft1d_ctx *)vctx;
@@ -542,6 +562,11 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
 
     if (smooth && single_pass_fits(n, c->prec))
         return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, 0, c->note);
+
+    /* index-dependent fused ops cannot follow a second level of digit reversal: such lines (odd smooth
+       real transforms beyond ~1.6e7 points) take the chirp-z route, whose pre/post maps carry the ops */
+    if (smooth && two_factor_split(n, c->prec) < 0 &&
+        ((c->ops.pre_op & B2D_LOAD_HERMCONJ) || (c->ops.post_op & B2D_STORE_TRUNC))) smooth = 0;
 
     if (!smooth) {
         /* Bluestein (dft/bluestein.c:82-128): one CTA does chirp, FFT_M, x B, IFFT_M, chirp */
@@ -628,10 +653,13 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
         }
     }
 
-    /* four-step: n = n1 * n2, pass A strided length-n1 FFTs + twiddle into
-       scratch, pass B contiguous length-n2 FFTs with transposed store */
-    if (c->ops.pre_op & (B2D_LOAD_HERMCONJ | B2D_LOAD_PAD | B2D_LOAD_CHIRP)) return -1;
-    if (c->ops.post_op) return -1;
+    /* four-step: n = n1 * n2, pass A strided length-n1 FFTs + twiddle into scratch, pass B contiguous
+       length-n2 FFTs with transposed store.  n2 itself may need the same treatment (n beyond the square of
+       the one-pass limit): pass B is then planned recursively through the next scratch slot.  Fused real-data
+       ops ride on the passes: LOAD_REAL / LOAD_HERMCONJ on the load of pass A, STORE_REALPART / STORE_TRUNC
+       on the store of pass B (the index-dependent ones through the pass's logical-index rule, idx_mul). */
+    if (c->ops.pre_op & (B2D_LOAD_PAD | B2D_LOAD_CHIRP | B2D_LOAD_R2R | B2D_LOAD_RADER)) return -1;
+    if (c->ops.post_op & ~(B2D_STORE_REALPART | B2D_STORE_TRUNC)) return -1;
     if (brank > 2) {
         int64_t k;
         for (k = 0; k < bd[brank - 1].n; ++k) {
@@ -641,26 +669,30 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
         return 0;
     }
     {
-        int64_t n1 = 0, n2 = 0, d, best = -1;
+        int64_t n1 = 0, n2 = 0, d, best = two_factor_split(n, c->prec);
         int64_t lines = 1, L;
-        b2_dim ba[3], bb[3];
+        b2_dim ba[3];
         b2_view sv;
         b2_ops oa, ob;
-        int i, rc, tmp[64];
+        int i, rc, tmp[64], slot = c->scratch_slot, nested = 0, next_slot = -1;
         size_t rs = real_size(c->prec);
-        for (d = 2; d * d <= n; ++d) {
-            if (n % d) continue;
-            if (!single_pass_fits(n / d, c->prec) || !single_pass_fits(d, c->prec)) continue;
-            if (!b2_factorize(d, c->prec, 0, tmp) || !b2_factorize(n / d, c->prec, 0, tmp)) continue;
-            if (d > best) best = d;      /* closest to sqrt(n) from below */
+        if (best < 0) {
+            /* no two-factor split fits: peel off the largest one-pass factor and recurse on the rest */
+            for (d = 2; d <= 16384; ++d) {
+                if (n % d || !single_pass_fits(d, c->prec) || !b2_factorize(d, c->prec, 0, tmp)) continue;
+                if (d > best) best = d;
+            }
+            if (best < 0) return -1;
+            nested = 1;
+            next_slot = (slot == 1) ? 4 : (slot == 4 ? 5 : -1);
+            if (next_slot < 0) return -1;
         }
-        if (best < 0) return -1;
         n1 = best; n2 = n / best;        /* n1 <= n2: rows of pass B are the long contiguous ones */
         for (i = 0; i < brank; ++i) lines *= bd[i].n;
-        need_scratch(p, c->scratch_slot, (size_t)lines * (size_t)n * 2 * rs);
+        need_scratch(p, slot, (size_t)lines * (size_t)n * 2 * rs);
         /* scratch layout [line][k1][j2], interleaved complex */
-        sv.re = mkref(BUF_SCRATCH0 + c->scratch_slot, 0);
-        sv.im = mkref(BUF_SCRATCH0 + c->scratch_slot, 1);
+        sv.re = mkref(BUF_SCRATCH0 + slot, 0);
+        sv.im = mkref(BUF_SCRATCH0 + slot, 1);
         /* pass A */
         ba[0].n = n2; ba[0].is = in.stride; ba[0].os = 2;
         {
@@ -672,23 +704,36 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
             ia.stride = n2 * in.stride;
             oa_v.stride = 2 * n2;
             L = 1; while (L * L < n) L <<= 1;
-            oa = c->ops; oa.post_op = B2D_STORE_TWIDDLE4; oa.n_in = 0; oa.n_out = 0;
+            oa = c->ops; oa.post_op = B2D_STORE_TWIDDLE4; oa.n_out = 0;
+            if (!(oa.pre_op & B2D_LOAD_HERMCONJ)) oa.n_in = 0;
+            else { oa.n_in = (int)n; oa.idx_mul = n2; }
             oa.big_n = n; oa.tw4_split = L;
             rc = emit_single(p, c->prec, n1, ia, oa_v, ba, brank + 1, oa, 0, "four-step A");
             if (rc) return rc;
         }
         /* pass B */
-        bb[0].n = n1; bb[0].is = 2 * n2; bb[0].os = out.stride;
-        {
-            int64_t ld = 2 * n;
-            for (i = 0; i < brank; ++i) { bb[i + 1].n = bd[i].n; bb[i + 1].is = ld; bb[i + 1].os = bd[i].os; ld *= bd[i].n; }
-        }
         {
             b2_view ib = sv, ob_v = out;
+            b2_tensor bb;
+            int64_t ld = 2 * n;
             ib.stride = 2;
             ob_v.stride = n1 * out.stride;
             memset(&ob, 0, sizeof ob);
-            rc = emit_single(p, c->prec, n2, ib, ob_v, bb, brank + 1, ob, 0, "four-step B");
+            ob.post_op = c->ops.post_op;
+            if (ob.post_op & B2D_STORE_TRUNC) { ob.n_out = c->ops.n_out; ob.idx_mul = n1; }
+            b2_tensor_init(&bb, 0);
+            bb.d[0].n = n1; bb.d[0].is = 2 * n2; bb.d[0].os = out.stride;
+            for (i = 0; i < brank; ++i) { bb.d[i + 1].n = bd[i].n; bb.d[i + 1].is = ld; bb.d[i + 1].os = bd[i].os; ld *= bd[i].n; }
+            bb.rnk = brank + 1;
+            if (!nested) rc = emit_single(p, c->prec, n2, ib, ob_v, bb.d, brank + 1, ob, 0, "four-step B");
+            else {
+                /* the nested transform sorts and merges its own batch; its k1 dimension must stay apart from
+                   the lines (different output strides), which sort_merge guarantees by checking both sides */
+                fft1d_ctx c2 = *c;
+                c2.n = n2; c2.in = ib; c2.out = ob_v; c2.ops = ob; c2.scratch_slot = next_slot; c2.note = "four-step B (nested)";
+                b2_tensor_drop_unit(&bb);
+                rc = for_outer_dims(p, &bb, fft1d_inner, &c2);
+            }
             if (rc) return rc;
         }
     }
@@ -1007,8 +1052,13 @@ static int plan_r2c(b2_plan *p)
     b2_view in, out;
     int src0 = BUF_IN0, src1 = BUF_IN0;
     if (q->sz.rnk < 1) {
-        /* rank 0 r2c: copy real part, zero imaginary: express as n=1 transform */
-        return -1;
+        /* rank 0 (rdft/rank0-rdft2.c): out = in + 0i for every element of the batch -- a length-1
+           transform with a real load */
+        memset(&ops, 0, sizeof ops);
+        ops.pre_op = B2D_LOAD_REAL;
+        in.re = in.im = mkref(BUF_IN0, 0); in.stride = 1;
+        out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = 2;
+        return emit_fft1d(p, q->prec, 1, in, out, &q->vecsz, ops, 1, "r2c rank 0");
     }
     n = q->sz.d[last].n;
     if (p->inplace && (n % 2) && !rows_self_contained(q, last)) {
@@ -1097,7 +1147,14 @@ static int plan_c2r(b2_plan *p)
     b2_view in, out;
     int src_re = BUF_IN0, src_im = BUF_IN1;
     int64_t im_off = 0;
-    if (q->sz.rnk < 1) return -1;
+    if (q->sz.rnk < 1) {
+        /* rank 0 (rdft/rank0-rdft2.c): out = Re(in) */
+        memset(&ops, 0, sizeof ops);
+        ops.post_op = B2D_STORE_REALPART;
+        in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN1, 0); in.stride = 2;
+        out.re = out.im = mkref(BUF_OUT0, 0); out.stride = 1;
+        return emit_fft1d(p, q->prec, 1, in, out, &q->vecsz, ops, 1, "c2r rank 0");
+    }
     n = q->sz.d[last].n;
     if (p->inplace && (n % 2) && !rows_self_contained(q, last)) {
         rc = stage_input(p, &qq, last, &src_re, &src_im);
@@ -1366,6 +1423,9 @@ static b2_plan *mkplan_locked(const b2_problem *prob)
         }
         t->rnk = k;
     }
+    /* internal tensors hold B2_MAXRANK dims: transform + batch dims together must fit (the reference has
+       no such bound, kernel/tensor.c:29-50 allocates; 16 combined non-unit dims is ample in practice) */
+    if (p->prob.sz.rnk + (p->prob.vecsz.rnk > 0 ? p->prob.vecsz.rnk : 0) > B2_MAXRANK) { b2_plan_destroy(p); return NULL; }
     p->inplace = (prob->in0 == prob->out0);
     if (prob->kind == B2_C2C && prob->in0 == prob->out1 && prob->in1 == prob->out0) p->inplace = 0;
     {
@@ -1427,7 +1487,7 @@ static b2_plan *mkplan_locked(const b2_problem *prob)
         }
     }
     if (rc) { b2_plan_destroy(p); return NULL; }
-    for (i = 0; i < 4; ++i) {
+    for (i = 0; i < B2_NSCRATCH; ++i) {
         if (p->scratch_bytes[i]) {
             p->scratch[i] = b2d_malloc(p->scratch_bytes[i]);
             if (!p->scratch[i]) { b2_plan_destroy(p); return NULL; }
@@ -1444,7 +1504,7 @@ static void plan_destroy_locked(b2_plan *p)
     b2_plan_lock_destroy(p);
     for (i = 0; i < p->ntables; ++i) b2_table_release(p->tables[i]);
     free(p->tables);
-    for (i = 0; i < 4; ++i) b2d_free(p->scratch[i]);
+    for (i = 0; i < B2_NSCRATCH; ++i) b2d_free(p->scratch[i]);
     for (i = 0; i < 4; ++i) b2d_free(p->stage_dev[i]);
     free(p->steps);
     free(p);

@@ -68,6 +68,11 @@ typedef struct b2d_fft_pass {
     int kernel;               /* 0: generic runtime-radix kernel; else code of a
                                  specialised kernel: tile width + 1000 for COL      */
     int n_in, n_out;          /* valid input / stored output length (pad, truncate)  */
+    /* idx_mul != 0: this pass is one half of a four-step transform of a longer line, and the LOGICAL
+       index of its element k in the line is k * idx_mul + b0 (b0 = batch dim 0 index, which walks the
+       line with stride bis[0] / bos[0]).  LOAD_HERMCONJ mirrors and STORE_TRUNC cuts on that index,
+       n_in / n_out then being lengths of the whole line.                                             */
+    int64_t idx_mul;
     /* LOAD_R2R / STORE_R2R, kinds whose PRE sequence is real: r2r_pair != 0 packs TWO lines into one
        complex transform (line A -> real part, line B = A + pair_is -> imaginary part; the spectra are
        separated as (Z_k +- conj Z_{n-k}) / 2 before the POST map).  Batch dim 0 then counts pairs. */
@@ -168,7 +173,10 @@ int  b2d_memcpy_d2d(void *dst, const void *src, size_t bytes);
 int  b2d_memset(void *dst, int byte, size_t bytes);
 int  b2d_sync(void);
 void b2d_set_stream(void *cuda_stream);  /* NULL = legacy default stream              */
-void *b2d_get_stream(void);
+void *b2d_get_stream(void);             /* the stream launches of THIS thread go to          */
+/* per-thread override of the launch stream (nested): returns the previous value for b2d_pop_stream */
+void *b2d_push_stream(void *cuda_stream);
+void b2d_pop_stream(void *prev);
 /* side streams for overlapping NVLink-bound kernels with HBM-bound ones */
 void *b2d_aux_stream(int idx);                           /* lazily created, non-blocking  */
 int  b2d_stream_wait_stream(void *waiter, void *signaler); /* event edge signaler -> waiter */

@@ -126,6 +126,8 @@ int b2d_memset(void *d, int b, size_t n) { memset(d, b, n); return 0; }
 int b2d_sync(void) { return 0; }
 void b2d_set_stream(void *) {}
 void *b2d_get_stream(void) { return NULL; }
+void *b2d_push_stream(void *) { return NULL; }
+void b2d_pop_stream(void *) {}
 void *b2d_aux_stream(int) { return NULL; }                 /* everything is synchronous here */
 int b2d_stream_wait_stream(void *, void *) { return 0; }
 int b2d_ipc_export(void *, unsigned char *) { return -1; }     /* no IPC in the unit-test double */
