@@ -86,6 +86,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------ CPU reference
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def cpu_reference_run(steps, warmup, sample_n=256):
     """The reference's own CPU implementation (oracle/_ref = unmodified FFTW
     sources compiled codelet-less here, with its OpenMP threads) on a bounded
@@ -96,8 +103,19 @@ def cpu_reference_run(steps, warmup, sample_n=256):
     kind = "reference"
     if not os.path.exists(path):
         return None
+    cores = host_cores()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers and the reference's `#pragma omp parallel for`
+    # (threads/openmp.c:77) obeys it: set the team size explicitly, before and after libgomp is loaded
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     lib = C.CDLL(path)
-    cores = os.cpu_count() or 1
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(cores)
+        gomp.omp_get_max_threads.restype = C.c_int
+        cores = int(gomp.omp_get_max_threads())
+    except OSError:
+        pass
     lib.fftw_init_threads()
     lib.fftw_plan_with_nthreads(C.c_int(cores))
     lib.fftw_plan_dft_3d.restype = C.c_void_p
@@ -142,21 +160,88 @@ def cpu_vectorised_run(sample_n=256, repeats=3):
         return {"unavailable": repr(e)[:120]}
 
 
+def reference_sample_size(args):
+    """512^3 (BASELINE config C3, ~10 s per step on the codelet-less build) when the requested number of
+    steps keeps the whole run within a few minutes, else 256^3."""
+    if args.ref_sample:
+        return args.ref_sample
+    return 512 if (max(1, args.steps) + 1) * 12.0 <= 200.0 and args.size >= 512 else min(256, args.size)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), sample_n=256)
+    sn = reference_sample_size(args)
+    r = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), sample_n=sn)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfftw3_ref.so is not built"}))
+        return
     n = args.size
     line = {
         "impl": "reference", "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": r["value"], "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%d^3 c2c double in place (reference arm runs the bounded sample below)" % n},
+        "config": {"workload": "%d^3 c2c double in place; this arm times the bounded sample %d^3 of it "
+                               "(same transform, 1/%d of the points) on the host CPU" % (n, sn, (n // sn) ** 3),
+                   "sample_size": sn, "same_config": sn == n},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------ self check
+def impulse_expected(n, j, ks):
+    """Closed form of the forward DFT of a unit impulse at j = (j0, j1, j2), sampled at ks (m x 3):
+    exp(-2 pi i (j . k) / n), with the exponent reduced exactly in integers (libbench2/verify-lib.c:293-323
+    checks impulses the same way, against a constant)."""
+    import numpy as np
+    e = (ks.astype(np.int64) * np.asarray(j, dtype=np.int64)[None, :]).sum(axis=1) % n
+    ang = -2.0 * np.pi * e.astype(np.float64) / n
+    return np.cos(ang) + 1j * np.sin(ang)
+
+
+def self_check_single(lib, B, plan, a, n, flags):
+    """Outside the timed region, on the very array and plan that were timed: (i) a unit impulse at a
+    non-trivial index against the closed-form phases at 512 sampled outputs, (ii) forward + backward of
+    random data against the input (relative L2, in plane blocks)."""
+    import numpy as np
+    import torch
+    ar = torch.view_as_real(a)
+    j = (n // 3 + 1, n // 5 + 2, n // 7 + 3)
+    a.zero_()
+    a[j] = 1.0
+    lib.execute("d", plan)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(1234)
+    ks = rng.integers(0, n, size=(512, 3))
+    kt = torch.from_numpy(ks).to(a.device)
+    got = a[kt[:, 0], kt[:, 1], kt[:, 2]].cpu().numpy()
+    imp = float(np.abs(got - impulse_expected(n, j, ks)).max())
+    # round trip
+    g = torch.Generator(device=a.device).manual_seed(7)
+    ar.copy_(torch.rand(ar.shape, dtype=torch.float64, device=a.device, generator=g) - 0.5)
+    keep = a.clone()
+    pb = lib.fn("d", "plan_dft_3d")(n, n, n, a.data_ptr(), a.data_ptr(), B.FFTW_BACKWARD, flags)
+    assert pb, "backward plan returned NULL"
+    lib.execute("d", plan)
+    lib.execute("d", pb)
+    torch.cuda.synchronize()
+    lib.destroy_plan("d", pb)
+    num = den = 0.0
+    step = max(1, n // 16)
+    inv = 1.0 / float(n) ** 3
+    for i in range(0, n, step):
+        d = a[i:i + step] * inv - keep[i:i + step]
+        num += float((d.real ** 2 + d.imag ** 2).sum())
+        den += float((keep[i:i + step].real ** 2 + keep[i:i + step].imag ** 2).sum())
+    del keep
+    rt = (num / den) ** 0.5
+    lg = 3 * math.log2(n)
+    ok = bool(imp <= 1e-13 * lg and rt <= 3.0 * 2.0 ** -52 * lg)
+    return {"impulse_max_err": imp, "impulse_at": list(j), "impulse_samples": 512, "roundtrip_rel_l2": rt,
+            "tolerance": {"impulse": 1e-13 * lg, "roundtrip": 3.0 * 2.0 ** -52 * lg}, "ok": ok}
 
 
 # --------------------------------------------------------------------- ours
@@ -172,7 +257,6 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = B.load()
     n = args.size
@@ -181,7 +265,8 @@ def run_ours(args):
 
     if world > 1:
         from fftw3_b200 import dist as fdist
-        return fdist.bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run)
+        return fdist.bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run,
+                                   impulse_expected)
 
     # ---- N = 1: whole array on one GPU, in place, device resident ----
     a = torch.empty(shape, dtype=torch.complex128, device=dev)
@@ -241,12 +326,25 @@ def run_ours(args):
         except (OSError, ValueError):
             pass
 
+    # ---- correctness of what was just timed (outside the timed region)
+    check = None if args.no_check else self_check_single(lib, B, plan, a, n, flags)
+
+    # ---- the other BASELINE.json configs (C1, C2, C3, C5a, C5b), device resident, same planner mode
+    extra = None
+    if not args.no_extra:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            extra = bench_configs.run_configs(lib, flags, peak)
+        except Exception as e:       # informational: never fail the headline for it
+            extra = [{"error": repr(e)[:200]}]
+
     # ---- e2e: the same transform through the C-ABI on HOST buffers ----
     e2e = None
     if not args.no_e2e:
         del a, ar
         torch.cuda.empty_cache()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = max(1, args.steps)
         nbytes = array_bytes
         hp = lib.fn("d", "malloc")(nbytes)          # pinned when possible
         assert hp
@@ -268,7 +366,7 @@ def run_ours(args):
                "api": "fftw_plan_dft_3d + fftw_execute on fftw_malloc'd host memory"}
     lib.destroy_plan("d", plan)
 
-    cpu = None if args.no_cpu else cpu_reference_run(1, 0, sample_n=256)
+    cpu = None if args.no_cpu else cpu_reference_run(1, 0, sample_n=min(256, n))
     line = {
         "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": gflops, "unit": "GFLOP/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
@@ -277,11 +375,14 @@ def run_ours(args):
                    "l2": "array (%.0f GiB) is larger than L2, no flush needed" % (array_bytes / GIB),
                    "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
                    "plan": " ".join(plan_txt.split())},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
         "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
-        "cpu_vectorised_context": None if args.no_cpu else cpu_vectorised_run(),
+        "cpu_vectorised_context": None if args.no_cpu else cpu_vectorised_run(min(256, n)),
+        "extra_configs": extra,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if check is not None and not check["ok"]:
+        sys.exit("bench.py: self check FAILED: %r" % (check,))
 
 
 def main():
@@ -295,6 +396,9 @@ def main():
     ap.add_argument("--wisdom", default=None, help="wisdom file to import before planning and export after")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the impulse / round-trip check of the timed plan")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (extra_configs)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: cube edge of the CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

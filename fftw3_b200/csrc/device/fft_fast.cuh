@@ -62,6 +62,50 @@ __device__ __forceinline__ void st_stream(cplx<float> *p, cplx<float> v)
     __stcs(reinterpret_cast<float2 *>(p), make_float2(v.x, v.y));
 }
 
+// L2-resident pass pairs (b2d_fft_pass.cache): the first pass of a pair leaves its output in L2 with
+// ordinary write-back stores (bit 1) or pins it there with an evict_last policy (bit 2); the second
+// pass reads it back with ordinary loads (bit 0) and streams its own output out.
+__device__ __forceinline__ cplx<double> ld_plain(const cplx<double> *p)
+{
+    double2 v = *reinterpret_cast<const double2 *>(p);
+    cplx<double> r; r.x = v.x; r.y = v.y; return r;
+}
+__device__ __forceinline__ cplx<float> ld_plain(const cplx<float> *p)
+{
+    float2 v = *reinterpret_cast<const float2 *>(p);
+    cplx<float> r; r.x = v.x; r.y = v.y; return r;
+}
+__device__ __forceinline__ void st_plain(cplx<double> *p, cplx<double> v)
+{
+    *reinterpret_cast<double2 *>(p) = make_double2(v.x, v.y);
+}
+__device__ __forceinline__ void st_plain(cplx<float> *p, cplx<float> v)
+{
+    *reinterpret_cast<float2 *>(p) = make_float2(v.x, v.y);
+}
+__device__ __forceinline__ unsigned long long policy_evict_last()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep(cplx<double> *p, cplx<double> v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(cplx<float> *p, cplx<float> v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+// store of one output element under the pass's cache hints
+template <typename T>
+__device__ __forceinline__ void st_out(cplx<T> *p, cplx<T> v, int cache, unsigned long long pol)
+{
+    if (cache & 4) st_keep(p, v, pol);
+    else if (cache & 2) st_plain(p, v);
+    else st_stream(p, v);
+}
+
 // Loads that ask L2 to fetch a whole 128 / 256-byte block from DRAM: a narrow COL tile
 // (64 B per row) then costs DRAM one long burst per block instead of several short ones; the
 // neighbouring tiles (other CTAs, scheduled next to this one) find their part in L2.
@@ -207,6 +251,8 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     //             q = i + PER*r -- the second run's outputs get conj * chirp * 1/M and are cut to n_out
     T bre[FLAVOR == 7 ? E : 1], bim[FLAVOR == 7 ? E : 1];
     int rep = 0;
+    const int cache = p.cache;
+    const unsigned long long keep_pol = (cache & 4) ? policy_evict_last() : 0ull;
     auto emit = [&](int kout, int q, T vr, T vi) {
         if (FLAVOR == 9) {
             if (p.r2r_pair) {       // two real lines per transform: park, the spectra are separated in flush_col()
@@ -262,7 +308,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             o.y = swap_out ? vr : vi;
             if (valid) {
                 if (FLAVOR == 4) *(gout + (int64_t)kout * os2) = o;     // let L2 merge the halves of a line
-                else st_stream(gout + (int64_t)kout * os2, o);
+                else st_out<T>(gout + (int64_t)kout * os2, o, cache, keep_pol);
             }
         }
     };
@@ -295,7 +341,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             cplx<T> o;
             o.x = swap_out ? v.y : v.x;
             o.y = swap_out ? v.x : v.y;
-            st_stream(gbase + (bb * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2]) / 2 + (int64_t)k * os2, o);
+            st_out<T>(gbase + (bb * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2]) / 2 + (int64_t)k * os2, o, cache, keep_pol);
         }
     };
 
@@ -319,7 +365,8 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         } else if (valid) {
             // flavors 4-6 (narrow COL tiles): 4 = L2::256B loads + write-back stores,
             // 5 = L2::128B loads + streaming stores, 6 = L2::256B loads + streaming stores
-            if (FLAVOR == 4 || FLAVOR == 6) v = ld_l2pf<256>(gin + (int64_t)(j + r * TPX) * is2);
+            if (cache & 1) v = ld_plain(gin + (int64_t)(j + r * TPX) * is2);          // expected in L2
+            else if (FLAVOR == 4 || FLAVOR == 6) v = ld_l2pf<256>(gin + (int64_t)(j + r * TPX) * is2);
             else if (FLAVOR == 5) v = ld_l2pf<128>(gin + (int64_t)(j + r * TPX) * is2);
             else v = ld_stream(gin + (int64_t)(j + r * TPX) * is2);
         }

@@ -2,13 +2,6 @@
 // instantiations live in the generated fft_fast_table_*.cu files.
 #include <stdint.h>
 #include "fft_fast.cuh"
-#include "fft_pipe.cuh"
-#include "fft_tma.cuh"
-
-namespace b2pipe {
-extern const PipeEntry pipe_table[];
-extern const int pipe_table_count;
-}
 
 namespace b2fast {
 
@@ -17,22 +10,6 @@ extern const int table_d_row_count, table_d_col_count, table_f_row_count, table_
 
 static int g_max_smem = 0;
 static int g_sms = 148;
-
-// persistent pipelined COL kernels (fft_pipe.cuh): kernel code 5000 + tile width
-static const b2pipe::PipeEntry *pipe_entry_for(const b2d_fft_pass &p)
-{
-    if (p.kernel < 5000 || p.kernel >= 6000) return nullptr;
-    if (p.pre_op || p.post_op || p.bluestein || p.npeer) return nullptr;
-    if (!p.load_col || !p.store_col || p.bis[0] != 2 || p.bos[0] != 2) return nullptr;
-    if ((p.is & 1) || (p.os & 1)) return nullptr;
-    for (int i = 0; i < B2D_MAX_BATCH_DIMS; ++i)
-        if ((p.bis[i] & 1) || (p.bos[i] & 1)) return nullptr;
-    for (int i = 0; i < b2pipe::pipe_table_count; ++i) {
-        const b2pipe::PipeEntry &e = b2pipe::pipe_table[i];
-        if (e.prec == p.prec && e.n == p.n && e.code == p.kernel && (!g_max_smem || (int)e.smem <= g_max_smem)) return &e;
-    }
-    return nullptr;
-}
 
 static const FastEntry *find(int prec, int n, int col, int code)
 {
@@ -48,14 +25,10 @@ static const FastEntry *find(int prec, int n, int col, int code)
 void init(int max_smem)
 {
     g_max_smem = max_smem;
-    b2tma::init(max_smem);
     {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_sms = sms;
-        for (int i = 0; i < b2pipe::pipe_table_count; ++i)
-            cudaFuncSetAttribute(b2pipe::pipe_table[i].func, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)b2pipe::pipe_table[i].smem);
     }
     const FastEntry *tabs[4] = { table_d_row, table_d_col, table_f_row, table_f_col };
     const int cnts[4] = { table_d_row_count, table_d_col_count, table_f_row_count, table_f_col_count };
@@ -115,40 +88,17 @@ int available(const b2d_fft_pass &p, int code)
 {
     b2d_fft_pass q = p;
     q.kernel = code;
-    if (code >= 6000) return b2tma::entry_for(q) != nullptr;
-    if (code >= 5000) return pipe_entry_for(q) != nullptr;
     return entry_for(q) != nullptr;
 }
 
 size_t smem_bytes(const b2d_fft_pass &p)
 {
-    if (p.kernel >= 6000) { const b2tma::TmaEntry *te = b2tma::entry_for(p); return te ? te->smem : 0; }
-    if (p.kernel >= 5000) { const b2pipe::PipeEntry *pe = pipe_entry_for(p); return pe ? pe->smem : 0; }
     const FastEntry *e = entry_for(p);
     return e ? e->smem : 0;
 }
 
 int try_launch(const b2d_fft_pass &p, cudaStream_t st)
 {
-    if (p.kernel >= 6000) return b2tma::try_launch(p, st);
-    if (p.kernel >= 5000) {
-        const b2pipe::PipeEntry *pe = pipe_entry_for(p);
-        if (!pe) return 1;
-        const size_t rs = p.prec == B2D_F32 ? 4 : 8;
-        const intptr_t din = (const char *)p.in_im - (const char *)p.in_re;
-        const intptr_t dout = (char *)p.out_im - (char *)p.out_re;
-        if ((din != (intptr_t)rs && din != -(intptr_t)rs) || (dout != (intptr_t)rs && dout != -(intptr_t)rs)) return 1;
-        const int swap_in = din < 0, swap_out = dout < 0;
-        if (((uintptr_t)(swap_in ? p.in_im : p.in_re) % (2 * rs)) || ((uintptr_t)(swap_out ? p.out_im : p.out_re) % (2 * rs)))
-            return 1;
-        b2d_fft_pass q = p;
-        q.tpb = pe->tpb;
-        const int64_t tiles = b2::grid_blocks(q);
-        if (tiles <= 0) return 0;
-        int64_t blocks = tiles < g_sms ? tiles : g_sms;          // one persistent CTA per SM
-        pe->launch(q, swap_in, swap_out, (unsigned)blocks, st);
-        return cudaGetLastError() == cudaSuccess ? 0 : -1;
-    }
     const FastEntry *e = entry_for(p);
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;

@@ -9,6 +9,12 @@
 #include "fft_generic.cuh"
 #include "real_ops.cuh"
 #include "fft_fast.cuh"
+#include "fft_split.cuh"
+
+namespace b2split {
+int launch(const b2d_split_pass &p, cudaStream_t st);
+int supported(int prec, int ra, int rb);
+}
 
 namespace {
 char g_err[512] = "";
@@ -257,6 +263,21 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(e, "fft_generic_kernel launch");
+    g_launches++;
+    return 0;
+}
+
+int b2d_split_supported(int prec, int ra, int rb)
+{
+    if (ensure_init()) return 0;
+    return b2split::supported(prec, ra, rb);
+}
+
+int b2d_launch_split_pass(const b2d_split_pass *p)
+{
+    if (ensure_init()) return -1;
+    int rc = b2split::launch(*p, g_stream);
+    if (rc) { snprintf(g_err, sizeof g_err, rc > 0 ? "split pass: layout not supported" : "split_kernel launch failed"); return -1; }
     g_launches++;
     return 0;
 }

@@ -59,13 +59,13 @@ enum { BUF_NONE = 0, BUF_IN0, BUF_IN1, BUF_OUT0, BUF_OUT1, BUF_SCRATCH0, BUF_SCR
 
 typedef struct { int buf; int64_t off; /* in reals (scratch/table: in bytes) */ } b2_ref;
 
-typedef enum { STEP_FFT = 1, STEP_COPY, STEP_REALOP } b2_step_kind;
+typedef enum { STEP_FFT = 1, STEP_COPY, STEP_REALOP, STEP_SPLIT } b2_step_kind;
 
 typedef struct {
     b2_step_kind kind;
-    union { b2d_fft_pass fft; b2d_copy copy; b2d_realop rop; } u;
+    union { b2d_fft_pass fft; b2d_copy copy; b2d_realop rop; b2d_split_pass split; } u;
     b2_ref r[6];              /* fft: in_re,in_im,out_re,out_im ; copy: in,out ;
-                                 realop: x_re,x_im,y_re,y_im,work                     */
+                                 realop: x_re,x_im,y_re,y_im,work ; split: user_re,user_im,-,-,work */
     char note[48];            /* for print_plan                                       */
     int lane;                 /* 0: caller's stream; k > 0: side stream k - 1 (exec.c: run_steps) */
 } b2_step;

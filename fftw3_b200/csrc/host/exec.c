@@ -71,6 +71,12 @@ static int run_steps(const b2_plan *p, void *const user[4])
             c.in = resolve(p, s->r[0], user, rs);
             c.out = resolve(p, s->r[1], user, rs);
             rc = b2d_launch_copy(&c);
+        } else if (s->kind == STEP_SPLIT) {
+            b2d_split_pass sp = s->u.split;
+            sp.user_re = resolve(p, s->r[0], user, rs);
+            sp.user_im = resolve(p, s->r[1], user, rs);
+            sp.work = resolve(p, s->r[4], user, rs);
+            rc = b2d_launch_split_pass(&sp);
         } else {
             b2d_realop r = s->u.rop;
             r.x_re = resolve(p, s->r[0], user, rs);

@@ -183,8 +183,6 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 }
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
-#define NPIPE 3               /* persistent pipelined strided kernels (fft_pipe.cuh), widest tiles first */
-#define NTMA 12               /* TMA-fed persistent strided kernels (fft_tma.cuh): 2 tile widths x (3 L2-promotion sizes x tiles single/paired) */
 #define NFAST 42              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor 0..6
                                  (flavor 0 plain, 1 register-capped, 4-6 L2 prefetch-size loads for narrow COL tiles) */
 
@@ -192,43 +190,7 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
-    if (variant >= NVARIANTS + NFAST + NPIPE) {
-        /* TMA-fed persistent strided kernels: k / 6 = which of the table's tile widths (widest first),
-           k % 6 = L2 promotion of the tensor map (none, 128 B, 256 B), +3 when a CTA takes tiles in adjacent pairs */
-        int k = variant - (NVARIANTS + NFAST + NPIPE), tpb, seen = 0;
-        if (k >= NTMA) return -1;
-        for (tpb = 32; tpb >= 2; --tpb) {
-            int code = 6000 + 100 * (k % 6) + tpb;
-            if (!b2d_fast_available(f, code)) continue;
-            if (seen++ == k / 6) {
-                ns = b2_factorize(f->n, f->prec, 0, f->radix);
-                if (ns == 0) return -1;
-                f->nstages = ns < 0 ? 0 : ns;
-                fill_geometry(f, 0);
-                f->kernel = code;
-                return 0;
-            }
-        }
-        return -1;
-    }
-    if (variant >= NVARIANTS + NFAST) {
-        /* persistent cp.async-pipelined strided kernels: tile widths are whatever the table holds;
-           variant k tries the k-th widest */
-        int want = variant - (NVARIANTS + NFAST), tpb, seen = 0;
-        if (want >= NPIPE) return -1;
-        for (tpb = 32; tpb >= 2; --tpb) {
-            if (!b2d_fast_available(f, 5000 + tpb)) continue;
-            if (seen++ == want) {
-                ns = b2_factorize(f->n, f->prec, 0, f->radix);
-                if (ns == 0) return -1;
-                f->nstages = ns < 0 ? 0 : ns;
-                fill_geometry(f, 0);
-                f->kernel = 5000 + tpb;
-                return 0;
-            }
-        }
-        return -1;
-    }
+    if (variant >= NVARIANTS + NFAST) return -1;
     if (variant >= NVARIANTS) {
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
@@ -267,13 +229,24 @@ static int configure_variant(b2d_fft_pass *f, int variant)
     return 0;
 }
 
-/* closed-form choice (FFTW_ESTIMATE): a specialised kernel when one exists */
+/* closed-form choice (FFTW_ESTIMATE): a specialised kernel when one exists.  Strided (COL) passes
+   measured on B200 (profiles/r01_*): 64-byte tiles with L2::256B loads win while a pencil's stride stays
+   inside a few 2 MiB pages (two CTAs per SM overlap load and compute), 128-byte tiles win beyond that
+   (every row of the tile is in a page of its own). */
 static int estimate_variant(b2d_fft_pass *f)
 {
     static const int col_pref[] = { 3, 4, 2, 5 }, row_pref[] = { 1, 2, 0, 3, 4, 5 };
     int col = f->load_col || f->store_col, i;       /* wide tiles whenever a side is strided */
     const int *pref = col ? col_pref : row_pref;
     int npref = col ? 4 : 6;
+    if (f->load_col && f->store_col && !f->pre_op && !f->post_op && !f->npeer) {
+        size_t esz = 2 * real_size(f->prec);
+        int64_t stride_bytes = llabs(f->is) * (int64_t)real_size(f->prec);
+        int want = stride_bytes >= (1 << 20) ? 128 : 64, lg = 0, v;
+        while (((size_t)1 << lg) * esz < (size_t)want) ++lg;
+        v = NVARIANTS + ((want == 64 && !(f->cache & 1)) ? 6 * 6 : 0) + lg;
+        { b2d_fft_pass t = *f; if (!configure_variant(&t, v)) return v; }
+    }
     for (i = 0; i < npref; ++i) {
         b2d_fft_pass t = *f;
         if (!configure_variant(&t, NVARIANTS + pref[i])) return NVARIANTS + pref[i];
@@ -438,9 +411,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         if (!have && b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
         if (!have && pat >= 1) {
-            /* the TMA-fed kernels (variants >= NVARIANTS + NFAST + NPIPE) are not searched: measured no
-               faster than the register-resident ones -- FFTW3_B200_FORCE_VARIANT only */
-            int v, nv = NVARIANTS + NFAST + NPIPE, bestv = -1;
+            int v, nv = NVARIANTS + NFAST, bestv = -1;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
@@ -461,7 +432,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
                             f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
                             (long long)f->bn[1], (long long)f->bn[2], v,
-                            trial.kernel >= 6000 ? "tma" : trial.kernel >= 5000 ? "pipelined" : (trial.kernel ? "codelet" : "generic"),
+                            trial.kernel ? "codelet" : "generic",
                             trial.kernel ? trial.kernel % 100 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
                 }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
@@ -535,6 +506,109 @@ typedef struct {
 static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                       const b2_tensor *batch_in, b2_ops ops, int scratch_slot, const char *note);
 
+/* ---- strided transform as two register-only sub-passes through an L2-resident buffer (device/fft_split.cuh)
+   Applicable to a plain c2c pass along a strided dimension whose pencils are contiguous interleaved complex
+   numbers on both sides.  The pencils are cut into groups of FFTW3_B200_SPLIT_MB MiB (default 16); a group's
+   phase A and phase B are consecutive launches on one lane, consecutive groups rotate over the lanes, and
+   every lane owns its slice of scratch slot 1 -- small enough that the work data never leaves L2. */
+static int split_radices(int64_t n, int prec, int *ra, int *rb)
+{
+    static const int cand[][2] = { {32, 32}, {16, 32}, {16, 16}, {8, 16}, {8, 8} };
+    size_t i;
+    for (i = 0; i < sizeof cand / sizeof cand[0]; ++i)
+        if ((int64_t)cand[i][0] * cand[i][1] == n && b2d_split_supported(prec, cand[i][0], cand[i][1])) {
+            *ra = cand[i][0]; *rb = cand[i][1];
+            return 1;
+        }
+    return 0;
+}
+
+/* does the view address interleaved complex numbers (im = re +- 1 real), vector-aligned at plan time? */
+static int view_interleaved(const b2_plan *p, b2_view v)
+{
+    int64_t rs = (int64_t)real_size(p->prob.prec);
+    const char *re = NULL, *im = NULL;
+    if (v.re.buf == v.im.buf) return llabs(v.im.off - v.re.off) == 1 && v.re.buf >= BUF_SCRATCH0 &&
+                                     ((v.re.off < v.im.off ? v.re.off : v.im.off) % 2) == 0;
+    if (v.re.buf == BUF_IN0 && v.im.buf == BUF_IN1) { re = (const char *)p->prob.in0; im = (const char *)p->prob.in1; }
+    else if (v.re.buf == BUF_IN1 && v.im.buf == BUF_IN0) { re = (const char *)p->prob.in1; im = (const char *)p->prob.in0; }
+    else if (v.re.buf == BUF_OUT0 && v.im.buf == BUF_OUT1) { re = (const char *)p->prob.out0; im = (const char *)p->prob.out1; }
+    else if (v.re.buf == BUF_OUT1 && v.im.buf == BUF_OUT0) { re = (const char *)p->prob.out1; im = (const char *)p->prob.out0; }
+    else return 0;
+    if (!re || !im || v.re.off != v.im.off) return 0;
+    if (im - re != rs && im - re != -rs) return 0;
+    return ((uintptr_t)((im < re ? im : re) + v.re.off * rs) % (size_t)(2 * rs)) == 0;
+}
+
+static int split_wanted(const b2_plan *p, const fft1d_ctx *c, b2_view in, b2_view out, const b2_dim *bd, int brank,
+                        int *ra, int *rb)
+{
+    const char *e = getenv("FFTW3_B200_SPLIT");
+    int mode = e ? atoi(e) : 1;
+    int64_t rs = (int64_t)real_size(c->prec), sb_in, sb_out;
+    if (!mode || brank < 1) return 0;
+    if (c->ops.pre_op || c->ops.post_op || c->ops.cache) return 0;
+    if (p->prob.flags & B2F_UNALIGNED) return 0;
+    if (bd[0].is != 2 || bd[0].os != 2 || bd[0].n < 64) return 0;
+    if ((in.stride & 1) || (out.stride & 1) || llabs(in.stride) <= 2 || llabs(out.stride) <= 2) return 0;
+    if (!view_interleaved(p, in) || !view_interleaved(p, out)) return 0;
+    if (brank >= 2 && ((bd[1].is & 1) || (bd[1].os & 1))) return 0;
+    if (brank >= 3 && ((bd[2].is & 1) || (bd[2].os & 1))) return 0;
+    if (!split_radices(c->n, c->prec, ra, rb)) return 0;
+    sb_in = llabs(in.stride) * rs; sb_out = llabs(out.stride) * rs;
+    if (mode == 1 && sb_in < (1 << 20) && sb_out < (1 << 20)) return 0;     /* rows share 2 MiB pages: one kernel does it */
+    return 1;
+}
+
+static int emit_split(b2_plan *p, const fft1d_ctx *c, b2_view in, b2_view out, const b2_dim *bd, int brank, int ra, int rb)
+{
+    const char *eg = getenv("FFTW3_B200_SPLIT_MB"), *el = getenv("FFTW3_B200_SPLIT_LANES");
+    int64_t n = c->n, esz = 2 * (int64_t)real_size(c->prec);
+    int64_t gbytes = (int64_t)(eg ? atol(eg) : 16) << 20;
+    int nlanes = el ? atoi(el) : 3;
+    int64_t pmax = gbytes / (n * esz), nc0 = bd[0].n, nb1 = brank >= 2 ? bd[1].n : 1, n2 = brank >= 3 ? bd[2].n : 1;
+    int64_t cstep, bstep, i2, b0, c0, gi = 0;
+    const void *tw = plan_table(p, c->prec, TAB_TWIDDLE, n, 0);
+    if (!tw) return -1;
+    if (nlanes < 1) nlanes = 1;
+    if (nlanes > 6) nlanes = 6;
+    pmax -= pmax % 128;
+    if (pmax < 128) pmax = 128;
+    if (nc0 > pmax) { cstep = pmax; bstep = 1; }
+    else { cstep = nc0; bstep = pmax / nc0; if (bstep < 1) bstep = 1; }
+    need_scratch(p, 1, (size_t)nlanes * (size_t)(cstep * bstep) * (size_t)n * (size_t)esz);
+    for (i2 = 0; i2 < n2; ++i2)
+        for (b0 = 0; b0 < nb1; b0 += bstep)
+            for (c0 = 0; c0 < nc0; c0 += cstep, ++gi) {
+                int64_t nc = nc0 - c0 < cstep ? nc0 - c0 : cstep, nb = nb1 - b0 < bstep ? nb1 - b0 : bstep;
+                int lane = (int)(gi % nlanes), ph;
+                for (ph = 0; ph < 2; ++ph) {
+                    b2_step *s = new_step(p, STEP_SPLIT);
+                    b2d_split_pass *sp;
+                    b2_view v = ph ? out : in;
+                    int64_t off;
+                    if (!s) return -1;
+                    sp = &s->u.split;
+                    sp->prec = c->prec; sp->ra = ra; sp->rb = rb; sp->phase = ph;
+                    sp->row_stride = v.stride;
+                    sp->nc = nc; sp->nb = nb;
+                    sp->bs = brank >= 2 ? (ph ? bd[1].os : bd[1].is) : 0;
+                    sp->tw = tw;
+                    off = 2 * c0 + b0 * sp->bs + (brank >= 3 ? i2 * (ph ? bd[2].os : bd[2].is) : 0);
+                    s->r[0] = v.re; s->r[0].off += off;
+                    s->r[1] = v.im; s->r[1].off += off;
+                    s->r[4] = mkref(BUF_SCRATCH1, (int64_t)lane * cstep * bstep * n * 2);
+                    s->lane = nlanes > 1 ? 1 + lane : 0;
+                    snprintf(s->note, sizeof s->note, "split %s %dx%d", ph ? "B" : "A", ra, rb);
+                }
+            }
+    {
+        double nbt = (double)(nc0 * nb1 * n2), lg = log2((double)n);
+        p->est_flops_add += nbt * 3.0 * n * lg; p->est_flops_mul += nbt * 0.5 * n * lg; p->est_flops_fma += nbt * 1.0 * n * lg;
+    }
+    return 0;
+}
+
 /* n = n1 * n2 with both halves smooth and one-pass sized: the n1 closest to sqrt(n) from below (or the one
    FFTW3_B200_FOURSTEP_N1 pins), -1 if there is none */
 static int64_t two_factor_split(int64_t n, int prec)
@@ -560,8 +634,11 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
     int radix[64];
     int smooth = b2_factorize(n, c->prec, 0, radix) != 0;
 
-    if (smooth && single_pass_fits(n, c->prec))
+    if (smooth && single_pass_fits(n, c->prec)) {
+        int ra, rb;
+        if (split_wanted(p, c, in, out, bd, brank, &ra, &rb)) return emit_split(p, c, in, out, bd, brank, ra, rb);
         return emit_single(p, c->prec, n, in, out, bd, brank, c->ops, 0, c->note);
+    }
 
     /* index-dependent fused ops cannot follow a second level of digit reversal: such lines (odd smooth
        real transforms beyond ~1.6e7 points) take the chirp-z route, whose pre/post maps carry the ops */
@@ -914,71 +991,82 @@ static int plan_c2c(b2_plan *p)
         if (rc) return rc;
         return emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_OUT1, 0), &q->vecsz, 1);
     }
-    d = q->sz.rnk - 1;
-    /* L2 blocking of the two innermost passes.  The pass over the last dim and
-       the pass over the next one only couple elements that share every other
-       index, so they can be run group by group over the outermost remaining
-       dim: with a group small enough to stay in the 126 MB L2, the second pass
-       reads what the first just wrote from L2 and the pair costs one HBM read
-       and one HBM write instead of two of each ("fused multi-pass": the role of
-       the reference's cache-oblivious rank-geq2 / buffered recursion,
-       dft/rank-geq2.c:42-52, dft/buffered.c:41-69, on a cache that is shared
-       by all SMs). */
-    if (q->sz.rnk >= 2 && p->l2_block_bytes > 0) {
-        int oi = -1, ovec = 0, i;
-        int64_t best = 0, per = 2 * (int64_t)real_size(q->prec), nout, G;
-        for (i = 0; i < q->sz.rnk - 2; ++i)
-            if (llabs(q->sz.d[i].os) > best) { best = llabs(q->sz.d[i].os); oi = i; ovec = 0; }
-        for (i = 0; i < q->vecsz.rnk; ++i)
-            if (llabs(q->vecsz.d[i].os) > best) { best = llabs(q->vecsz.d[i].os); oi = i; ovec = 1; }
-        if (oi >= 0) {
-            const b2_dim *od = ovec ? &q->vecsz.d[oi] : &q->sz.d[oi];
-            nout = od->n;
-            for (i = 0; i < q->sz.rnk; ++i) if (ovec || i != oi) per *= q->sz.d[i].n;
-            for (i = 0; i < q->vecsz.rnk; ++i) if (!ovec || i != oi) per *= q->vecsz.d[i].n;
-            if (!p->inplace) per *= 2;
-            G = (int64_t)p->l2_block_bytes / (per > 0 ? per : 1);
-            if (G >= 1 && G < nout && nout / G <= 4096) {
-                int64_t g0;
-                for (g0 = 0; g0 < nout; g0 += G) {
-                    int64_t cnt = (nout - g0 < G) ? nout - g0 : G;
-                    int pass;
-                    for (pass = 0; pass < 2; ++pass) {
-                        b2_problem qq = *q;
-                        b2_tensor batch;
-                        b2_view in, out;
-                        int dd = q->sz.rnk - 1 - pass;
-                        b2_dim *md = ovec ? &qq.vecsz.d[oi] : &qq.sz.d[oi];
-                        md->n = cnt;
-                        other_dims(&qq, dd, pass, &batch);
-                        out.re = mkref(BUF_OUT0, g0 * od->os); out.im = mkref(BUF_OUT1, g0 * od->os);
-                        out.stride = q->sz.d[dd].os;
-                        if (pass == 0) {
-                            in.re = mkref(BUF_IN0, g0 * od->is); in.im = mkref(BUF_IN1, g0 * od->is);
-                            in.stride = q->sz.d[dd].is;
-                        } else in = out;
-                        none.cache = pass ? 1 : 2;   /* first pass leaves its output in L2 for the second */
-                        rc = emit_fft1d(p, q->prec, q->sz.d[dd].n, in, out, &batch, none, 1,
-                                        pass ? "dft(in place, L2 group)" : "dft(L2 group)");
-                        none.cache = 0;
-                        if (rc) return rc;
+    /* L2-resident pass pairs.  The pass over the last (contiguous) dim and the pass over one other dim
+       only couple elements that share every remaining index, so the two can be run group by group over a
+       third dim: with a group small enough to stay in the 126 MB L2, the second pass reads what the first
+       just wrote from L2 and the pair costs one HBM read and one HBM write instead of two of each ("fused
+       multi-pass": the role of the reference's cache-oblivious rank-geq2 / buffered recursion,
+       dft/rank-geq2.c:42-52, dft/buffered.c:41-69, on a cache shared by all SMs).  Consecutive groups go to
+       different lanes (side streams, exec.c): they are independent, so the tail of one group's kernels is
+       filled by the head of the next group's.  The first pass keeps its output in L2 (ordinary or
+       evict_last stores), the second reads it with ordinary loads and streams its result out. */
+    {
+        int done[B2_MAXRANK];
+        int i, last = q->sz.rnk - 1;
+        for (i = 0; i < B2_MAXRANK; ++i) done[i] = 0;
+        if (q->sz.rnk >= 2 && p->l2_block_bytes > 0) {
+            const char *em = getenv("FFTW3_B200_L2_PAIR"), *el = getenv("FFTW3_B200_L2_LANES"), *ek = getenv("FFTW3_B200_L2_KEEP");
+            int pair = (em && !strcmp(em, "outer") && q->sz.rnk >= 3) ? 0 : last - 1;
+            int nlanes = el ? atoi(el) : 3, keep = ek ? atoi(ek) : 2;
+            int oi = -1, ovec = 0;
+            int64_t best = 0, per = 2 * (int64_t)real_size(q->prec), nout, G;
+            if (nlanes < 0) nlanes = 0;
+            if (nlanes > 6) nlanes = 6;
+            for (i = 0; i < q->sz.rnk; ++i)
+                if (i != last && i != pair && llabs(q->sz.d[i].os) > best) { best = llabs(q->sz.d[i].os); oi = i; ovec = 0; }
+            for (i = 0; i < q->vecsz.rnk; ++i)
+                if (llabs(q->vecsz.d[i].os) > best) { best = llabs(q->vecsz.d[i].os); oi = i; ovec = 1; }
+            if (oi >= 0) {
+                const b2_dim *od = ovec ? &q->vecsz.d[oi] : &q->sz.d[oi];
+                nout = od->n;
+                for (i = 0; i < q->sz.rnk; ++i) if (ovec || i != oi) per *= q->sz.d[i].n;
+                for (i = 0; i < q->vecsz.rnk; ++i) if (!ovec || i != oi) per *= q->vecsz.d[i].n;
+                if (!p->inplace) per *= 2;
+                G = (int64_t)p->l2_block_bytes / (per > 0 ? per : 1);
+                if (G >= 1 && G < nout && nout / G <= 8192) {
+                    int64_t g0, gi = 0;
+                    for (g0 = 0; g0 < nout; g0 += G, ++gi) {
+                        int64_t cnt = (nout - g0 < G) ? nout - g0 : G;
+                        int pass, s0 = p->nsteps;
+                        for (pass = 0; pass < 2; ++pass) {
+                            b2_problem qq = *q;
+                            b2_tensor batch;
+                            b2_view in, out;
+                            int dd = pass ? pair : last;
+                            b2_dim *md = ovec ? &qq.vecsz.d[oi] : &qq.sz.d[oi];
+                            md->n = cnt;
+                            other_dims(&qq, dd, pass, &batch);
+                            out.re = mkref(BUF_OUT0, g0 * od->os); out.im = mkref(BUF_OUT1, g0 * od->os);
+                            out.stride = q->sz.d[dd].os;
+                            if (pass == 0) {
+                                in.re = mkref(BUF_IN0, g0 * od->is); in.im = mkref(BUF_IN1, g0 * od->is);
+                                in.stride = q->sz.d[dd].is;
+                            } else in = out;
+                            none.cache = pass ? 1 : keep;   /* first pass leaves its output in L2 for the second */
+                            rc = emit_fft1d(p, q->prec, q->sz.d[dd].n, in, out, &batch, none, 1,
+                                            pass ? "dft(in place, L2 group)" : "dft(L2 group)");
+                            none.cache = 0;
+                            if (rc) return rc;
+                        }
+                        if (nlanes > 0) for (i = s0; i < p->nsteps; ++i) p->steps[i].lane = 1 + (int)(gi % nlanes);
                     }
+                    first = 0;
+                    done[last] = done[pair] = 1;
                 }
-                first = 0;
-                d = q->sz.rnk - 3;
             }
         }
-    }
-    for (; d >= 0; --d) {
-        b2_tensor batch;
-        b2_view in, out;
-        other_dims(q, d, !first, &batch);
-        out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = q->sz.d[d].os;
-        if (first) { in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN1, 0); in.stride = q->sz.d[d].is; }
-        else in = out;
-        rc = emit_fft1d(p, q->prec, q->sz.d[d].n, in, out, &batch, none, 1, first ? "dft" : "dft(in place)");
-        if (rc) return rc;
-        first = 0;
+        for (d = q->sz.rnk - 1; d >= 0; --d) {
+            b2_tensor batch;
+            b2_view in, out;
+            if (done[d]) continue;
+            other_dims(q, d, !first, &batch);
+            out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = q->sz.d[d].os;
+            if (first) { in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN1, 0); in.stride = q->sz.d[d].is; }
+            else in = out;
+            rc = emit_fft1d(p, q->prec, q->sz.d[d].n, in, out, &batch, none, 1, first ? "dft" : "dft(in place)");
+            if (rc) return rc;
+            first = 0;
+        }
     }
     return 0;
 }
@@ -1526,12 +1614,12 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel >= 6000) fprintf(f, "tma-tile=%d/l2p%d", q->kernel % 100, (q->kernel / 100) % 10);
-            else if (q->kernel >= 5000) fprintf(f, "pipelined-tile=%d", q->kernel - 5000);
-            else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
+            if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",
                     q->bluestein == 2 ? " rader" : (q->bluestein ? " bluestein" : (q->r2r_pair ? " paired-lines" : "")));
+        } else if (s->kind == STEP_SPLIT) {
+            fprintf(f, "\n  (%s pencils=%lldx%lld lane=%d)", s->note, (long long)s->u.split.nc, (long long)s->u.split.nb, s->lane);
         } else if (s->kind == STEP_COPY) {
             fprintf(f, "\n  (copy %lldx%lldx%lldx%lld)", (long long)s->u.copy.n[0], (long long)s->u.copy.n[1],
                     (long long)s->u.copy.n[2], (long long)s->u.copy.n[3]);

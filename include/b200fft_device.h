@@ -110,6 +110,23 @@ typedef struct b2d_fft_pass {
     int tw_smem;              /* generic kernel: stage the n-entry twiddle table in shared memory */
 } b2d_fft_pass;
 
+/* One half of a strided transform of length ra * rb done as two register-only sub-passes through an
+ * L2-resident work buffer (device/fft_split.cuh).  Pencils are contiguous interleaved complex numbers:
+ * `nc` of them per batch item, `nb` batch items `bs` reals apart; consecutive transform indices are
+ * `row_stride` reals apart.  work = [ka][r0][b][c] interleaved complex.
+ *   phase 0: user rows rb*j + r0 (j < ra) -> FFT_ra -> times W^(r0 ka) -> work[ka][r0]
+ *   phase 1: work[ka][r0] (r0 < rb) -> FFT_rb -> user rows ka + ra*kb                              */
+typedef struct b2d_split_pass {
+    int prec;
+    int ra, rb;
+    int phase;
+    int64_t row_stride;
+    int64_t nc, nb, bs;
+    void *user_re, *user_im;  /* phase 0 reads them, phase 1 writes them; im = re +- 1 (interleaved) */
+    void *work;
+    const void *tw;           /* ra * rb entries exp(-2 pi i k / (ra rb)) */
+} b2d_split_pass;
+
 /* strided N-d copy / rank-0 transform (kernel/cpy2d.c, rdft/rank0.c analogue);
  * element = `elem_reals` consecutive reals (1: real scalar, 2: interleaved complex) */
 typedef struct b2d_copy {
@@ -196,6 +213,8 @@ int  b2d_timer_stop(float *ms);
 int  b2d_launch_fft_pass(const b2d_fft_pass *p);
 size_t b2d_fft_pass_smem(const b2d_fft_pass *p);  /* dynamic smem bytes it needs   */
 int  b2d_fast_available(const b2d_fft_pass *p, int code); /* specialised kernel exists for this shape? */
+int  b2d_launch_split_pass(const b2d_split_pass *p);
+int  b2d_split_supported(int prec, int ra, int rb);      /* register-only sub-pass kernels exist for this split? */
 int  b2d_launch_copy(const b2d_copy *c);
 int  b2d_launch_realop(const b2d_realop *r);
 

@@ -20,6 +20,7 @@
 
 #include "../../fftw3_b200/csrc/device/fft_generic.cuh"
 #include "../../fftw3_b200/csrc/device/real_ops.cuh"
+#include "../../fftw3_b200/csrc/device/fft_split.cuh"
 
 static char g_err[256] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -88,6 +89,34 @@ static void run_realop(const b2d_realop &r)
         }
 }
 
+/* the register-only sub-passes: same per-thread body as the CUDA kernel, CTAs and threads as loops */
+template <typename T, int R, int PHASE>
+static void run_split(const b2d_split_pass &p, int swap)
+{
+    using namespace b2split;
+    const int64_t blocks = split_blocks(p);
+    const int64_t tiles_c = (p.nc + B2_SPLIT_THREADS - 1) / B2_SPLIT_THREADS;
+    for (int64_t blk = 0; blk < blocks; ++blk) {
+        b2::cplx<T> tws[R];
+        const int o = (int)((blk / tiles_c) % p.rb);
+        for (int k = 0; k < R; ++k) tws[k] = ((const b2::cplx<T> *)p.tw)[(int64_t)o * k];
+        for (int t = 0; t < B2_SPLIT_THREADS; ++t) split_thread<T, R, PHASE>(p, swap, blk, t, tws);
+    }
+}
+template <typename T>
+static int run_split_t(const b2d_split_pass &p, int swap)
+{
+    const int r = p.phase == 0 ? p.ra : p.rb;
+    if (p.phase == 0) {
+        if (r == 8) run_split<T, 8, 0>(p, swap); else if (r == 16) run_split<T, 16, 0>(p, swap);
+        else if (r == 32) run_split<T, 32, 0>(p, swap); else return -1;
+    } else {
+        if (r == 8) run_split<T, 8, 1>(p, swap); else if (r == 16) run_split<T, 16, 1>(p, swap);
+        else if (r == 32) run_split<T, 32, 1>(p, swap); else return -1;
+    }
+    return 0;
+}
+
 extern "C" {
 int b2d_device_count(void) { return 1; }
 const char *b2d_device_name(void) { return "emulated-for-unit-tests"; }
@@ -154,6 +183,22 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     if (p->prec == B2D_F32) run_fft_pass<float>(*p); else run_fft_pass<double>(*p);
     ++g_launches;
     return 0;
+}
+int b2d_split_supported(int, int ra, int rb)
+{
+    return (ra == 8 || ra == 16 || ra == 32) && (rb == 8 || rb == 16 || rb == 32);
+}
+int b2d_launch_split_pass(const b2d_split_pass *p)
+{
+    const size_t rs = p->prec == B2D_F32 ? 4 : 8;
+    const intptr_t d = (const char *)p->user_im - (const char *)p->user_re;
+    if ((d != (intptr_t)rs && d != -(intptr_t)rs) || (p->row_stride & 1) || (p->bs & 1)) {
+        snprintf(g_err, sizeof g_err, "split pass: layout not supported");
+        return -1;
+    }
+    int rc = p->prec == B2D_F32 ? run_split_t<float>(*p, d < 0) : run_split_t<double>(*p, d < 0);
+    ++g_launches;
+    return rc;
 }
 int b2d_launch_copy(const b2d_copy *c)
 {

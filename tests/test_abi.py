@@ -34,6 +34,18 @@ def test_exports_every_declared_symbol():
         assert os.path.exists(os.path.join(os.path.dirname(path), alias))
 
 
+def test_exports_nothing_but_the_fftw_namespace():
+    """A libfftw3.so.3 stand-in must not leak internals (C++ kernel templates, b2_* / b2d_* helpers):
+    the linker version script fftw3_b200/csrc/exports.map keeps fftw_* and fftwf_* only."""
+    import subprocess
+    from fftw3_b200 import binding
+    out = subprocess.run(["nm", "-D", "--defined-only", binding.default_library_path()], capture_output=True, text=True,
+                         check=True).stdout
+    names = [ln.split()[-1] for ln in out.splitlines() if ln.strip()]
+    leaked = [n for n in names if not (n.startswith("fftw_") or n.startswith("fftwf_"))]
+    assert len(names) > 150 and not leaked, leaked[:10]
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -43,18 +43,10 @@ def timeit(lib, prec, plan, reps, scale_fn=None):
     return best, launches
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="")
-    ap.add_argument("--flags", default="measure")
-    a = ap.parse_args()
-    lib = B.load()
-    peak = 6454.3
-    try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        pass
-    flags = B.FFTW_MEASURE if a.flags == "measure" else B.FFTW_ESTIMATE
+def run_configs(lib, flags, peak, only="", echo=False):
+    """Times the BASELINE.json configs other than the bench workload; returns one dict per config.
+    `roofline_frac_1pass` = (one read + one write of the arrays) / time / peak: the fraction of the
+    speed of light a plan that touched HBM exactly once would reach."""
     dev = "cuda"
     out = []
 
@@ -62,11 +54,12 @@ def main():
         line = {"config": name, "ms": ms, "gflops": flops / ms / 1e6, "ideal_gbs_1pass": bytes_1pass / ms / 1e6,
                 "roofline_frac_1pass": bytes_1pass / ms / 1e6 / peak, "launches": launches,
                 "plan": " ".join(lib.sprint_plan(prec, plan).split())[:600]}
-        print(json.dumps(line), flush=True)
+        if echo:
+            print(json.dumps(line), flush=True)
         out.append(line)
 
     def want(k):
-        return not a.only or k in a.only.split(",")
+        return not only or k in only.split(",")
 
     if want("C1"):
         n, hm = 1024, 16384
@@ -134,6 +127,23 @@ def main():
         ms, l = timeit(lib, "f", p, 20)
         report("(extra) c2c f32 N=1024 x16384", 5 * n * hm * math.log2(n), 2 * 8 * n * hm, ms, l, p, "f")
         lib.destroy_plan("f", p)
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--flags", default="measure")
+    a = ap.parse_args()
+    lib = B.load()
+    peak = 6454.3
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    flags = B.FFTW_MEASURE if a.flags == "measure" else B.FFTW_ESTIMATE
+    run_configs(lib, flags, peak, a.only, echo=True)
 
 
 if __name__ == "__main__":
