@@ -68,6 +68,8 @@ typedef struct {
                                  realop: x_re,x_im,y_re,y_im,work ; split: user_re,user_im,-,-,work */
     char note[48];            /* for print_plan                                       */
     int lane;                 /* 0: caller's stream; k > 0: side stream k - 1 (exec.c: run_steps) */
+    int fence;                /* all lanes are joined before this step: it starts a pass that reads what
+                                 the previous pass wrote through other lanes                            */
 } b2_step;
 
 typedef struct b2_table {     /* device-resident constant table, refcounted & shared */
@@ -78,6 +80,19 @@ typedef struct b2_table {     /* device-resident constant table, refcounted & sh
     size_t bytes;
     int refs;
 } b2_table;
+
+/* decomposition choices above the single pass (what the reference's planner explores as alternative
+   solver trees, kernel/planner.c:518-615): measured as whole plans by FFTW_MEASURE and remembered in
+   wisdom under the problem's signature.  Environment variables (FFTW3_B200_L2_*, FFTW3_B200_SPLIT*)
+   pin them for experiments and tests. */
+typedef struct {
+    size_t l2_block_bytes;    /* L2-resident pass pairs: group size, 0 = off                    */
+    int l2_lanes, l2_keep;    /* lanes the groups rotate over; cache hint of the first pass     */
+    int l2_pair_outer;        /* pair the last dim with dim 0 instead of the next-to-last       */
+    int split_mode;           /* strided pass as two register-only sub-passes: 0 never, 1 when rows are >= 1 MiB apart, 2 whenever applicable */
+    size_t split_bytes;       /* its group size                                                  */
+    int split_lanes;
+} b2_plan_opts;
 
 typedef struct b2_plan {
     int refcnt;
@@ -91,7 +106,9 @@ typedef struct b2_plan {
     double est_flops_add, est_flops_mul, est_flops_fma;
     double cost;              /* measured ms (or estimate) */
     int is_nop;
-    size_t l2_block_bytes;    /* group size for L2-blocked pass pairs (0 = off) */
+    b2_plan_opts opt;
+    int alt;                  /* which whole-plan alternative this is (print_plan)               */
+    int no_fence;             /* planner state: passes emitted now are independent of the previous one (L2 groups) */
     int inplace;
     int destroys_input;
     /* host staging state (execute on host pointers) */
@@ -145,6 +162,7 @@ int64_t b2_max_single_pass(int prec);
 /* wisdom.c */
 typedef struct { uint64_t h[2]; } b2_sig;
 b2_sig b2_sig_of_pass(const b2d_fft_pass *p, int inplace);
+b2_sig b2_sig_of_problem(const b2_problem *q, int inplace);
 int  b2_wisdom_lookup(b2_sig s, unsigned patience, int *variant);
 void b2_wisdom_store(b2_sig s, unsigned patience, int variant);
 void b2_wisdom_forget(void);

@@ -55,6 +55,7 @@ static int run_steps(const b2_plan *p, void *const user[4])
         int rc = 0;
         void *aux = NULL, *prev = NULL;
         if (s->lane > 0 && s->lane <= B2_MAX_LANES) aux = b2d_aux_stream(s->lane + 1);
+        if (s->fence && active) join_lanes(mainst, &active);
         if (aux) {
             if (!(active & (1u << s->lane))) { b2d_stream_wait_stream(aux, mainst); active |= 1u << s->lane; }
             prev = b2d_push_stream(aux);

@@ -23,6 +23,50 @@ double b2_timelimit = -1.0;
    FFTW3_B200_L2_BLOCK_MB overrides, 0 disables */
 #define B2_DEFAULT_L2_BLOCK_MB 0    /* measured on B200: per-group launches lose more to tails than L2 reuse wins */
 
+/* ------------------------------------------------------------------ plan options */
+static void opts_from_env(b2_plan_opts *o)
+{
+    const char *e;
+    memset(o, 0, sizeof *o);
+    o->l2_block_bytes = (size_t)B2_DEFAULT_L2_BLOCK_MB << 20;
+    o->l2_lanes = 2; o->l2_keep = 4;
+    o->split_mode = 0; o->split_bytes = (size_t)16 << 20; o->split_lanes = 3;
+    if ((e = getenv("FFTW3_B200_L2_BLOCK_MB"))) o->l2_block_bytes = (size_t)atol(e) << 20;
+    if ((e = getenv("FFTW3_B200_L2_BLOCK_KB"))) o->l2_block_bytes = (size_t)atol(e) << 10;      /* finer unit, for tests */
+    if ((e = getenv("FFTW3_B200_L2_LANES"))) o->l2_lanes = atoi(e);
+    if ((e = getenv("FFTW3_B200_L2_KEEP"))) o->l2_keep = atoi(e);
+    if ((e = getenv("FFTW3_B200_L2_PAIR"))) o->l2_pair_outer = !strcmp(e, "outer");
+    if ((e = getenv("FFTW3_B200_SPLIT"))) o->split_mode = atoi(e);
+    if ((e = getenv("FFTW3_B200_SPLIT_MB"))) o->split_bytes = (size_t)atol(e) << 20;
+    if ((e = getenv("FFTW3_B200_SPLIT_KB"))) o->split_bytes = (size_t)atol(e) << 10;
+    if ((e = getenv("FFTW3_B200_SPLIT_LANES"))) o->split_lanes = atoi(e);
+}
+
+static int opts_pinned_by_env(void)
+{
+    static const char *names[] = { "FFTW3_B200_L2_BLOCK_MB", "FFTW3_B200_L2_BLOCK_KB", "FFTW3_B200_L2_LANES",
+        "FFTW3_B200_L2_KEEP", "FFTW3_B200_L2_PAIR", "FFTW3_B200_SPLIT", "FFTW3_B200_SPLIT_MB", "FFTW3_B200_SPLIT_KB",
+        "FFTW3_B200_SPLIT_LANES", "FFTW3_B200_FORCE_VARIANT" };
+    size_t i;
+    for (i = 0; i < sizeof names / sizeof names[0]; ++i) if (getenv(names[i])) return 1;
+    return 0;
+}
+
+/* planning clock: fftw_set_timelimit (api/apiplan.c:92-136, kernel/planner.c:493-516) bounds the time
+   spent MEASURING; once it has run out every remaining choice is made by the estimator */
+#include <time.h>
+static double g_plan_t0 = 0.0;
+static double now_seconds(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static int time_is_up(void)
+{
+    return b2_timelimit >= 0.0 && now_seconds() - g_plan_t0 >= b2_timelimit;
+}
+
 /* ------------------------------------------------------------------ helpers */
 typedef struct {           /* where a complex (or real) line lives */
     b2_ref re, im;
@@ -410,8 +454,8 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         }
         if (!have && b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
-        if (!have && pat >= 1) {
-            int v, nv = NVARIANTS + NFAST, bestv = -1;
+        if (!have && pat >= 1 && !time_is_up()) {
+            int v, nv = NVARIANTS + NFAST, bestv = -1, timed_any = 0;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
@@ -425,8 +469,9 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                 b2d_fft_pass trial = *f;
                 if (v >= 6 && v < NVARIANTS && pat < 2) continue;   /* extra generic shapes: PATIENT only */
                 if (configure_variant(&trial, v)) continue;
-                /* skip duplicates of an earlier geometry */
+                if (timed_any && time_is_up()) break;     /* fftw_set_timelimit: keep the best so far */
                 t = time_pass(&trial, inplace, dri, dro);
+                timed_any = 1;
                 if (getenv("FFTW3_B200_VERBOSE")) {
                     double bytes = 4.0 * real_size(prec) * (double)f->n * (double)(f->bn[0] * f->bn[1] * f->bn[2]);
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
@@ -439,7 +484,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
             }
             if (bestv >= 0) { variant = bestv; have = 1; p->cost += bestt; }
         }
-        if (!have) variant = estimate_variant(f);
+        if (!have) { variant = estimate_variant(f); pat = 0; }      /* nothing was timed: remembered as an estimate */
         if (configure_variant(f, variant)) {
             if (configure_variant(f, 0)) return -1;
             variant = 0;
@@ -543,8 +588,7 @@ static int view_interleaved(const b2_plan *p, b2_view v)
 static int split_wanted(const b2_plan *p, const fft1d_ctx *c, b2_view in, b2_view out, const b2_dim *bd, int brank,
                         int *ra, int *rb)
 {
-    const char *e = getenv("FFTW3_B200_SPLIT");
-    int mode = e ? atoi(e) : 1;
+    int mode = p->opt.split_mode;
     int64_t rs = (int64_t)real_size(c->prec), sb_in, sb_out;
     if (!mode || brank < 1) return 0;
     if (c->ops.pre_op || c->ops.post_op || c->ops.cache) return 0;
@@ -562,10 +606,9 @@ static int split_wanted(const b2_plan *p, const fft1d_ctx *c, b2_view in, b2_vie
 
 static int emit_split(b2_plan *p, const fft1d_ctx *c, b2_view in, b2_view out, const b2_dim *bd, int brank, int ra, int rb)
 {
-    const char *eg = getenv("FFTW3_B200_SPLIT_MB"), *el = getenv("FFTW3_B200_SPLIT_LANES");
     int64_t n = c->n, esz = 2 * (int64_t)real_size(c->prec);
-    int64_t gbytes = (int64_t)(eg ? atol(eg) : 16) << 20;
-    int nlanes = el ? atoi(el) : 3;
+    int64_t gbytes = (int64_t)p->opt.split_bytes;
+    int nlanes = p->opt.split_lanes;
     int64_t pmax = gbytes / (n * esz), nc0 = bd[0].n, nb1 = brank >= 2 ? bd[1].n : 1, n2 = brank >= 3 ? bd[2].n : 1;
     int64_t cstep, bstep, i2, b0, c0, gi = 0;
     const void *tw = plan_table(p, c->prec, TAB_TWIDDLE, n, 0);
@@ -822,12 +865,16 @@ static int emit_fft1d(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
 {
     b2_tensor batch = *batch_in;
     fft1d_ctx c;
+    int s0 = p->nsteps, rc;
     if (batch.rnk == B2_RNK_MINFTY) return 0;
     b2_tensor_drop_unit(&batch);
     b2_tensor_sort_merge(&batch);
     if (b2_tensor_count(&batch) == 0) return 0;
     c.prec = prec; c.n = n; c.in = in; c.out = out; c.ops = ops; c.scratch_slot = scratch_slot; c.note = note;
-    return for_outer_dims(p, &batch, fft1d_inner, &c);
+    rc = for_outer_dims(p, &batch, fft1d_inner, &c);
+    /* a pass reads what the previous pass wrote, possibly through several lanes: join them first */
+    if (!rc && p->nsteps > s0 && !p->no_fence) p->steps[s0].fence = 1;
+    return rc;
 }
 
 /* every b2_ref offset, user buffer or scratch, is in units of the real scalar type */
@@ -1004,10 +1051,9 @@ static int plan_c2c(b2_plan *p)
         int done[B2_MAXRANK];
         int i, last = q->sz.rnk - 1;
         for (i = 0; i < B2_MAXRANK; ++i) done[i] = 0;
-        if (q->sz.rnk >= 2 && p->l2_block_bytes > 0) {
-            const char *em = getenv("FFTW3_B200_L2_PAIR"), *el = getenv("FFTW3_B200_L2_LANES"), *ek = getenv("FFTW3_B200_L2_KEEP");
-            int pair = (em && !strcmp(em, "outer") && q->sz.rnk >= 3) ? 0 : last - 1;
-            int nlanes = el ? atoi(el) : 3, keep = ek ? atoi(ek) : 2;
+        if (q->sz.rnk >= 2 && p->opt.l2_block_bytes > 0) {
+            int pair = (p->opt.l2_pair_outer && q->sz.rnk >= 3) ? 0 : last - 1;
+            int nlanes = p->opt.l2_lanes, keep = p->opt.l2_keep;
             int oi = -1, ovec = 0;
             int64_t best = 0, per = 2 * (int64_t)real_size(q->prec), nout, G;
             if (nlanes < 0) nlanes = 0;
@@ -1022,12 +1068,13 @@ static int plan_c2c(b2_plan *p)
                 for (i = 0; i < q->sz.rnk; ++i) if (ovec || i != oi) per *= q->sz.d[i].n;
                 for (i = 0; i < q->vecsz.rnk; ++i) if (!ovec || i != oi) per *= q->vecsz.d[i].n;
                 if (!p->inplace) per *= 2;
-                G = (int64_t)p->l2_block_bytes / (per > 0 ? per : 1);
+                G = (int64_t)p->opt.l2_block_bytes / (per > 0 ? per : 1);
                 if (G >= 1 && G < nout && nout / G <= 8192) {
                     int64_t g0, gi = 0;
                     for (g0 = 0; g0 < nout; g0 += G, ++gi) {
                         int64_t cnt = (nout - g0 < G) ? nout - g0 : G;
                         int pass, s0 = p->nsteps;
+                        p->no_fence = gi > 0;      /* groups are independent of each other */
                         for (pass = 0; pass < 2; ++pass) {
                             b2_problem qq = *q;
                             b2_tensor batch;
@@ -1048,6 +1095,7 @@ static int plan_c2c(b2_plan *p)
                             none.cache = 0;
                             if (rc) return rc;
                         }
+                        p->no_fence = 0;
                         if (nlanes > 0) for (i = s0; i < p->nsteps; ++i) p->steps[i].lane = 1 + (int)(gi % nlanes);
                     }
                     first = 0;
@@ -1484,16 +1532,109 @@ void b2_plan_destroy(b2_plan *p)
     b2_planner_unlock();
 }
 
+static b2_plan *build_plan(const b2_problem *prob, const b2_plan_opts *opt, int alt);
+
+/* time a built plan on the user's own arrays (they are overwritten, as with the reference's measuring
+   planner: kernel/timer.c:148-149, doc/reference.texi:405-416): one warm-up, then the minimum of `reps` runs */
+static double time_plan(b2_plan *pl, int reps)
+{
+    const b2_problem *q = &pl->prob;
+    float ms = 0, best = 1e30f;
+    int r;
+    b2_execute_ex(pl, q->in0, q->in1, q->out0, q->out1, 1);
+    if (b2d_sync()) return -1;
+    for (r = 0; r < reps; ++r) {
+        if (b2d_timer_start()) return -1;
+        b2_execute_ex(pl, q->in0, q->in1, q->out0, q->out1, 1);
+        if (b2d_timer_stop(&ms)) return -1;
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+/* Whole-plan alternatives (the role of the reference planner's search over solver trees,
+   kernel/planner.c:518-615): for multi-dimensional complex transforms that are much larger than L2, the
+   plain plan (one HBM pass per dimension) competes with L2-resident pass pairs and with register-only
+   sub-pass pairs.  FFTW_MEASURE builds each alternative, times it on the user's arrays and keeps the
+   fastest; the choice is wisdom under the problem's signature, so FFTW_ESTIMATE / WISDOM_ONLY plans of
+   the same problem reuse it. */
+static int plan_alternatives(const b2_problem *prob, const b2_plan_opts *base, b2_plan_opts *alts, int max)
+{
+    int n = 0, i;
+    int64_t bytes = 2 * (int64_t)real_size(prob->prec);
+    alts[n++] = *base;
+    if (prob->kind != B2_C2C || prob->sz.rnk < 2 || opts_pinned_by_env()) return n;
+    for (i = 0; i < prob->sz.rnk; ++i) bytes *= prob->sz.d[i].n;
+    for (i = 0; i < prob->vecsz.rnk; ++i) bytes *= prob->vecsz.d[i].n > 0 ? prob->vecsz.d[i].n : 1;
+    {
+        const char *e = getenv("FFTW3_B200_ALT_MIN_KB");      /* tests: let small problems have alternatives */
+        if (bytes < (e ? (int64_t)atol(e) << 10 : (int64_t)512 << 20)) return n;   /* arrays that (nearly) fit L2 gain nothing */
+    }
+    {
+        /* group sizes relative to the array so that the same code paths run on the tests' small problems */
+        size_t g32 = (size_t)32 << 20, g16 = (size_t)16 << 20;
+        while ((int64_t)g32 * 8 > bytes && g32 > 4096) { g32 >>= 1; g16 >>= 1; }
+        if (n < max) { alts[n] = *base; alts[n].l2_block_bytes = g32; alts[n].l2_lanes = 2; alts[n].l2_keep = 4; ++n; }
+        if (n < max) { alts[n] = *base; alts[n].l2_block_bytes = g16; alts[n].l2_lanes = 4; alts[n].l2_keep = 4; ++n; }
+    }
+    if (n < max && (prob->flags & (B2F_PATIENT | B2F_EXHAUSTIVE))) {
+        alts[n] = *base; alts[n].split_mode = 1; alts[n].split_bytes = (size_t)16 << 20; alts[n].split_lanes = 3; ++n;
+    }
+    return n;
+}
+
 static b2_plan *mkplan_locked(const b2_problem *prob)
+{
+    b2_plan_opts base, alts[6];
+    b2_plan *best = NULL;
+    int nalt, a, chosen = 0, have = 0, inplace = (prob->in0 == prob->out0);
+    unsigned pat = patience_of(prob->flags);
+    b2_sig sig;
+    double bestt = 1e30;
+    if (!tensor_valid(&prob->sz, 0) || !tensor_valid(&prob->vecsz, 1)) return NULL;
+    g_plan_t0 = now_seconds();
+    opts_from_env(&base);
+    nalt = plan_alternatives(prob, &base, alts, 6);
+    if (nalt == 1) return build_plan(prob, &alts[0], 0);
+    sig = b2_sig_of_problem(prob, inplace);
+    b2_wisdom_set_prec(prob->prec);
+    if (b2_wisdom_lookup(sig, pat, &chosen) && chosen >= 0 && chosen < nalt) have = 1;
+    /* no wisdom for the decomposition is not a reason to fail a WISDOM_ONLY plan: the plain plan's passes
+       decide that (api/apiplan.c:102-107 asks for wisdom of the problem, which its passes carry) */
+    if (!have && (pat == 0 || (prob->flags & B2F_WISDOM_ONLY) || b2d_pointer_is_device(prob->in0 ? prob->in0 : prob->out0) != 1))
+        return build_plan(prob, &alts[0], 0);
+    if (have) {
+        best = build_plan(prob, &alts[chosen], chosen);
+        return best ? best : build_plan(prob, &alts[0], 0);
+    }
+    for (a = 0; a < nalt; ++a) {
+        b2_plan *pl;
+        double t;
+        if (a > 0 && time_is_up()) break;
+        pl = build_plan(prob, &alts[a], a);
+        if (!pl) continue;
+        t = pl->is_nop ? 0.0 : time_plan(pl, 3);
+        if (getenv("FFTW3_B200_VERBOSE"))
+            fprintf(stderr, "[b200 planner] whole-plan alternative %d (l2 %zu MiB x %d lanes, split %d): %d steps, %.3f ms\n", a,
+                    alts[a].l2_block_bytes >> 20, alts[a].l2_lanes, alts[a].split_mode, pl->nsteps, t);
+        if (t >= 0 && t < bestt) { if (best) plan_destroy_locked(best); best = pl; bestt = t; chosen = a; }
+        else plan_destroy_locked(pl);
+    }
+    if (best) { best->cost = bestt; b2_wisdom_store(sig, pat, chosen); }
+    return best;
+}
+
+static b2_plan *build_plan(const b2_problem *prob, const b2_plan_opts *opt, int alt)
 {
     b2_plan *p;
     int rc = 0, i;
-    if (!tensor_valid(&prob->sz, 0) || !tensor_valid(&prob->vecsz, 1)) return NULL;
     if (b2d_device_count() <= 0) return NULL;      /* no GPU, no plan: there is no CPU fallback */
     p = (b2_plan *)calloc(1, sizeof *p);
     if (!p) return NULL;
     p->refcnt = 1;
     p->prob = *prob;
+    p->opt = *opt;
+    p->alt = alt;
     b2_plan_lock_init(p);
     b2_wisdom_set_prec(prob->prec);
     b2_tensor_drop_unit(&p->prob.vecsz);
@@ -1516,12 +1657,6 @@ static b2_plan *mkplan_locked(const b2_problem *prob)
     if (p->prob.sz.rnk + (p->prob.vecsz.rnk > 0 ? p->prob.vecsz.rnk : 0) > B2_MAXRANK) { b2_plan_destroy(p); return NULL; }
     p->inplace = (prob->in0 == prob->out0);
     if (prob->kind == B2_C2C && prob->in0 == prob->out1 && prob->in1 == prob->out0) p->inplace = 0;
-    {
-        const char *e = getenv("FFTW3_B200_L2_BLOCK_MB");
-        const char *ek = getenv("FFTW3_B200_L2_BLOCK_KB");      /* finer unit, for tests */
-        p->l2_block_bytes = (size_t)(e ? atol(e) : B2_DEFAULT_L2_BLOCK_MB) << 20;
-        if (ek) p->l2_block_bytes = (size_t)atol(ek) << 10;
-    }
     if (b2_tensor_count(&p->prob.vecsz) == 0) { p->is_nop = 1; return p; }
     {
         /* In place with different input and output strides (e.g. an in-place transpose
@@ -1603,6 +1738,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
     int i, j;
     if (p->is_nop) { fprintf(f, "(b200-nop)"); return; }
     fprintf(f, "(b200-plan");
+    if (p->opt.l2_block_bytes && p->prob.kind == B2_C2C && p->prob.sz.rnk >= 2)
+        fprintf(f, " [L2-resident pass pairs: %zu KiB groups, %d lanes]", p->opt.l2_block_bytes >> 10, p->opt.l2_lanes);
     for (i = 0; i < p->nsteps; ++i) {
         const b2_step *s = &p->steps[i];
         if (i >= 6 && i < p->nsteps - 3) {

@@ -54,6 +54,22 @@ b2_sig b2_sig_of_pass(const b2d_fft_pass *p, int inplace)
     return s;
 }
 
+/* signature of a whole problem (sizes, strides, kind, in-placeness): keys the measured choice between
+   whole-plan alternatives */
+b2_sig b2_sig_of_problem(const b2_problem *q, int inplace)
+{
+    b2_sig s;
+    int64_t v[8 + 6 * B2_MAXRANK];
+    int k = 0, i;
+    v[k++] = 0x706c616e; v[k++] = q->prec; v[k++] = q->kind; v[k++] = inplace;
+    v[k++] = q->sz.rnk; v[k++] = q->vecsz.rnk;
+    for (i = 0; i < q->sz.rnk; ++i) { v[k++] = q->sz.d[i].n; v[k++] = q->sz.d[i].is; v[k++] = q->sz.d[i].os; }
+    for (i = 0; i < q->vecsz.rnk; ++i) { v[k++] = q->vecsz.d[i].n; v[k++] = q->vecsz.d[i].is; v[k++] = q->vecsz.d[i].os; }
+    s.h[0] = fnv(0xcbf29ce484222325ULL, v, (size_t)k * sizeof(int64_t));
+    s.h[1] = fnv(0x84222325cbf29ce4ULL ^ s.h[0], v, (size_t)k * sizeof(int64_t));
+    return s;
+}
+
 static went *find(b2_sig s)
 {
     went *e;

@@ -36,3 +36,11 @@ def gpu_lib():
     name = lib.device_name()
     assert name, "no CUDA device visible to libfftw3_b200.so"
     return lib
+
+
+@pytest.fixture(scope="session", params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def host_lib(request):
+    """The host-logic suites (API contract checklist, every entry point, guru fuzz) run twice: on the
+    emulated device layer here (`-m "not gpu"`) and on the product library on the B200 (`-m gpu`), where
+    they also exercise shim.cu's dispatch, the specialised kernels, alignment fallbacks and host staging."""
+    return request.getfixturevalue("emu_lib" if request.param == "emu" else "gpu_lib")

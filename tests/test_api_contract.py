@@ -22,117 +22,117 @@ INVERSE = {"R2HC": "HC2R", "HC2R": "R2HC", "DHT": "DHT", "REDFT00": "REDFT00", "
            "RODFT01": "RODFT10", "RODFT11": "RODFT11"}
 
 
-def test_planning_touches_arrays_only_when_measuring(emu_lib):
+def test_planning_touches_arrays_only_when_measuring(host_lib):
     """#2 doc/reference.texi:405-416, kernel/timer.c:148-149: FFTW_ESTIMATE never touches the arrays;
     measuring modes may overwrite them (here: planning runs on scratch, arrays stay intact, which
     the contract allows)."""
     x = np.arange(256, dtype=np.float64).view(np.complex128).copy()
     keep = x.copy()
-    p = emu_lib.fn("d", "plan_dft_1d")(128, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    p = host_lib.fn("d", "plan_dft_1d")(128, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
     assert p and np.array_equal(x, keep)
-    emu_lib.destroy_plan("d", p)
+    host_lib.destroy_plan("d", p)
 
 
 @pytest.mark.parametrize("kind", sorted(LOGICAL))
-def test_unnormalised_roundtrip_scales_by_logical_size(emu_lib, kind):
+def test_unnormalised_roundtrip_scales_by_logical_size(host_lib, kind):
     """#3 doc/reference.texi:432-435,904-911,936-990: kind followed by its inverse kind multiplies by
     the logical size (n, 2(n-1), 2(n+1) or 2n)."""
     n = 12
     rng = np.random.default_rng(1)
     x0 = rng.uniform(-0.5, 0.5, n)
     x, y, z = x0.copy(), np.zeros(n), np.zeros(n)
-    p = emu_lib.plan_many_r2r("d", [n], 1, x.ctypes.data, None, 1, n, y.ctypes.data, None, 1, n, [kind], B.FFTW_ESTIMATE)
-    q = emu_lib.plan_many_r2r("d", [n], 1, y.ctypes.data, None, 1, n, z.ctypes.data, None, 1, n, [INVERSE[kind]],
+    p = host_lib.plan_many_r2r("d", [n], 1, x.ctypes.data, None, 1, n, y.ctypes.data, None, 1, n, [kind], B.FFTW_ESTIMATE)
+    q = host_lib.plan_many_r2r("d", [n], 1, y.ctypes.data, None, 1, n, z.ctypes.data, None, 1, n, [INVERSE[kind]],
                               B.FFTW_ESTIMATE)
     assert p and q
-    emu_lib.execute("d", p)
-    emu_lib.execute("d", q)
-    emu_lib.destroy_plan("d", p)
-    emu_lib.destroy_plan("d", q)
+    host_lib.execute("d", p)
+    host_lib.execute("d", q)
+    host_lib.destroy_plan("d", p)
+    host_lib.destroy_plan("d", q)
     assert np.allclose(z, LOGICAL[kind](n) * x0, rtol=0, atol=1e-12)
 
 
 @pytest.mark.parametrize("n", [8, 9])
-def test_halfcomplex_layout(emu_lib, n):
+def test_halfcomplex_layout(host_lib, n):
     """#4 doc/reference.texi:916-927, rdft/rdft2-rdft.c:42-74: r0 r1 ... r(n/2) i((n+1)/2-1) ... i1"""
     rng = np.random.default_rng(2)
     x = rng.uniform(-0.5, 0.5, n)
     y = np.zeros(n)
-    p = emu_lib.plan_many_r2r("d", [n], 1, x.ctypes.data, None, 1, n, y.ctypes.data, None, 1, n, ["R2HC"], B.FFTW_ESTIMATE)
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    p = host_lib.plan_many_r2r("d", [n], 1, x.ctypes.data, None, 1, n, y.ctypes.data, None, 1, n, ["R2HC"], B.FFTW_ESTIMATE)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     X = np.fft.fft(x)
     want = np.concatenate([X.real[:n // 2 + 1], X.imag[1:(n + 1) // 2][::-1]])
     assert np.allclose(y, want, atol=1e-13)
 
 
-def test_guru_split_is_always_forward_backward_by_pointer_swap(emu_lib):
+def test_guru_split_is_always_forward_backward_by_pointer_swap(host_lib):
     """#11 api/plan-guru-split-dft.h:30-31, kernel/extract-reim.c:27-36: no sign argument; passing
     (ii, ri, io, ro) computes the backward transform."""
     n = 20
     rng = np.random.default_rng(3)
     re, im = rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n)
     ro, io = np.zeros(n), np.zeros(n)
-    p = emu_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], re.ctypes.data, im.ctypes.data, ro.ctypes.data, io.ctypes.data,
+    p = host_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], re.ctypes.data, im.ctypes.data, ro.ctypes.data, io.ctypes.data,
                                     B.FFTW_ESTIMATE)
     assert p
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     assert np.allclose(ro + 1j * io, np.fft.fft(re + 1j * im), atol=1e-13)
-    p = emu_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], im.ctypes.data, re.ctypes.data, io.ctypes.data, ro.ctypes.data,
+    p = host_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], im.ctypes.data, re.ctypes.data, io.ctypes.data, ro.ctypes.data,
                                     B.FFTW_ESTIMATE)
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     assert np.allclose(ro + 1j * io, np.fft.ifft(re + 1j * im) * n, atol=1e-13)
 
 
-def test_malloc_alignment_class(emu_lib):
+def test_malloc_alignment_class(host_lib):
     """#13 kernel/align.c:24-41, tests/fftw-bench.c:230-234: fftw_malloc memory has alignment class 0"""
     for prec in ("d", "f"):
         for size in (8, 1000, 1 << 20):
-            ptr = emu_lib.fn(prec, "malloc")(size)
-            assert ptr and emu_lib.fn(prec, "alignment_of")(ptr) == 0
-            emu_lib.fn(prec, "free")(ptr)
+            ptr = host_lib.fn(prec, "malloc")(size)
+            assert ptr and host_lib.fn(prec, "alignment_of")(ptr) == 0
+            host_lib.fn(prec, "free")(ptr)
 
 
-def test_copy_plan_is_reference_counted(emu_lib):
+def test_copy_plan_is_reference_counted(host_lib):
     """#14 api/apiplan.c:180-210: a copy stays usable after the original is destroyed"""
     x = (np.arange(32) + 0j).astype(np.complex128)
     y = np.zeros_like(x)
-    p = emu_lib.fn("d", "plan_dft_1d")(32, x.ctypes.data, y.ctypes.data, -1, B.FFTW_ESTIMATE)
-    q = emu_lib.fn("d", "copy_plan")(p)
+    p = host_lib.fn("d", "plan_dft_1d")(32, x.ctypes.data, y.ctypes.data, -1, B.FFTW_ESTIMATE)
+    q = host_lib.fn("d", "copy_plan")(p)
     assert q
-    emu_lib.destroy_plan("d", p)
-    emu_lib.execute("d", q)
+    host_lib.destroy_plan("d", p)
+    host_lib.execute("d", q)
     assert np.allclose(y, np.fft.fft(x), atol=1e-12)
-    emu_lib.destroy_plan("d", q)
+    host_lib.destroy_plan("d", q)
 
 
-def test_flops_and_cost_are_reported(emu_lib):
+def test_flops_and_cost_are_reported(host_lib):
     """#15 api/flops.c:23-43: (add, mul, fma) of the plan, estimate_cost = add + mul + 2 fma"""
     x = np.zeros(1000, np.complex128)
-    p = emu_lib.fn("d", "plan_dft_1d")(1000, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
+    p = host_lib.fn("d", "plan_dft_1d")(1000, x.ctypes.data, x.ctypes.data, -1, B.FFTW_ESTIMATE)
     a, m, f = C.c_double(), C.c_double(), C.c_double()
-    emu_lib.fn("d", "flops")(p, C.byref(a), C.byref(m), C.byref(f))
+    host_lib.fn("d", "flops")(p, C.byref(a), C.byref(m), C.byref(f))
     total = a.value + m.value + 2 * f.value
     assert 0.2 * 5 * 1000 * np.log2(1000) < total < 3 * 5 * 1000 * np.log2(1000)
-    emu_lib.fn("d", "estimate_cost").restype = C.c_double
-    emu_lib.fn("d", "cost").restype = C.c_double
-    assert emu_lib.fn("d", "estimate_cost")(p) >= total * 0.999
-    assert emu_lib.fn("d", "cost")(p) >= 0
-    emu_lib.destroy_plan("d", p)
+    host_lib.fn("d", "estimate_cost").restype = C.c_double
+    host_lib.fn("d", "cost").restype = C.c_double
+    assert host_lib.fn("d", "estimate_cost")(p) >= total * 0.999
+    assert host_lib.fn("d", "cost")(p) >= 0
+    host_lib.destroy_plan("d", p)
 
 
-def test_execute_is_reentrant(emu_lib):
+def test_execute_is_reentrant(host_lib):
     """#18 doc/threads.texi:225-270: fftw_execute* may be called concurrently, also on one plan with
     new arrays."""
     n, hm = 256, 6
     rng = np.random.default_rng(4)
     x0 = rng.uniform(-0.5, 0.5, (hm, n)) + 1j * rng.uniform(-0.5, 0.5, (hm, n))
     y0 = np.zeros_like(x0)
-    p = emu_lib.plan_many_dft("d", [n], hm, x0.ctypes.data, None, 1, n, y0.ctypes.data, None, 1, n, -1, B.FFTW_ESTIMATE)
+    p = host_lib.plan_many_dft("d", [n], hm, x0.ctypes.data, None, 1, n, y0.ctypes.data, None, 1, n, -1, B.FFTW_ESTIMATE)
     assert p
-    ex = emu_lib.fn("d", "execute_dft")
+    ex = host_lib.fn("d", "execute_dft")
     ins = [(rng.uniform(-0.5, 0.5, (hm, n)) + 1j * rng.uniform(-0.5, 0.5, (hm, n))) for _ in range(8)]
     outs = [np.zeros_like(a) for a in ins]
     errs = []
@@ -149,13 +149,13 @@ def test_execute_is_reentrant(emu_lib):
         t.start()
     for t in ts:
         t.join()
-    emu_lib.destroy_plan("d", p)
+    host_lib.destroy_plan("d", p)
     assert not errs
     for a, b in zip(ins, outs):
         assert O.rel_l2(b, np.fft.fft(a, axis=1)) < 1e-14
 
 
-def test_c2r_ignores_imag_of_dc_and_nyquist(emu_lib):
+def test_c2r_ignores_imag_of_dc_and_nyquist(host_lib):
     """#19 rdft/rdft2-rdft.c:61-74: the halfcomplex packer never reads imag(DC) / imag(Nyquist)"""
     n = 16
     rng = np.random.default_rng(5)
@@ -165,32 +165,32 @@ def test_c2r_ignores_imag_of_dc_and_nyquist(emu_lib):
     Xd[0] += 3.25j
     Xd[-1] -= 1.5j
     y = np.zeros(n)
-    p = emu_lib.plan_many_dft_c2r("d", [n], 1, Xd.ctypes.data, None, 1, n // 2 + 1, y.ctypes.data, None, 1, n, B.FFTW_ESTIMATE)
+    p = host_lib.plan_many_dft_c2r("d", [n], 1, Xd.ctypes.data, None, 1, n // 2 + 1, y.ctypes.data, None, 1, n, B.FFTW_ESTIMATE)
     assert p
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     assert np.allclose(y, n * x, atol=1e-12)
 
 
-def test_multidimensional_r2r_is_separable(emu_lib):
+def test_multidimensional_r2r_is_separable(host_lib):
     """#20 doc/reference.texi:2353-2400, rdft/rank-geq2.c:135-180: kind[i] applies along dimension i"""
     rng = np.random.default_rng(6)
     x = rng.uniform(-0.5, 0.5, (6, 10))
     y = np.zeros_like(x)
-    p = emu_lib.plan_many_r2r("d", [6, 10], 1, x.ctypes.data, None, 1, 60, y.ctypes.data, None, 1, 60,
+    p = host_lib.plan_many_r2r("d", [6, 10], 1, x.ctypes.data, None, 1, 60, y.ctypes.data, None, 1, 60,
                               ["RODFT10", "REDFT01"], B.FFTW_ESTIMATE)
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     a = np.stack([O.r2r(x[:, j].copy(), ["RODFT10"], rank=1) for j in range(10)], axis=1)
     b = np.stack([O.r2r(a[i].copy(), ["REDFT01"], rank=1) for i in range(6)], axis=0)
     assert O.rel_l2(y, b) < 1e-14
 
 
-def test_planner_entry_points_are_thread_safe(emu_lib):
+def test_planner_entry_points_are_thread_safe(host_lib):
     """#18 doc/threads.texi:225-270, api/apiplan.c:23-29: after fftw_make_planner_thread_safe() plan
     creation / destruction / wisdom calls may come from any thread (here they always serialise on one
     process-wide lock; ThreadSanitizer runs of the same scenario are clean)."""
-    emu_lib.fn("d", "make_planner_thread_safe")()
+    host_lib.fn("d", "make_planner_thread_safe")()
     errs = []
 
     def work(i):
@@ -202,13 +202,13 @@ def test_planner_entry_points_are_thread_safe(emu_lib):
                 y = np.zeros_like(x)
                 flags = B.FFTW_ESTIMATE if it % 2 else B.FFTW_MEASURE
                 x0 = x.copy()
-                p = emu_lib.fn("d", "plan_dft_1d")(n, x.ctypes.data, y.ctypes.data, -1, flags)
+                p = host_lib.fn("d", "plan_dft_1d")(n, x.ctypes.data, y.ctypes.data, -1, flags)
                 assert p
                 x[:] = x0
-                emu_lib.execute("d", p)
+                host_lib.execute("d", p)
                 assert O.rel_l2(y, np.fft.fft(x0)) < 1e-14
-                assert emu_lib.export_wisdom_to_string("d").startswith("(fftw3_b200-")
-                emu_lib.destroy_plan("d", p)
+                assert host_lib.export_wisdom_to_string("d").startswith("(fftw3_b200-")
+                host_lib.destroy_plan("d", p)
         except Exception as e:      # pragma: no cover
             errs.append(repr(e))
 
@@ -221,7 +221,7 @@ def test_planner_entry_points_are_thread_safe(emu_lib):
 
 
 @pytest.mark.parametrize("shape", [(16,), (9,), (6, 10), (5, 4, 7)])
-def test_guru_split_r2c_c2r_and_new_array_execute(emu_lib, shape):
+def test_guru_split_r2c_c2r_and_new_array_execute(host_lib, shape):
     """api/plan-guru-split-dft-r2c.h, plan-guru-split-dft-c2r.h, execute-split-dft-r2c.c, execute-split-dft-c2r.c:
     real <-> split (re, im) half spectrum, planned on one set of arrays and executed on another."""
     rank = len(shape)
@@ -240,36 +240,36 @@ def test_guru_split_r2c_c2r_and_new_array_execute(emu_lib, shape):
     dims = (B.Iodim * rank)(*[B.Iodim(shape[i], rs[i], cs[i]) for i in range(rank)])
     none = (B.Iodim * 1)(B.Iodim(1, 0, 0))
     VP = C.c_void_p
-    p = emu_lib.fn("d", "plan_guru_split_dft_r2c")(rank, C.cast(dims, VP), 0, C.cast(none, VP), x.ctypes.data, ro.ctypes.data,
+    p = host_lib.fn("d", "plan_guru_split_dft_r2c")(rank, C.cast(dims, VP), 0, C.cast(none, VP), x.ctypes.data, ro.ctypes.data,
                                                    io.ctypes.data, B.FFTW_ESTIMATE)
     assert p
     x2 = rng.uniform(-0.5, 0.5, shape)
     ro2, io2 = np.zeros(cshape), np.zeros(cshape)
-    emu_lib.fn("d", "execute_split_dft_r2c")(p, x2.ctypes.data, ro2.ctypes.data, io2.ctypes.data)
-    emu_lib.destroy_plan("d", p)
+    host_lib.fn("d", "execute_split_dft_r2c")(p, x2.ctypes.data, ro2.ctypes.data, io2.ctypes.data)
+    host_lib.destroy_plan("d", p)
     want = np.fft.rfftn(x2)
     assert np.abs(ro2 + 1j * io2 - want).max() < 1e-12
     # back: split half spectrum -> real (input may be destroyed: hand over copies)
     dims = (B.Iodim * rank)(*[B.Iodim(shape[i], cs[i], rs[i]) for i in range(rank)])
     ri, ii, y = want.real.copy(), want.imag.copy(), np.zeros(shape)
-    p = emu_lib.fn("d", "plan_guru_split_dft_c2r")(rank, C.cast(dims, VP), 0, C.cast(none, VP), ri.ctypes.data, ii.ctypes.data,
+    p = host_lib.fn("d", "plan_guru_split_dft_c2r")(rank, C.cast(dims, VP), 0, C.cast(none, VP), ri.ctypes.data, ii.ctypes.data,
                                                    y.ctypes.data, B.FFTW_ESTIMATE)
     assert p
     ri2, ii2, y2 = want.real.copy(), want.imag.copy(), np.zeros(shape)
-    emu_lib.fn("d", "execute_split_dft_c2r")(p, ri2.ctypes.data, ii2.ctypes.data, y2.ctypes.data)
-    emu_lib.destroy_plan("d", p)
+    host_lib.fn("d", "execute_split_dft_c2r")(p, ri2.ctypes.data, ii2.ctypes.data, y2.ctypes.data)
+    host_lib.destroy_plan("d", p)
     assert np.abs(y2 / np.prod(shape) - x2).max() < 1e-12
 
 
-def test_execute_split_dft_on_new_arrays(emu_lib):
+def test_execute_split_dft_on_new_arrays(host_lib):
     """api/execute-split-dft.c:25-29"""
     n = 24
     rng = np.random.default_rng(9)
     a = [np.zeros(n) for _ in range(4)]
-    p = emu_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+    p = host_lib.plan_guru_split_dft("d", [(n, 1, 1)], [], a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
                                     a[3].ctypes.data, B.FFTW_ESTIMATE)
     assert p
     re, im, ro, io = rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n), np.zeros(n), np.zeros(n)
-    emu_lib.fn("d", "execute_split_dft")(p, re.ctypes.data, im.ctypes.data, ro.ctypes.data, io.ctypes.data)
-    emu_lib.destroy_plan("d", p)
+    host_lib.fn("d", "execute_split_dft")(p, re.ctypes.data, im.ctypes.data, ro.ctypes.data, io.ctypes.data)
+    host_lib.destroy_plan("d", p)
     assert np.abs(ro + 1j * io - np.fft.fft(re + 1j * im)).max() < 1e-13

@@ -23,8 +23,8 @@ class Iodim64(C.Structure):
 
 
 @pytest.fixture(scope="module")
-def L(emu_lib):
-    lib = C.CDLL(emu_lib.path if hasattr(emu_lib, "path") else os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
+def L(host_lib):
+    lib = C.CDLL(host_lib.path if hasattr(host_lib, "path") else os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
     return lib
 
 

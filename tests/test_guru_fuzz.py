@@ -35,7 +35,7 @@ def _gather(buf, shape, strides):
 
 
 @pytest.mark.parametrize("seed", range(120))
-def test_random_guru_c2c(emu_lib, seed):
+def test_random_guru_c2c(host_lib, seed):
     rng = np.random.default_rng(1000 + seed)
     rank = int(rng.integers(0, 4))
     hrank = int(rng.integers(0, 3))
@@ -65,23 +65,23 @@ def test_random_guru_c2c(emu_lib, seed):
         ri[iidx], ii[iidx] = x.real, x.imag
         ro, io = (ri, ii) if inplace else (np.full(osz, 9.0), np.full(osz, 9.0))
         if sign < 0:
-            p = emu_lib.plan_guru_split_dft("d", dims, hows, ri.ctypes.data, ii.ctypes.data, ro.ctypes.data, io.ctypes.data,
+            p = host_lib.plan_guru_split_dft("d", dims, hows, ri.ctypes.data, ii.ctypes.data, ro.ctypes.data, io.ctypes.data,
                                             B.FFTW_ESTIMATE)
         else:       # backward = forward with re/im exchanged (api/plan-guru-split-dft.h:30-31)
-            p = emu_lib.plan_guru_split_dft("d", dims, hows, ii.ctypes.data, ri.ctypes.data, io.ctypes.data, ro.ctypes.data,
+            p = host_lib.plan_guru_split_dft("d", dims, hows, ii.ctypes.data, ri.ctypes.data, io.ctypes.data, ro.ctypes.data,
                                             B.FFTW_ESTIMATE)
         assert p, (shape, dims, hows)
-        emu_lib.execute("d", p)
-        emu_lib.destroy_plan("d", p)
+        host_lib.execute("d", p)
+        host_lib.destroy_plan("d", p)
         got = ro[oidx] + 1j * io[oidx]
     else:
         a = np.full(isz, 7 + 7j)
         a[iidx] = x
         b = a if inplace else np.full(osz, 9 + 9j)
-        p = emu_lib.plan_guru_dft("d", dims, hows, a.ctypes.data, b.ctypes.data, sign, B.FFTW_ESTIMATE)
+        p = host_lib.plan_guru_dft("d", dims, hows, a.ctypes.data, b.ctypes.data, sign, B.FFTW_ESTIMATE)
         assert p, (shape, dims, hows)
-        emu_lib.execute("d", p)
-        emu_lib.destroy_plan("d", p)
+        host_lib.execute("d", p)
+        host_lib.destroy_plan("d", p)
         got = b[oidx]
         if not inplace:         # nothing outside the output tensor may be written, and the input is preserved
             mask = np.ones(osz, dtype=bool)
@@ -93,7 +93,7 @@ def test_random_guru_c2c(emu_lib, seed):
 
 
 @pytest.mark.parametrize("seed", range(60))
-def test_random_guru_r2r(emu_lib, seed):
+def test_random_guru_r2r(host_lib, seed):
     """random r2r kinds / strided batches (api/plan-guru-r2r.h), against the oracle"""
     import ctypes as C
     from oracle import oracle as O
@@ -118,11 +118,11 @@ def test_random_guru_r2r(emu_lib, seed):
     dims = (B.Iodim * rank)(*[B.Iodim(shape[i], is_[i], os_[i]) for i in range(rank)])
     hows = (B.Iodim * max(hrank, 1))(*[B.Iodim(shape[rank + i], is_[rank + i], os_[rank + i]) for i in range(hrank)])
     ks = (C.c_int * rank)(*[B.R2R_KINDS[k] for k in kinds])
-    p = emu_lib.fn("d", "plan_guru_r2r")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p), a.ctypes.data,
+    p = host_lib.fn("d", "plan_guru_r2r")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p), a.ctypes.data,
                                          b.ctypes.data, ks, B.FFTW_ESTIMATE)
     assert p, (shape, kinds)
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     want = x
     for ax in range(rank):      # separable: kind[ax] along axis ax
         moved = np.moveaxis(want, ax, -1)
@@ -141,7 +141,7 @@ def test_random_guru_r2r(emu_lib, seed):
 
 
 @pytest.mark.parametrize("seed", range(40))
-def test_random_guru_r2c_c2r(emu_lib, seed):
+def test_random_guru_r2c_c2r(host_lib, seed):
     """random out-of-place r2c and c2r through the guru interface (api/plan-guru-dft-r2c.h,
     plan-guru-dft-c2r.h): real strides in reals, complex strides in complex elements."""
     import ctypes as C
@@ -162,11 +162,11 @@ def test_random_guru_r2c_c2r(emu_lib, seed):
     b = np.full(csz, 9 + 9j)
     dims = (B.Iodim * rank)(*[B.Iodim(shape[i], rs[i], cs[i]) for i in range(rank)])
     hows = (B.Iodim * max(hrank, 1))(*[B.Iodim(shape[rank + i], rs[rank + i], cs[rank + i]) for i in range(hrank)])
-    p = emu_lib.fn("d", "plan_guru_dft_r2c")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p),
+    p = host_lib.fn("d", "plan_guru_dft_r2c")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p),
                                              a.ctypes.data, b.ctypes.data, B.FFTW_ESTIMATE)
     assert p, (shape, rank, hrank)
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     want = np.fft.rfftn(x, axes=tuple(range(rank)))
     scale = max(1.0, float(np.abs(want).max()))
     assert np.abs(b[cidx] - want).max() <= 1e-12 * scale, (seed, "r2c", shape, rank, hrank)
@@ -180,17 +180,17 @@ def test_random_guru_r2c_c2r(emu_lib, seed):
     back = np.full(rsz, 5.0)
     dims = (B.Iodim * rank)(*[B.Iodim(shape[i], cs[i], rs[i]) for i in range(rank)])
     hows = (B.Iodim * max(hrank, 1))(*[B.Iodim(shape[rank + i], cs[rank + i], rs[rank + i]) for i in range(hrank)])
-    p = emu_lib.fn("d", "plan_guru_dft_c2r")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p),
+    p = host_lib.fn("d", "plan_guru_dft_c2r")(rank, C.cast(dims, C.c_void_p), hrank, C.cast(hows, C.c_void_p),
                                              spec.ctypes.data, back.ctypes.data, B.FFTW_ESTIMATE)
     assert p, (shape, rank, hrank, "c2r")
-    emu_lib.execute("d", p)
-    emu_lib.destroy_plan("d", p)
+    host_lib.execute("d", p)
+    host_lib.destroy_plan("d", p)
     n = float(np.prod(shape[:rank]))
     assert np.abs(back[ridx] / n - x).max() <= 1e-12, (seed, "c2r", shape, rank, hrank)
 
 
 @pytest.mark.parametrize("seed", range(40))
-def test_random_guru_c2c_single_precision(emu_lib, seed):
+def test_random_guru_c2c_single_precision(host_lib, seed):
     """the same random strided problems in single precision (fftwf_ entry points)"""
     rng = np.random.default_rng(3000 + seed)
     rank = int(rng.integers(1, 4))
@@ -214,10 +214,10 @@ def test_random_guru_c2c_single_precision(emu_lib, seed):
     a = np.full(isz, 7 + 7j, dtype=np.complex64)
     a[iidx] = x
     b = a if inplace else np.full(osz, 9 + 9j, dtype=np.complex64)
-    p = emu_lib.plan_guru_dft("f", dims, hows, a.ctypes.data, b.ctypes.data, sign, B.FFTW_ESTIMATE)
+    p = host_lib.plan_guru_dft("f", dims, hows, a.ctypes.data, b.ctypes.data, sign, B.FFTW_ESTIMATE)
     assert p, (shape, dims, hows)
-    emu_lib.execute("f", p)
-    emu_lib.destroy_plan("f", p)
+    host_lib.execute("f", p)
+    host_lib.destroy_plan("f", p)
     got = b[oidx].astype(np.complex128)
     n = max(2.0, float(np.prod(shape[:rank])))
     assert np.linalg.norm(got - want) <= 4 * 1.2e-7 * np.log2(n) * max(np.linalg.norm(want), 1e-30), (seed, shape, rank, hrank)
