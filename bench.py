@@ -283,7 +283,8 @@ def run_ours(args):
     plan_txt = lib.sprint_plan("d", plan)
     if args.wisdom:
         lib.fn("d", "export_wisdom_to_filename")(args.wisdom.encode())
-    # data for the timed runs (planning may have scribbled on nothing: it times on scratch)
+    # FFTW_MEASURE overwrites the arrays while planning (doc/reference.texi:405-416): fresh data for the timed runs
+    ar.copy_(torch.rand(ar.shape, dtype=torch.float64, device=dev, generator=g) - 0.5)
     lib.lib.fftw_b200_set_async(1)
     for _ in range(max(3, args.warmup)):
         lib.execute("d", plan)
@@ -306,19 +307,53 @@ def run_ours(args):
     gflops = flops_c2c(shape) / (ms * 1e-3) / 1e9
     lib.lib.fftw_b200_set_async(0)
 
-    # roofline: every pass reads and writes the whole array once
+    # ---- roofline.  Algorithmic bytes of one HBM pass = one read + one write of the array (DESIGN.md
+    # section 3: 32 B per point per pass in f64).  The dominant kernel is the pass along dim 0 (stride
+    # 16 MiB); it and the two other passes are timed alone, live, through single-dimension guru plans of
+    # the same array (same kernels and variants: their pass signatures hit the wisdom just measured).
     array_bytes = 16 * n ** 3
-    passes = launches // args.steps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = passes * 2 * array_bytes / (ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "passes": passes, "algorithmic_bytes_per_launch": 2 * array_bytes,
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)"}
+    strides = [n * n, n, 1]
+    per_pass = []
+    for d in range(3):
+        dims = [(n, strides[d], strides[d])]
+        hm = [(n, strides[e], strides[e]) for e in range(3) if e != d]
+        sp = lib.plan_guru_dft("d", dims, hm, a.data_ptr(), a.data_ptr(), B.FFTW_FORWARD, flags)
+        assert sp
+        for _ in range(2):
+            lib.execute("d", sp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            lib.execute("d", sp)
+        e1.record()
+        torch.cuda.synchronize()
+        pms = e0.elapsed_time(e1) / 5
+        txt = " ".join(lib.sprint_plan("d", sp).split())
+        lib.destroy_plan("d", sp)
+        ar.mul_(1e-6)
+        per_pass.append({"dim": d, "ms": pms, "achieved_gbs": 2 * array_bytes / (pms * 1e-3) / 1e9,
+                         "frac": 2 * array_bytes / (pms * 1e-3) / 1e9 / peak, "kernel": txt[:200]})
+    dom = max(per_pass, key=lambda q: q["ms"])
+    l2_paired = "L2-resident pass pairs" in plan_txt
+    hbm_passes = 2 if l2_paired else 3          # a pair of passes that meets in L2 costs one read + one write
+    step_gbs = hbm_passes * 2 * array_bytes / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "kernel": "pass along dim %d (the slowest of the three), timed alone: %.3f ms" % (dom["dim"], dom["ms"]),
+                "algorithmic_bytes_per_launch": 2 * array_bytes,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                "per_pass_alone": per_pass,
+                "step": {"hbm_pass_equivalents": hbm_passes, "algorithmic_bytes": hbm_passes * 2 * array_bytes,
+                         "achieved": step_gbs, "frac": step_gbs / peak,
+                         "as_three_passes_frac": 3 * 2 * array_bytes / (ms * 1e-3) / 1e9 / peak,
+                         "note": ("dims 2 and 1 run as L2-resident pairs per plane group: 2 HBM pass-equivalents"
+                                  if l2_paired else "one HBM pass per dimension")}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:

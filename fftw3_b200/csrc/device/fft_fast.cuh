@@ -208,13 +208,23 @@ struct FastCfg {
     static_assert(TPX % E == 0 || R2 == 1, "stage-2 twiddle index must be thread-constant");
 };
 
-template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
-__global__ void __launch_bounds__(FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::MINB)
-fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
+// smem-staged real line (FLAVOR 9 ROW: the tile's lines are brought in with coalesced loads first)
+template <typename T>
+struct SmemLineIn {
+    const T *p;
+    __device__ __forceinline__ T operator()(int j) const { return p[j]; }
+};
+
+// KIND >= 0: the r2r kind is a compile-time constant (the PRE / POST switches fold away: the runtime-kind
+// kernel is 13.9k SASS instructions and instruction-cache bound, profiles/r01_ncu_full_r2r4096_summary.txt).
+// one tile (CTA-sized unit of work) of the pass; `block` is its index in the grid of tiles
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR, int KIND>
+__device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, int swap_out, int64_t block,
+                                          unsigned char *smem_raw)
 {
     using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>;
+    const int r2r_kind = KIND >= 0 ? KIND : p.r2r_kind;
     constexpr int TPX = Cfg::TPX;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx<T> *sm = reinterpret_cast<cplx<T> *>(smem_raw);
 
     const int tid = threadIdx.x;
@@ -222,7 +232,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     const int j = COL ? (tid / TPB) : (tid % TPX);
     auto sidx = [&](int k) -> int { return COL ? (k * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
 
-    const b2::TileCtx c = b2::decode_block(p, (int64_t)blockIdx.x);
+    const b2::TileCtx c = b2::decode_block(p, block);
     const int64_t b0 = c.tile0 * TPB + t;
     const bool valid = b0 < p.bn[0];
     const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
@@ -263,7 +273,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
             if (valid) {
                 b2::RealLineOut<T> y = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
                 cplx<T> v; v.x = vr; v.y = vi;
-                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, kout, v, reinterpret_cast<const cplx<T> *>(p.aux0), y);
+                b2::r2r_post_scatter<T>(r2r_kind, p.n_out, kout, v, reinterpret_cast<const cplx<T> *>(p.aux0), y);
             }
             return;
         }
@@ -325,8 +335,8 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
                 const int k = j + r * TPX;
                 cplx<T> u, v;
                 b2::r2r_unpack_pair<T>(sm[sidx(k)], sm[sidx(k ? N - k : 0)], u, v);
-                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, u, qt, ya);
-                b2::r2r_post_scatter<T>(p.r2r_kind, p.n_out, k, v, qt, yb);
+                b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, u, qt, ya);
+                b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, v, qt, yb);
             }
             return;
         }
@@ -346,17 +356,43 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     };
 
     T re[E], im[E];
+    // FLAVOR 9, ROW: the PRE maps gather with strides 2 / -2 (types 2, 3) or mirrored (types 1, HC2R): bring
+    // the tile's real lines into shared memory with coalesced loads first (the raw lines alias the exchange
+    // buffer: n_in reals per line <= N complex per transform), then gather from there
+    T *raw = reinterpret_cast<T *>(sm);
+    if (FLAVOR == 9 && !COL) {
+        const int nl = p.r2r_pair ? 2 : 1, nin = p.n_in;
+        for (int idx = tid; idx < TPB * nl * nin; idx += Cfg::THREADS) {
+            const int tt = idx / (nl * nin), rem = idx - tt * (nl * nin);
+            const int ln = rem / nin, e = rem - ln * nin;
+            const int64_t bb = c.tile0 * TPB + tt;
+            if (bb < p.bn[0])
+                raw[idx] = __ldcs(reinterpret_cast<const T *>(p.in_re) + bb * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2] +
+                                  (ln ? p.pair_is : 0) + e);
+        }
+        __syncthreads();
+    }
     // ---- stage 1: radix E straight from HBM (butterfly index b = j, Ns = 1)
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = T(0); v.y = T(0);
-        if (FLAVOR == 9) {
+        if (FLAVOR == 9 && !COL) {
+            if (valid) {
+                const int nl = p.r2r_pair ? 2 : 1;
+                SmemLineIn<T> x = { raw + (t * nl) * p.n_in };
+                v = b2::r2r_pre_value<T>(r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x);
+                if (p.r2r_pair) {
+                    SmemLineIn<T> x2 = { raw + (t * nl + 1) * p.n_in };
+                    v.y = b2::r2r_pre_value<T>(r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x2).x;
+                }
+            }
+        } else if (FLAVOR == 9) {
             if (valid) {
                 b2::RealLineIn<T> x = { reinterpret_cast<const T *>(p.in_re) + boff_in, p.is };
-                v = b2::r2r_pre_value<T>(p.r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x);
+                v = b2::r2r_pre_value<T>(r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x);
                 if (p.r2r_pair) {
                     b2::RealLineIn<T> x2 = { reinterpret_cast<const T *>(p.in_re) + boff_in + p.pair_is, p.is };
-                    v.y = b2::r2r_pre_value<T>(p.r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x2).x;
+                    v.y = b2::r2r_pre_value<T>(r2r_kind, p.n_in, j + r * TPX, reinterpret_cast<const cplx<T> *>(p.aux0), x2).x;
                 }
             }
         } else if (FLAVOR == 7) {
@@ -395,6 +431,7 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
         for (int r = 0; r < E; ++r) { re[r] = bre[FLAVOR == 7 ? r : 0]; im[r] = bim[FLAVOR == 7 ? r : 0]; }
     }
     Butterfly<E, T>::run(re, im);
+    if (FLAVOR == 9 && !COL) __syncthreads();      // every thread has gathered its inputs from the raw lines
 #pragma unroll
     for (int r = 0; r < E; ++r) {
         cplx<T> v; v.x = re[r]; v.y = im[r];
@@ -490,26 +527,55 @@ fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out)
     }   // rep
 }
 
+// KIND >= 0: the r2r kind is a compile-time constant.  grid_limit > 0 (multi-GPU passes that are bound by
+// NVLink, not by the SMs): the grid is smaller than the number of tiles and every CTA loops over tiles,
+// so that the pass leaves SMs free for an HBM-bound pass running next to it on another stream.
+// (PERSIST is its own instantiation: the tile loop costs the one-tile kernels 25 registers, i.e. a resident CTA.)
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR, int KIND = -1, bool PERSIST = false>
+__global__ void __launch_bounds__(FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::MINB)
+fast_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_out, long long ntiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (!PERSIST) {
+        fast_tile<T, N, E, R1, R2, TPB, COL, FLAVOR, KIND>(p, swap_in, swap_out, (int64_t)blockIdx.x, smem_raw);
+        return;
+    }
+    long long tile = blockIdx.x;
+    for (;;) {
+        fast_tile<T, N, E, R1, R2, TPB, COL, FLAVOR, KIND>(p, swap_in, swap_out, (int64_t)tile, smem_raw);
+        tile += gridDim.x;
+        if (tile >= ntiles) break;
+        __syncthreads();          // the next tile reuses the exchange buffer
+    }
+}
+
 // ------------------------------------------------------------------ registry
 struct FastEntry {
     int prec, n, col, tpb, code;
+    int r2r_kind;            // flavour 9: the kind this instantiation is specialised for, -1 = any (runtime switch)
+    int persist;             // 1: CTAs loop over the tiles (launched with a grid smaller than the tile count)
     size_t smem;
     int threads;
-    void (*launch)(const b2d_fft_pass &, int, int, unsigned, cudaStream_t);
+    void (*launch)(const b2d_fft_pass &, int, int, unsigned, long long, cudaStream_t);
     const void *func;
 };
 
-template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR>
-void launch_one(const b2d_fft_pass &p, int swap_in, int swap_out, unsigned blocks, cudaStream_t st)
+template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVOR, int KIND, bool PERSIST>
+void launch_one(const b2d_fft_pass &p, int swap_in, int swap_out, unsigned blocks, long long ntiles, cudaStream_t st)
 {
     using Cfg = FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>;
-    fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR><<<blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, swap_in, swap_out);
+    fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR, KIND, PERSIST><<<blocks, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p, swap_in, swap_out, ntiles);
 }
 
+#define B2_FAST_ENTRY_KP(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE, KIND, PERSIST)                      \
+    { PREC, N, COL, TPB, CODE, KIND, PERSIST, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::SMEM_BYTES,       \
+      FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS,                                                  \
+      &launch_one<T, N, E, R1, R2, TPB, COL, FLAVOR, KIND, (PERSIST != 0)>,                                 \
+      (const void *)&fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR, KIND, (PERSIST != 0)> }
+#define B2_FAST_ENTRY_K(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE, KIND)                                \
+    B2_FAST_ENTRY_KP(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE, KIND, 0)
 #define B2_FAST_ENTRY(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE)                                        \
-    { PREC, N, COL, TPB, CODE, FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::SMEM_BYTES,                      \
-      FastCfg<T, N, E, R1, R2, TPB, COL, FLAVOR>::THREADS, &launch_one<T, N, E, R1, R2, TPB, COL, FLAVOR>,          \
-      (const void *)&fast_kernel<T, N, E, R1, R2, TPB, COL, FLAVOR> }
+    B2_FAST_ENTRY_KP(PREC, T, N, E, R1, R2, TPB, COL, FLAVOR, CODE, -1, 0)
 
 const FastEntry *table(int *count);   // defined in fft_fast_table.cu
 

@@ -11,15 +11,18 @@ extern const int table_d_row_count, table_d_col_count, table_f_row_count, table_
 static int g_max_smem = 0;
 static int g_sms = 148;
 
-static const FastEntry *find(int prec, int n, int col, int code)
+static const FastEntry *find(int prec, int n, int col, int code, int kind = -1, int persist = 0)
 {
-    const FastEntry *t;
+    const FastEntry *t, *any = nullptr;
     int cnt, i;
     if (prec == B2D_F64) { t = col ? table_d_col : table_d_row; cnt = col ? table_d_col_count : table_d_row_count; }
     else { t = col ? table_f_col : table_f_row; cnt = col ? table_f_col_count : table_f_row_count; }
     for (i = 0; i < cnt; ++i)
-        if (t[i].n == n && t[i].code == code) return &t[i];
-    return nullptr;
+        if (t[i].n == n && t[i].code == code && t[i].persist == persist) {
+            if (t[i].r2r_kind == kind) return &t[i];          // specialised for this kind (or the plain entry)
+            if (t[i].r2r_kind < 0) any = &t[i];
+        }
+    return any;
 }
 
 void init(int max_smem)
@@ -54,7 +57,7 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
         const int64_t unit = p.r2r_pair ? 2 : 1;          // paired lines: batch dim 0 steps over two adjacent reals
         if (col ? (p.bis[0] != unit || p.bos[0] != unit || (p.r2r_pair && (p.pair_is != 1 || p.pair_os != 1)))
                 : (p.is != 1 || p.os != 1)) return nullptr;
-        const FastEntry *e9 = find(p.prec, p.n, col, p.kernel);
+        const FastEntry *e9 = find(p.prec, p.n, col, p.kernel, p.r2r_kind);
         if (e9 && (int)e9->smem > g_max_smem && g_max_smem) return nullptr;
         return e9;
     }
@@ -121,7 +124,13 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     if (blocks > 2147483647LL) return -1;
     b2d_fft_pass q = p;
     q.tpb = e->tpb;                  // decode_block() uses the tile width
-    e->launch(q, swap_in, swap_out, (unsigned)blocks, st);
+    int64_t grid = blocks;
+    if (p.grid_limit > 0 && grid > p.grid_limit) {
+        // an instantiation whose CTAs loop over the tiles, when the table has one for this kernel
+        const FastEntry *pe = find(p.prec, p.n, p.kernel >= 1000, p.kernel, -1, 1);
+        if (pe && pe->tpb == e->tpb) { e = pe; grid = p.grid_limit; }
+    }
+    e->launch(q, swap_in, swap_out, (unsigned)grid, (long long)blocks, st);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

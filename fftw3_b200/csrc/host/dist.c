@@ -41,6 +41,8 @@ struct fftw_b200_dist_plan_s {
     b2_plan **z;             /* [c1] */
     b2_plan **g;             /* [c1 * nranks] */
     int real_gather;         /* r2r plan: x[] = stage-1 gathers (before z), g[] = stage-2 gathers */
+    int zcopy;               /* real-data plans whose dim-0 pass cannot split its stores by row (Bluestein / Rader /
+                                multi-pass n0): z[] transforms in place, g[s] then copies the rows to their owner s */
     b2_plan *pre, *post;     /* real-data plans: local r2c rows before stage 0 / local c2r rows as the last stage */
 };
 typedef struct fftw_b200_dist_plan_s *dplan;
@@ -102,12 +104,11 @@ void fftw_b200_dist_destroy_plan(dplan p)
 static int comm_ctas(void)
 {
     const char *e = getenv("FFTW3_B200_DIST_COMM_CTAS");
-    int sms = b2d_sm_count();
-    (void)sms;
-    /* measured on B200: restricting the scatter/gather kernels to a CTA budget made
-       them slower than the overlap gained; the default is no limit.  Only copy kernels are
-       grid-stride and honour the limit. */
-    return e ? atoi(e) : 0;
+    /* An NVLink-bound pass needs few CTAs to keep the links busy; launched with a full grid its CTAs would
+       sit on every SM waiting for remote stores and starve the HBM-bound pass that runs next to it.  Both
+       the copy kernels (grid-stride) and the specialised FFT kernels (persistent twins, fft_fast.cuh)
+       honour the limit.  Default: two CTAs per SM. */
+    return e ? atoi(e) : 2 * b2d_sm_count();
 }
 
 static void limit_grid(b2_plan *pl, int limit)
@@ -116,13 +117,14 @@ static void limit_grid(b2_plan *pl, int limit)
     if (!pl || limit <= 0) return;
     for (i = 0; i < pl->nsteps; ++i) {
         if (pl->steps[i].kind == STEP_COPY) pl->steps[i].u.copy.grid_limit = limit;
+        else if (pl->steps[i].kind == STEP_FFT) pl->steps[i].u.fft.grid_limit = limit;
     }
 }
 
 static int chunks_for(int64_t n)
 {
     const char *e = getenv("FFTW3_B200_DIST_CHUNKS");
-    int c = e ? atoi(e) : 1;      /* chunked overlap is opt-in: it did not pay off with stream concurrency */
+    int c = e ? atoi(e) : 4;      /* stage 0: the HBM-bound Y pass of chunk c + 1 overlaps the NVLink-bound X pass of chunk c */
     if (c < 1) c = 1;
     if (c > 64) c = 64;
     while (c > 1 && n / c < 2) c /= 2;
@@ -332,8 +334,32 @@ static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int 
         set_ptrs(&q, (double *)cplx, (double *)zbuf, sign);       /* zbuf only stands in while planning */
         p->x[0] = b2_mkplan(&q);
         if (!p->x[0]) goto fail;
-        if (p->x[0]->nsteps != 1 || rowsplit(p->x[0], nranks, b1, push_targets, 0, 2 * h)) goto fail;
-        p->x_fused[0] = 1;
+        if (p->x[0]->nsteps == 1 && !rowsplit(p->x[0], nranks, b1, push_targets, 0, 2 * h)) p->x_fused[0] = 1;
+        else {
+            /* n1 whose transform cannot split its stores by row (non-smooth: Bluestein / Rader, or multi-pass):
+               transform in place on the local slab (runs as the "Y" of stage 0), then one strided copy per
+               destination pushes its rows -- the reference's transpose as plain copies into peer memory
+               (mpi/transpose-alltoall.c:49-100 with the all-to-all replaced by peer stores) */
+            int d;
+            b2_plan_destroy(p->x[0]); p->x[0] = NULL;
+            init_problem(&q, flags);
+            dim(&q.sz, n1, 2 * h, 2 * h);
+            dim(&q.vecsz, ln0, 2 * n1 * h, 2 * n1 * h);
+            dim(&q.vecsz, h, 2, 2);
+            set_ptrs(&q, (double *)cplx, (double *)cplx, sign);
+            p->y[0] = b2_mkplan(&q);
+            if (!p->y[0]) goto fail;
+            for (d = 0; d < nranks; ++d) {
+                int64_t l1 = share(n1, nranks, d);
+                if (!l1) continue;
+                init_problem(&q, flags | B2F_ESTIMATE);
+                dim(&q.vecsz, ln0, 2 * n1 * h, 2 * b1 * h);
+                dim(&q.vecsz, l1 * h, 2, 2);
+                set_ptrs(&q, (double *)cplx + 2 * d * b1 * h, (double *)push_targets[d], -1);
+                p->x[d] = b2_mkplan(&q);
+                if (!p->x[d]) goto fail;
+            }
+        }
     }
     if (ln1 > 0) {
         /* c2c along n0 on zbuf = [n0][b1][h] (row pitch b1 = the block size on every rank; this rank fills
@@ -344,8 +370,30 @@ static dplan mkdist_real(int c2r, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int 
         set_ptrs(&q, (double *)zbuf, (double *)zbuf, sign);
         p->z[0] = b2_mkplan(&q);
         if (!p->z[0]) goto fail;
-        if (p->z[0]->nsteps != 1 || p->z[0]->steps[0].u.fft.bn[1] != 1 ||
-            rowsplit(p->z[0], nranks, b0, out_targets, 2 * (b1 * rank) * h, 2 * n1 * h)) goto fail;
+        if (p->z[0]->nsteps != 1 || p->z[0]->steps[0].kind != STEP_FFT || p->z[0]->steps[0].u.fft.bn[1] != 1 ||
+            rowsplit(p->z[0], nranks, b0, out_targets, 2 * (b1 * rank) * h, 2 * n1 * h)) {
+            /* same fallback for n0: in place on zbuf (the plan above, untouched by a failed rowsplit? no --
+               replan it), then copy every owner's rows into its slab */
+            int s2;
+            b2_plan_destroy(p->z[0]);
+            init_problem(&q, flags);
+            dim(&q.sz, n0, 2 * b1 * h, 2 * b1 * h);
+            dim(&q.vecsz, ln1 * h, 2, 2);
+            set_ptrs(&q, (double *)zbuf, (double *)zbuf, sign);
+            p->z[0] = b2_mkplan(&q);
+            if (!p->z[0]) goto fail;
+            p->zcopy = 1;
+            for (s2 = 0; s2 < nranks; ++s2) {
+                int64_t l0 = share(n0, nranks, s2);
+                if (!l0) continue;
+                init_problem(&q, flags | B2F_ESTIMATE);
+                dim(&q.vecsz, l0, 2 * b1 * h, 2 * n1 * h);
+                dim(&q.vecsz, ln1 * h, 2, 2);
+                set_ptrs(&q, (double *)zbuf + 2 * (b0 * s2) * b1 * h, (double *)out_targets[s2] + 2 * (b1 * rank) * h, -1);
+                p->g[s2] = b2_mkplan(&q);
+                if (!p->g[s2]) goto fail;
+            }
+        }
     }
     return p;
 fail:
@@ -487,6 +535,7 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
         if (aux) b2d_pop_stream(prev);
     } else if (stage == 1 && c < p->c1) {
         run(p->z[c]);
+        if (p->zcopy) for (d = 0; d < p->nranks; ++d) run(p->g[(p->rank + 1 + d) % p->nranks]);
     } else if (stage == 2 && c < p->c1) {
         void *aux = b2d_aux_stream(1);
         if (aux) { b2d_stream_wait_stream(aux, mainst); prev = b2d_push_stream(aux); }

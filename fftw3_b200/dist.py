@@ -466,9 +466,77 @@ class SlabPlanR2R3D:
 # --------------------------------------------------------------------------
 # bench.py leg for N > 1 (one rank per GPU, launched by torchrun)
 # --------------------------------------------------------------------------
-def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run):
+def _nvlink_tx_kib(index):
+    """Sum of the NVLink transmit counters of one GPU (`nvidia-smi nvlink -gt d`), KiB; None if unavailable."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    vals = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    return sum(vals) if vals else None
+
+
+def _self_check_slab(lib, n, world, rank, local, plan, flags, exchange, impulse_expected):
+    """Correctness of the distributed plan that was timed, outside the timed region: a unit impulse
+    at a non-trivial global index against the closed-form phases (every rank samples its own output
+    planes), then forward + backward against the input (relative L2 over all ranks)."""
+    import math
+    dev = local.device
+    alloc, ln0, s0, ln1, s1 = local_size_3d(lib, n, n, n, rank, world)
+    nel = ln0 * n * n
+    slab = local[:nel].view(ln0, n, n) if ln0 else None
+    j = (n // 3 + 1, n // 5 + 2, n // 7 + 3)
+    local.zero_()
+    if ln0 and s0 <= j[0] < s0 + ln0:
+        slab[j[0] - s0, j[1], j[2]] = 1.0
+    torch.cuda.synchronize()
+    dist.barrier()
+    plan.execute()
+    torch.cuda.synchronize()
+    dist.barrier()
+    err = torch.zeros(1, dtype=torch.float64, device=dev)
+    if ln0:
+        rng = np.random.default_rng(1000 + rank)
+        ks = np.stack([rng.integers(s0, s0 + ln0, 256), rng.integers(0, n, 256), rng.integers(0, n, 256)], axis=1)
+        kt = torch.from_numpy(ks).to(dev)
+        got = slab[kt[:, 0] - s0, kt[:, 1], kt[:, 2]].cpu().numpy()
+        err[0] = float(np.abs(got - impulse_expected(n, j, ks)).max())
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    imp = float(err.item())
+    # round trip
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    lr = torch.view_as_real(local)
+    lr.copy_(torch.rand(lr.shape, dtype=torch.float64, device=dev, generator=g) - 0.5)
+    keep = local[:nel].clone()
+    back = SlabPlan3D(lib, n, n, n, local, sign=B.FFTW_BACKWARD, flags=flags, transposed_out=False, exchange=exchange)
+    torch.cuda.synchronize()
+    dist.barrier()
+    plan.execute()
+    back.execute()
+    torch.cuda.synchronize()
+    dist.barrier()
+    back.destroy()
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    if ln0:
+        d = torch.view_as_real(local[:nel] * (1.0 / float(n) ** 3) - keep)
+        acc[0] = (d ** 2).sum()
+        acc[1] = (torch.view_as_real(keep) ** 2).sum()
+    dist.all_reduce(acc)
+    rt = float((acc[0] / acc[1]).sqrt().item())
+    lg = 3 * math.log2(n)
+    return {"impulse_max_err": imp, "impulse_at": list(j), "impulse_samples": 256 * world, "roundtrip_rel_l2": rt,
+            "tolerance": {"impulse": 1e-13 * lg, "roundtrip": 3.0 * 2.0 ** -52 * lg},
+            "ok": bool(imp <= 1e-13 * lg and rt <= 3.0 * 2.0 ** -52 * lg)}
+
+
+def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c, cpu_reference_run,
+                  impulse_expected=None):
     import json
     import os
+    import sys
     import time
 
     dev = torch.device("cuda", local_rank)
@@ -507,8 +575,33 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    tx0 = _nvlink_tx_kib(local_rank) if rank == 0 else None
     ms, launches = timed(plan, args.steps, max(3, args.warmup))
+    tx1 = _nvlink_tx_kib(local_rank) if rank == 0 else None
     clocks = sampler.stop() if rank == 0 else None
+
+    # per-stage times of one transform (diagnostic, outside the timed region): stage 0 = Y + X (first
+    # exchange rides on X's stores), stage 1 = Z (second exchange rides on its stores)
+    stage_ms = None
+    if plan.exchange == "peer" and plan.push:
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        acc = [0.0, 0.0]
+        for _ in range(3):
+            torch.cuda.synchronize()
+            dist.barrier()
+            evs[0].record()
+            lib.lib.fftw_b200_dist_execute_stage(plan.plan, 0)
+            plan._barrier()
+            evs[1].record()
+            lib.lib.fftw_b200_dist_execute_stage(plan.plan, 1)
+            plan._barrier()
+            evs[2].record()
+            torch.cuda.synchronize()
+            acc[0] += evs[0].elapsed_time(evs[1]) / 3
+            acc[1] += evs[1].elapsed_time(evs[2]) / 3
+        st = torch.tensor(acc, device=dev)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        stage_ms = [float(v) for v in st.tolist()]
 
     # the same transform with FFTW_MPI_TRANSPOSED_OUT semantics (one exchange instead of two)
     plan_t = SlabPlan3D(lib, n, n, n, local, flags=flags, transposed_out=True, exchange=exchange)
@@ -539,10 +632,14 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                "api": "fftw3_b200.dist.SlabPlan3D.execute on pinned host slabs (one per rank)"}
     lib.lib.fftw_b200_set_async(0)
     pushed = plan.push
+    check = None
+    if impulse_expected is not None and not getattr(args, "no_check", False):
+        check = _self_check_slab(lib, n, world, rank, local, plan, flags, exchange, impulse_expected)
     plan.destroy()
     plan_t.destroy()
     if rank != 0:
         return
+    cpu = None if args.no_cpu else cpu_reference_run(1, 0, sample_n=min(256, n))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -569,7 +666,18 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                      "traffic": None, "passes": passes, "per": "GPU",
                      "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback (of fallback)",
                      "nvlink": {"sent_bytes_per_gpu_per_step": nv_bytes,
-                                "if_serialised_gbs": nv_bytes / (ms * 1e-3) / 1e9, "peak_gbs": 770.0}},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": None,
+                                "if_serialised_gbs": nv_bytes / (ms * 1e-3) / 1e9, "peak_gbs": 900.0,
+                                "counter_tx_bytes_per_step": (None if tx0 is None or tx1 is None else
+                                                              (tx1 - tx0) * 1024.0 / (args.steps + max(3, args.warmup))),
+                                "stage_ms": stage_ms,
+                                "stage_exchange_gbs": (None if not stage_ms else
+                                                       [nv_bytes / 2 / (t * 1e-3) / 1e9 for t in stage_ms]),
+                                "note": "each of the two stages pushes sent_bytes/2 over NVLink inside a pass; "
+                                        "stage_exchange_gbs = that / the stage's time (a lower bound of the link rate "
+                                        "while the store pass runs)"}},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if check is not None and not check["ok"]:
+        sys.exit("bench.py: self check FAILED: %r" % (check,))

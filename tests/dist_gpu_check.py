@@ -66,7 +66,8 @@ def main():
                     print("dist check %s P=%d %-11s transposed=%d push=%d rel L2 %.2e %s"
                           % (shape, world, exchange, transposed, pushed, err, "OK" if good else "FAIL"), flush=True)
     # real data: r2c then c2r (round trip) of padded slabs, even and uneven column blocks
-    for shape in [(64, 16 * world, 50), (24, 8 * world, 33), (30, 7 * world + 1, 25), (128, 128, 128)]:
+    # (30, 17, 25) and (19, 34, 20): uneven blocks AND a non-smooth distributed dimension (copy fallback of dist.c)
+    for shape in [(64, 16 * world, 50), (24, 8 * world, 33), (30, 7 * world + 1, 25), (30, 17, 25), (19, 34, 20), (128, 128, 128)]:
         n0, n1, n2 = shape
         h = n2 // 2 + 1
         rng = np.random.default_rng(7)

@@ -157,6 +157,9 @@ def _run_real(lib, shape, P, inplace):
     ((6, 5, 4), 4),         # column blocks (2, 2, 1, 0) and the last rank owns no planes
     ((6, 8, 16), 4),        # block 2: the last rank owns no planes
     ((5, 3, 8), 1),
+    ((6, 17, 10), 2),       # non-smooth n1 (Rader / Bluestein pass cannot split its stores by row): copy fallback
+    ((19, 12, 6), 3),       # non-smooth n0: the same fallback on the second exchange
+    ((17, 19, 5), 2),       # both
 ])
 def test_real_data_plans_all_ranks_in_one_process(emu_lib, shape, P, inplace):
     """Distributed r2c / c2r (mpi/api.c:650-760): local real pass over the rows plus two c2c
