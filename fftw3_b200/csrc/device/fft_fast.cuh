@@ -233,8 +233,26 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
     auto sidx = [&](int k) -> int { return COL ? (k * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
 
     const b2::TileCtx c = b2::decode_block(p, block);
-    const int64_t b0 = c.tile0 * TPB + t;
-    const bool valid = b0 < p.bn[0];
+    // FLAVOR 10 (last pass of an even-size r2c, rdft/ct-hc2c.c:146-273 / ct-hc2c-direct.c:45-60 in the reference):
+    // the CTA transforms HALF = TPB / 2 rows k1 of the four-step's second pass together with their mirror rows
+    // n1 - k1, so that every pair (k, m - k) of the half-size spectrum Z meets in shared memory and the split
+    // X_k = 1/2 [(Z_k + conj Z_{m-k}) - i w^k (Z_k - conj Z_{m-k})] rides on the store: no separate pass over HBM.
+    // Tiles: rows [1 + HALF*tile, 1 + HALF*(tile+1)) and their mirrors; the last tile holds row 0 (its own mirror).
+    constexpr int HALF = TPB / 2 > 0 ? TPB / 2 : 1;
+    const int64_t f10_n1 = p.aux_split;
+    const bool f10_row0 = FLAVOR == 10 && c.tile0 * (2 * HALF) >= f10_n1;
+    int64_t b0_ = c.tile0 * TPB + t;
+    bool valid_ = b0_ < p.bn[0];
+    if (FLAVOR == 10) {
+        if (f10_row0) { b0_ = 0; valid_ = (t == 0); }
+        else {
+            const int64_t k1 = 1 + (int64_t)HALF * c.tile0 + (t % HALF);
+            b0_ = t < HALF ? k1 : f10_n1 - k1;
+            valid_ = true;
+        }
+    }
+    const int64_t b0 = b0_;
+    const bool valid = valid_;
     const int64_t boff_in = b0 * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2];
     const int64_t boff_out = b0 * p.bos[0] + c.b1 * p.bos[1] + ((p.npeer && FLAVOR != 8) ? 0 : c.b2 * p.bos[2]);
     // interleaved data: vector pointer at the lower of (re, im)
@@ -304,7 +322,7 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
             vr = v.x; vi = v.y;
         }
         cplx<T> o;
-        if (FLAVOR == 3) {
+        if (FLAVOR == 3 || FLAVOR == 10) {
             o.x = vr; o.y = vi;
             sm[sidx(kout)] = o;
         } else if (FLAVOR == 8) {
@@ -330,13 +348,53 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
             const cplx<T> *qt = reinterpret_cast<const cplx<T> *>(p.aux0);
             b2::RealLineOut<T> ya = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
             b2::RealLineOut<T> yb = { reinterpret_cast<T *>(p.out_re) + boff_out + p.pair_os, p.os };
-#pragma unroll 4
+#pragma unroll
             for (int r = 0; r < E; ++r) {
                 const int k = j + r * TPX;
                 cplx<T> u, v;
                 b2::r2r_unpack_pair<T>(sm[sidx(k)], sm[sidx(k ? N - k : 0)], u, v);
                 b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, u, qt, ya);
                 b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, v, qt, yb);
+            }
+            return;
+        }
+        if (FLAVOR == 10) {
+            __syncthreads();
+            const cplx<T> *w = reinterpret_cast<const cplx<T> *>(p.aux0);      // exp(-2 pi i q / n), q <= m = n / 2
+            cplx<T> *ob = reinterpret_cast<cplx<T> *>(p.out_re) + (c.b1 * p.bos[1] + c.b2 * p.bos[2]) / 2;
+            const int64_t s1 = p.bos[0] / 2, s2 = p.os / 2;                    // complex strides of k1 and of k2
+            auto pair = [&](cplx<T> a, cplx<T> cz, int64_t q, cplx<T> &xq, cplx<T> &xp) {
+                const T sr = a.x + cz.x, si = a.y - cz.y, dr = a.x - cz.x, di = a.y + cz.y;
+                const cplx<T> wq = ldg_c(w + q);
+                const T tr = wq.x * di + wq.y * dr, ti = -(wq.x * dr - wq.y * di);
+                xq.x = T(0.5) * (sr + tr); xq.y = T(0.5) * (si + ti);
+                xp.x = T(0.5) * (sr - tr); xp.y = T(0.5) * (-si + ti);
+            };
+            if (!f10_row0) {
+                for (int idx = tid; idx < N * HALF; idx += Cfg::THREADS) {
+                    const int ta = idx % HALF, k2 = idx / HALF;
+                    const int64_t k1 = 1 + (int64_t)HALF * c.tile0 + ta;
+                    cplx<T> xq, xp;
+                    pair(sm[ta * pitch_c(N) + padk_c(k2)], sm[(HALF + ta) * pitch_c(N) + padk_c(N - 1 - k2)],
+                         k1 + f10_n1 * (int64_t)k2, xq, xp);
+                    st_stream(ob + k1 * s1 + (int64_t)k2 * s2, xq);
+                    st_stream(ob + (f10_n1 - k1) * s1 + (int64_t)(N - 1 - k2) * s2, xp);
+                }
+            } else {
+                for (int k2 = tid; k2 <= N / 2; k2 += Cfg::THREADS) {
+                    if (k2 == 0) {
+                        const cplx<T> z0 = sm[0];
+                        cplx<T> x0, xm;
+                        x0.x = z0.x + z0.y; x0.y = T(0); xm.x = z0.x - z0.y; xm.y = T(0);
+                        st_stream(ob, x0);
+                        st_stream(ob + (int64_t)N * s2, xm);                    // Nyquist bin, index m = n1 * N
+                    } else {
+                        cplx<T> xq, xp;
+                        pair(sm[padk_c(k2)], sm[padk_c(N - k2)], f10_n1 * (int64_t)k2, xq, xp);
+                        st_stream(ob + (int64_t)k2 * s2, xq);
+                        if (2 * k2 != N) st_stream(ob + (int64_t)(N - k2) * s2, xp);
+                    }
+                }
             }
             return;
         }
@@ -361,14 +419,29 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
     // buffer: n_in reals per line <= N complex per transform), then gather from there
     T *raw = reinterpret_cast<T *>(sm);
     if (FLAVOR == 9 && !COL) {
+        // eight independent loads in flight per thread and round (a plain strided loop would wait for each load
+        // before issuing the next: 32 serial HBM round trips per tile, profiles/r02_c5b_pieces.txt)
         const int nl = p.r2r_pair ? 2 : 1, nin = p.n_in;
-        for (int idx = tid; idx < TPB * nl * nin; idx += Cfg::THREADS) {
-            const int tt = idx / (nl * nin), rem = idx - tt * (nl * nin);
-            const int ln = rem / nin, e = rem - ln * nin;
-            const int64_t bb = c.tile0 * TPB + tt;
-            if (bb < p.bn[0])
-                raw[idx] = __ldcs(reinterpret_cast<const T *>(p.in_re) + bb * p.bis[0] + c.b1 * p.bis[1] + c.b2 * p.bis[2] +
-                                  (ln ? p.pair_is : 0) + e);
+        const int total = TPB * nl * nin;
+        const T *gbase = reinterpret_cast<const T *>(p.in_re) + c.b1 * p.bis[1] + c.b2 * p.bis[2];
+        for (int base = 0; base < total; base += 8 * Cfg::THREADS) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * Cfg::THREADS + tid;
+                v[u] = T(0);
+                if (idx < total) {
+                    const int tt = idx / (nl * nin), rem = idx - tt * (nl * nin);
+                    const int ln = rem / nin, e = rem - ln * nin;
+                    const int64_t bb = c.tile0 * TPB + tt;
+                    if (bb < p.bn[0]) v[u] = __ldcs(gbase + bb * p.bis[0] + (ln ? p.pair_is : 0) + e);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * Cfg::THREADS + tid;
+                if (idx < total) raw[idx] = v[u];
+            }
         }
         __syncthreads();
     }

@@ -45,11 +45,26 @@ void init(int max_smem)
 // structural applicability (known at plan time).  kernel code = tile + 100*flavor + 1000*col;
 // flavor 2 = COL kernel with the four-step twiddle fused in its store, flavor 3 = ROW load
 // with COL (transposed) store.
+// kernel code = tile + 100 * flavor (+ 1000 for COL kernels), flavors 0-9; codes 2000 + tile = flavor 10 (ROW)
+static inline int code_col(int code) { return code >= 1000 && code < 2000; }
+static inline int code_flavor(int code) { return code >= 2000 ? 10 : (code / 100) % 10; }
+
 static const FastEntry *entry_for(const b2d_fft_pass &p)
 {
     if (!p.kernel) return nullptr;
-    const int col = p.kernel >= 1000;
-    const int flavor = (p.kernel / 100) % 10;
+    const int col = code_col(p.kernel);
+    const int flavor = code_flavor(p.kernel);
+    if (flavor == 10) {
+        // r2c split fused into the four-step's second pass: ROW load from dense scratch rows, split spectrum to
+        // the user's interleaved output; n1 = bn[0] rows, a whole number of mirror-paired tiles
+        if (p.pre_op || p.post_op != B2D_STORE_R2C_SPLIT || p.bluestein || p.npeer || p.load_col || !p.store_col) return nullptr;
+        if (p.is != 2 || (p.os & 1) || (p.bos[0] & 1) || (p.bos[1] & 1) || (p.bos[2] & 1) || (p.bis[0] & 1) ||
+            (p.bis[1] & 1) || (p.bis[2] & 1)) return nullptr;
+        const FastEntry *e10 = find(p.prec, p.n, 0, p.kernel);
+        if (!e10 || ((int)e10->smem > g_max_smem && g_max_smem)) return nullptr;
+        if (p.bn[0] < e10->tpb || p.bn[0] % e10->tpb) return nullptr;
+        return e10;
+    }
     if (flavor == 9) {
         // r2r kinds fused into the pass: real lines, so strides are in single reals
         if (p.pre_op != B2D_LOAD_R2R || p.post_op != B2D_STORE_R2R || p.bluestein || p.npeer) return nullptr;
@@ -105,7 +120,7 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     const FastEntry *e = entry_for(p);
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;
-    const bool reals = ((p.kernel / 100) % 10) == 9;            // r2r: scalar accesses, no re/im pairing
+    const bool reals = code_flavor(p.kernel) == 9;              // r2r: scalar accesses, no re/im pairing
     const intptr_t din = reals ? (intptr_t)rs : (const char *)p.in_im - (const char *)p.in_re;
     const intptr_t dout = reals ? (intptr_t)rs : (char *)p.out_im - (char *)p.out_re;   /* also tells the peer path whether to swap */
     // interleaved (im = re +- 1 scalar) and vector-aligned, else the generic kernel handles it
@@ -118,16 +133,23 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
         for (int i = 0; i < p.npeer; ++i) lo_out |= (uintptr_t)p.peer_out[i];
     }
     if (!reals && ((lo_in % (2 * rs)) || (lo_out % (2 * rs)))) return 1;
-    const int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
+    int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
+    b2d_fft_pass q = p;
+    q.tpb = e->tpb;                  // decode_block() uses the tile width
+    if (code_flavor(p.kernel) == 10) {
+        if (swap_in || swap_out) return 1;
+        // tiles of HALF = tpb / 2 rows + their mirrors over rows 1 .. n1/2, plus one tile for row 0
+        q.aux_split = p.bn[0];
+        tiles0 = p.bn[0] / e->tpb + 1;
+        q.bn[0] = tiles0 * e->tpb;
+    }
     const int64_t blocks = tiles0 * p.bn[1] * p.bn[2];
     if (blocks <= 0) return 0;
     if (blocks > 2147483647LL) return -1;
-    b2d_fft_pass q = p;
-    q.tpb = e->tpb;                  // decode_block() uses the tile width
     int64_t grid = blocks;
     if (p.grid_limit > 0 && grid > p.grid_limit) {
         // an instantiation whose CTAs loop over the tiles, when the table has one for this kernel
-        const FastEntry *pe = find(p.prec, p.n, p.kernel >= 1000, p.kernel, -1, 1);
+        const FastEntry *pe = find(p.prec, p.n, code_col(p.kernel), p.kernel, -1, 1);
         if (pe && pe->tpb == e->tpb) { e = pe; grid = p.grid_limit; }
     }
     e->launch(q, swap_in, swap_out, (unsigned)grid, (long long)blocks, st);

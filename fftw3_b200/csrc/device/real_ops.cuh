@@ -232,30 +232,37 @@ B2_HD void copy_elem(const b2d_copy &c, int64_t idx)
 // analogue): when the dimension that is contiguous on the input side (da) is not the one that is
 // contiguous on the output side (db), move 32x32 tiles through shared memory so that both the
 // loads and the stores of a warp are contiguous.  V = one element (real, or a whole complex).
-template <typename V>
-__global__ void transpose_kernel(const __grid_constant__ b2d_copy c, int da, int db, int dc, int dd,
-                                 int64_t tiles_a, int64_t tiles_b)
+template <typename V, int TS>
+__global__ void __launch_bounds__(256) transpose_kernel(const __grid_constant__ b2d_copy c, int da, int db, int dc, int dd,
+                                                        int64_t tiles_a, int64_t tiles_b)
 {
-    __shared__ V tile[32][33];
+    // TS x TS tile, 256 threads: TS*TS/256 independent loads in flight per thread (16 for the 64 x 64 tile of
+    // 4- and 8-byte elements) -- the 32 x 32 tile with 4 loads per thread ran at 2.5 TB/s (profiles/r02_c5b_pieces.txt)
+    __shared__ V tile[TS][TS + 1];
+    constexpr int ROWS = 256 / TS;                      // tile rows covered by one sweep of the CTA
+    constexpr int SWEEPS = TS / ROWS;
     const int es = c.elem_reals;                        // strides are in reals; V spans es reals
     int64_t blk = blockIdx.x;
     const int64_t ta = blk % tiles_a; blk /= tiles_a;
     const int64_t tb = blk % tiles_b; blk /= tiles_b;
     const int64_t ic = blk % c.n[dc], id = blk / c.n[dc];
     const int64_t rest_in = ic * c.is[dc] + id * c.is[dd], rest_out = ic * c.os[dc] + id * c.os[dd];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8 threads
+    const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
     const V *in = reinterpret_cast<const V *>(c.in);
     V *out = reinterpret_cast<V *>(c.out);
+    V v[SWEEPS];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int64_t a = ta * 32 + tx, b = tb * 32 + ty + 8 * r;
-        if (a < c.n[da] && b < c.n[db]) tile[ty + 8 * r][tx] = in[(a * c.is[da] + b * c.is[db] + rest_in) / es];
+    for (int r = 0; r < SWEEPS; ++r) {
+        const int64_t a = ta * TS + tx, b = tb * TS + ty + ROWS * r;
+        if (a < c.n[da] && b < c.n[db]) v[r] = in[(a * c.is[da] + b * c.is[db] + rest_in) / es];
     }
+#pragma unroll
+    for (int r = 0; r < SWEEPS; ++r) tile[ty + ROWS * r][tx] = v[r];
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int64_t b = tb * 32 + tx, a = ta * 32 + ty + 8 * r;
-        if (a < c.n[da] && b < c.n[db]) out[(a * c.os[da] + b * c.os[db] + rest_out) / es] = tile[tx][ty + 8 * r];
+    for (int r = 0; r < SWEEPS; ++r) {
+        const int64_t b = tb * TS + tx, a = ta * TS + ty + ROWS * r;
+        if (a < c.n[da] && b < c.n[db]) out[(a * c.os[da] + b * c.os[db] + rest_out) / es] = tile[tx][ty + ROWS * r];
     }
 }
 

@@ -29,6 +29,7 @@ size_t g_max_smem = 0;
 char g_name[256] = "";
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 std::atomic<uint64_t> g_launches{0};
+int g_generic_max_threads[2][2] = { { 1024, 1024 }, { 1024, 1024 } };   // [f32?][plain?]: register-limited block size
 
 int fail(cudaError_t e, const char *what)
 {
@@ -59,6 +60,16 @@ int ensure_init()
     cudaFuncSetAttribute(b2::fft_generic_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
     cudaFuncSetAttribute(b2::fft_generic_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
     cudaFuncSetAttribute(b2::fft_generic_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+    {
+        // the generic kernel is register-heavy: a block of tpb * tpx threads may not be launchable
+        // (e.g. 648 threads x 104 registers); its loops stride by blockDim, so the launch clamps
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, b2::fft_generic_kernel<double, false>) == cudaSuccess) g_generic_max_threads[0][0] = fa.maxThreadsPerBlock;
+        if (cudaFuncGetAttributes(&fa, b2::fft_generic_kernel<double, true>) == cudaSuccess) g_generic_max_threads[0][1] = fa.maxThreadsPerBlock;
+        if (cudaFuncGetAttributes(&fa, b2::fft_generic_kernel<float, false>) == cudaSuccess) g_generic_max_threads[1][0] = fa.maxThreadsPerBlock;
+        if (cudaFuncGetAttributes(&fa, b2::fft_generic_kernel<float, true>) == cudaSuccess) g_generic_max_threads[1][1] = fa.maxThreadsPerBlock;
+        cudaGetLastError();
+    }
     b2fast::init((int)g_max_smem);
     return 0;
 }
@@ -254,6 +265,15 @@ int b2d_launch_fft_pass(const b2d_fft_pass *p)
     if (threads > 1024) threads = 1024;
     int swi = 0, swo = 0;
     const bool plain = b2::plain_ok(*p, &swi, &swo);
+    {
+        int cap = g_generic_max_threads[p->prec == B2D_F32 ? 1 : 0][plain ? 1 : 0];
+        if (threads > cap) {
+            // whole threads-per-transform groups: the stage loops map thread -> (transform, butterfly) by blockDim / tpb
+            int tpx = cap / (p->tpb > 0 ? p->tpb : 1);
+            threads = tpx >= 1 ? tpx * p->tpb : cap;
+            if (threads < 32) threads = cap;
+        }
+    }
     if (p->prec == B2D_F32) {
         if (plain) b2::fft_generic_kernel<float, true><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, swi, swo);
         else b2::fft_generic_kernel<float, false><<<(unsigned)blocks, threads, smem, g_stream>>>(*p, 0, 0);
@@ -304,12 +324,15 @@ int b2d_launch_copy(const b2d_copy *c)
         if (ok && da >= 0 && db >= 0 && da != db && c->n[da] >= 16 && c->n[db] >= 16 &&
             c->is[da] > 0 && c->os[db] > 0) {
             for (i = 0; i < 4; ++i) if (i != da && i != db) { if (dc < 0) dc = i; else dd = i; }
-            int64_t ta = (c->n[da] + 31) / 32, tb = (c->n[db] + 31) / 32;
+            const int ts = (vs == 16 || c->n[da] < 64 || c->n[db] < 64) ? 32 : 64;
+            int64_t ta = (c->n[da] + ts - 1) / ts, tb = (c->n[db] + ts - 1) / ts;
             int64_t nblk = ta * tb * c->n[dc] * c->n[dd];
             if (nblk <= 2147483647LL) {
-                if (vs == 4) b2::transpose_kernel<float><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
-                else if (vs == 8) b2::transpose_kernel<double><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
-                else b2::transpose_kernel<double2><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                if (vs == 4 && ts == 64) b2::transpose_kernel<float, 64><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else if (vs == 4) b2::transpose_kernel<float, 32><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else if (vs == 8 && ts == 64) b2::transpose_kernel<double, 64><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else if (vs == 8) b2::transpose_kernel<double, 32><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
+                else b2::transpose_kernel<double2, 32><<<(unsigned)nblk, 256, 0, g_stream>>>(*c, da, db, dc, dd, ta, tb);
                 cudaError_t e2 = cudaGetLastError();
                 if (e2 != cudaSuccess) return fail(e2, "transpose_kernel launch");
                 g_launches++;

@@ -124,7 +124,7 @@ static void limit_grid(b2_plan *pl, int limit)
 static int chunks_for(int64_t n)
 {
     const char *e = getenv("FFTW3_B200_DIST_CHUNKS");
-    int c = e ? atoi(e) : 4;      /* stage 0: the HBM-bound Y pass of chunk c + 1 overlaps the NVLink-bound X pass of chunk c */
+    int c = e ? atoi(e) : 8;      /* stage 0: the HBM-bound Y pass of chunk c + 1 overlaps the NVLink-bound X pass of chunk c */
     if (c < 1) c = 1;
     if (c > 64) c = 64;
     while (c > 1 && n / c < 2) c /= 2;

@@ -16,8 +16,8 @@
 #include "b2_internal.h"
 
 #define B2_WISDOM_VERSION "fftw3_b200-1.0"
-/* changes whenever the meaning of `variant` changes (kernel registry signature) */
-#define B2_REGISTRY_SIG 0x0b2000010001ULL
+/* changes whenever the meaning of `variant` changes (kernel registry version) */
+#define B2_REGISTRY_VERSION 0x0b2000020001ULL
 
 typedef struct went {
     struct went *next;
@@ -36,6 +36,19 @@ static uint64_t fnv(uint64_t h, const void *data, size_t n)
     size_t i;
     for (i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ULL; }
     return h;
+}
+
+/* Wisdom is only valid for the solver configuration that produced it (the reference refuses wisdom written
+   by a different set of solvers, kernel/planner.c:847-852).  Here the "configuration" is the kernel registry
+   AND the device the timings were taken on: registry version, device name and SM count are hashed into the
+   signature in the header line; a file from another GPU model is rejected wholesale. */
+static unsigned long long registry_sig(void)
+{
+    const char *name = b2d_device_name();
+    int sms = b2d_sm_count();
+    uint64_t h = fnv(0xcbf29ce484222325ULL ^ B2_REGISTRY_VERSION, name ? name : "", name ? strlen(name) : 0);
+    h = fnv(h, &sms, sizeof sms);
+    return (unsigned long long)h;
 }
 
 b2_sig b2_sig_of_pass(const b2d_fft_pass *p, int inplace)
@@ -128,7 +141,7 @@ static void wisdom_export_locked(void (*emit)(char c, void *), void *data, int p
     char buf[160];
     int i;
     snprintf(buf, sizeof buf, "(%s %s #x%llx\n", B2_WISDOM_VERSION,
-             prec == B2D_F32 ? "fftwf_wisdom" : "fftw_wisdom", (unsigned long long)B2_REGISTRY_SIG);
+             prec == B2D_F32 ? "fftwf_wisdom" : "fftw_wisdom", registry_sig());
     emit_str(emit, data, buf);
     for (i = 0; i < NBUCKET; ++i) {
         went *e;
@@ -183,7 +196,7 @@ static int wisdom_import_locked(int (*next)(void *), void *data, int prec)
     if (!expect(&s, '(')) return 0;
     if (!token(&s, tok, sizeof tok) || strcmp(tok, B2_WISDOM_VERSION)) return 0;
     if (!token(&s, tok, sizeof tok) || strcmp(tok, prec == B2D_F32 ? "fftwf_wisdom" : "fftw_wisdom")) return 0;
-    if (!token(&s, tok, sizeof tok) || !hexval(tok, &v) || v != B2_REGISTRY_SIG) return 0;
+    if (!token(&s, tok, sizeof tok) || !hexval(tok, &v) || v != registry_sig()) return 0;
     for (;;) {
         int c;
         unsigned long long pat, pr, h0, h1;

@@ -45,8 +45,11 @@ enum {
     B2D_STORE_CHIRP_SCALE = 4, /* Bluestein: z * aux0[k] * scale                      */
     B2D_STORE_TWIDDLE4 = 8,    /* four-step: z *= W_big^(k * b0) (two-level tables)   */
     B2D_STORE_RADER = 32,      /* element k goes to output index perm_out[k], times scale */
-    B2D_STORE_R2R = 16         /* output k scattered into the real line of n_out elements by the
+    B2D_STORE_R2R = 16,        /* output k scattered into the real line of n_out elements by the
                                   POST map of r2r_kind                                 */
+    B2D_STORE_R2C_SPLIT = 64   /* second pass of a four-step half-size transform of an even-size r2c: the split
+                                  X_k = 1/2[(Z_k + conj Z_{m-k}) - i w^k (Z_k - conj Z_{m-k})] rides on the store
+                                  (aux0 = exp(-2 pi i q / n), q <= n/2; specialised kernels only)      */
 };
 
 /* One batched strided 1-D complex FFT pass.  All strides/offsets are in units

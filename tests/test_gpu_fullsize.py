@@ -337,12 +337,14 @@ def test_config5b_full_size_redft10_4096sq(gpu_lib):
     gpu_lib.destroy_plan("d", p)
     xh = x.cpu().numpy().astype(np.longdouble)
     yh = y.cpu().numpy()
-    jj = (np.arange(n, dtype=np.longdouble) + 0.5)
+    pi_ld = np.longdouble("3.14159265358979323846264338327950288")
+    jodd = 2 * np.arange(n, dtype=np.int64) + 1
     rng = np.random.default_rng(2)
     scale = float(np.sqrt((xh ** 2).sum())) * 4
     for k1, k2 in [(0, 0), (n - 1, n - 1), (1, n - 2)] + [tuple(rng.integers(0, n, 2)) for _ in range(9)]:
-        c1 = np.cos(np.pi * jj * int(k1) / n)
-        c2 = np.cos(np.pi * jj * int(k2) / n)
+        # cos(pi (2j+1) k / (2n)) with the argument reduced exactly in integers (mod 4n) before the long-double cosine
+        c1 = np.cos(pi_ld * ((jodd * int(k1)) % (4 * n)).astype(np.longdouble) / (2 * n))
+        c2 = np.cos(pi_ld * ((jodd * int(k2)) % (4 * n)).astype(np.longdouble) / (2 * n))
         want = 4 * float(c1 @ xh @ c2)
         assert abs(yh[k1, k2] - want) <= 1e-14 * scale, (k1, k2, yh[k1, k2], want)
     q = gpu_lib.fn("d", "plan_r2r_2d")(n, n, y.data_ptr(), y.data_ptr(), 4, 4, B.FFTW_ESTIMATE)     # REDFT01, in place

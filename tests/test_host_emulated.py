@@ -186,6 +186,14 @@ def test_wisdom_roundtrip(emu_lib):
     assert emu_lib.fn("f", "import_wisdom_from_string")(s.encode()) == 0
     assert emu_lib.fn("d", "import_wisdom_from_string")(b"(fftw-3.3.11 fftw_wisdom #x0)") == 0
     assert emu_lib.fn("d", "import_wisdom_from_string")(s[:-10].encode()) == 0
+    # wisdom measured on another device / kernel registry (different configuration signature in the header
+    # line, kernel/planner.c:847-852) is rejected wholesale
+    import re
+    m = re.match(r"\((\S+) (\S+) #x([0-9a-f]+)", s)
+    other = s.replace("#x" + m.group(3), "#x%x" % (int(m.group(3), 16) ^ 0x5a5a), 1)
+    emu_lib.fn("d", "forget_wisdom")()
+    assert emu_lib.fn("d", "import_wisdom_from_string")(other.encode()) == 0
+    assert not mk(B.FFTW_WISDOM_ONLY | B.FFTW_MEASURE)
 
 
 def test_plan_introspection(emu_lib):
