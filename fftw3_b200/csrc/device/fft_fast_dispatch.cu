@@ -2,6 +2,7 @@
 // instantiations live in the generated fft_fast_table_*.cu files.
 #include <stdint.h>
 #include "fft_fast.cuh"
+#include "fft_warp.cuh"
 
 namespace b2fast {
 
@@ -33,6 +34,7 @@ void init(int max_smem)
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) g_sms = sms;
     }
+    b2warp::init(max_smem, g_sms);
     const FastEntry *tabs[4] = { table_d_row, table_d_col, table_f_row, table_f_col };
     const int cnts[4] = { table_d_row_count, table_d_col_count, table_f_row_count, table_f_col_count };
     for (int k = 0; k < 4; ++k)
@@ -106,17 +108,20 @@ int available(const b2d_fft_pass &p, int code)
 {
     b2d_fft_pass q = p;
     q.kernel = code;
+    if (code >= 3000) return code == 3001 && b2warp::applicable(q);
     return entry_for(q) != nullptr;
 }
 
 size_t smem_bytes(const b2d_fft_pass &p)
 {
+    if (p.kernel >= 3000) return b2warp::applicable(p) ? (p.prec == B2D_F32 ? b2warp::smem_bytes<float>() : b2warp::smem_bytes<double>()) : 0;
     const FastEntry *e = entry_for(p);
     return e ? e->smem : 0;
 }
 
 int try_launch(const b2d_fft_pass &p, cudaStream_t st)
 {
+    if (p.kernel >= 3000) return b2warp::launch(p, st);
     const FastEntry *e = entry_for(p);
     if (!e) return 1;
     const size_t rs = p.prec == B2D_F32 ? 4 : 8;

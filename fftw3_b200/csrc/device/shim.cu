@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 
 #include "fft_generic.cuh"
 #include "real_ops.cuh"
@@ -75,7 +76,40 @@ int ensure_init()
 }
 }  // namespace
 
+namespace {
+struct BarrierArgs { unsigned long long *flags[B2D_MAX_PEERS]; int rank, nranks; unsigned long long epoch; };
+
+__global__ void peer_barrier_kernel(BarrierArgs a)
+{
+    const int d = threadIdx.x;
+    if (d >= a.nranks) return;
+    __threadfence_system();                                  // this stream's earlier (remote) stores first
+    unsigned long long *dst = a.flags[d] + a.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(a.epoch) : "memory");
+    const unsigned long long *mine = a.flags[a.rank] + d;
+    unsigned long long seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < a.epoch);
+}
+}  // namespace
+
 extern "C" {
+
+int b2d_peer_barrier(void *const *flags, int rank, int nranks, unsigned long long epoch)
+{
+    if (ensure_init()) return -1;
+    if (nranks < 1 || nranks > B2D_MAX_PEERS || rank < 0 || rank >= nranks) return -1;
+    if (nranks == 1) return 0;
+    BarrierArgs a;
+    for (int i = 0; i < nranks; ++i) a.flags[i] = (unsigned long long *)flags[i];
+    a.rank = rank; a.nranks = nranks; a.epoch = epoch;
+    peer_barrier_kernel<<<1, 32, 0, g_stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(e, "peer_barrier_kernel launch");
+    g_launches++;
+    return 0;
+}
 
 int b2d_device_count(void) { ensure_init(); return g_ndev; }
 const char *b2d_device_name(void) { ensure_init(); return g_name; }
@@ -189,17 +223,42 @@ int b2d_ipc_export(void *devptr, unsigned char handle[64])
     memcpy(handle, &h, 64);
     return 0;
 }
+/* One mapping per exported allocation and process: several plans may map the same peer slab (a forward and a
+   backward plan on one array), but a handle can be opened only once -- imports are cached and refcounted. */
+namespace {
+struct IpcMap { unsigned char h[64]; void *ptr; int refs; };
+IpcMap g_ipc[256];
+int g_nipc = 0;
+std::mutex g_ipc_mu;
+}
 void *b2d_ipc_import(const unsigned char handle[64])
 {
     if (ensure_init()) return nullptr;
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    for (int i = 0; i < g_nipc; ++i)
+        if (g_ipc[i].refs > 0 && !memcmp(g_ipc[i].h, handle, 64)) { g_ipc[i].refs++; return g_ipc[i].ptr; }
     cudaIpcMemHandle_t h;
     void *p = nullptr;
     memcpy(&h, handle, 64);
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) { fail(e, "cudaIpcOpenMemHandle"); cudaGetLastError(); return nullptr; }
+    int slot = -1;
+    for (int i = 0; i < g_nipc; ++i) if (g_ipc[i].refs == 0) { slot = i; break; }
+    if (slot < 0 && g_nipc < 256) slot = g_nipc++;
+    if (slot >= 0) { memcpy(g_ipc[slot].h, handle, 64); g_ipc[slot].ptr = p; g_ipc[slot].refs = 1; }
     return p;
 }
-void b2d_ipc_close(void *devptr) { if (devptr) cudaIpcCloseMemHandle(devptr); }
+void b2d_ipc_close(void *devptr)
+{
+    if (!devptr) return;
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    for (int i = 0; i < g_nipc; ++i)
+        if (g_ipc[i].refs > 0 && g_ipc[i].ptr == devptr) {
+            if (--g_ipc[i].refs == 0) cudaIpcCloseMemHandle(devptr);
+            return;
+        }
+    cudaIpcCloseMemHandle(devptr);
+}
 int64_t b2d_alloc_offset(const void *devptr)
 {
     // cuMemGetAddressRange through the runtime's driver entry point (the library does not link libcuda)

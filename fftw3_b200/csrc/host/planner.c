@@ -228,6 +228,7 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 }
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
+#define NWARP 1               /* warp-per-transform kernel */
 #define NFAST 42              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor 0..6
                                  (flavor 0 plain, 1 register-capped, 4-6 L2 prefetch-size loads for narrow COL tiles) */
 
@@ -235,7 +236,17 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
-    if (variant >= NVARIANTS + NFAST) return -1;
+    if (variant == NVARIANTS + NFAST) {
+        /* warp-per-transform kernel (device/fft_warp.cuh): contiguous 1024-point lines as 32 x 32 */
+        if (!b2d_fast_available(f, 3001)) return -1;
+        ns = b2_factorize(f->n, f->prec, 0, f->radix);
+        if (ns == 0) return -1;
+        f->nstages = ns < 0 ? 0 : ns;
+        fill_geometry(f, 0);            /* generic geometry stays configured: fallback for misaligned new arrays */
+        f->kernel = 3001;
+        return 0;
+    }
+    if (variant > NVARIANTS + NFAST) return -1;
     if (variant >= NVARIANTS) {
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
@@ -284,6 +295,12 @@ static int estimate_variant(b2d_fft_pass *f)
     int col = f->load_col || f->store_col, i;       /* wide tiles whenever a side is strided */
     const int *pref = col ? col_pref : row_pref;
     int npref = col ? 4 : 6;
+    if (!col) {
+        /* contiguous 1024-point lines: the warp-per-transform kernel (measured 6.1 TB/s vs 5.3 for the
+           block-cooperative one, profiles/r02_row_experiment.log) */
+        b2d_fft_pass t = *f;
+        if (!configure_variant(&t, NVARIANTS + NFAST)) return NVARIANTS + NFAST;
+    }
     if (f->load_col && f->store_col && !f->pre_op && !f->post_op && !f->npeer) {
         size_t esz = 2 * real_size(f->prec);
         int64_t stride_bytes = llabs(f->is) * (int64_t)real_size(f->prec);
@@ -483,7 +500,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
         if (!have && b2_wisdom_lookup(sig, pat, &variant)) have = 1;
         if (!have && (p->prob.flags & B2F_WISDOM_ONLY)) return -2;
         if (!have && pat >= 1 && !time_is_up()) {
-            int v, nv = NVARIANTS + NFAST, bestv = -1, timed_any = 0;
+            int v, nv = NVARIANTS + NFAST + NWARP, bestv = -1, timed_any = 0;
             double bestt = 1e30;
             int64_t dri = (in.im.buf == in.re.buf) ? in.im.off - in.re.off : 1;
             int64_t dro = (out.im.buf == out.re.buf) ? out.im.off - out.re.off : 1;
@@ -505,7 +522,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
                     fprintf(stderr, "[b200 planner] n=%d %s->%s batch=%lldx%lldx%lld variant %2d %s tile=%d: %.4f ms  %.0f GB/s\n",
                             f->n, f->load_col ? "col" : "row", f->store_col ? "col" : "row", (long long)f->bn[0],
                             (long long)f->bn[1], (long long)f->bn[2], v,
-                            trial.kernel ? "codelet" : "generic",
+                            trial.kernel >= 3000 ? "warp32x32" : (trial.kernel ? "codelet" : "generic"),
                             trial.kernel ? trial.kernel % 100 : trial.tpb, t, t > 0 ? bytes / t / 1e6 : 0.0);
                 }
                 if (t >= 0 && t < bestt) { bestt = t; bestv = v; }
@@ -1814,7 +1831,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel >= 2000) fprintf(f, "codelet-tile=%d/r2c-split", q->kernel % 100);
+            if (q->kernel >= 3000) fprintf(f, "warp-per-transform 32x32");
+            else if (q->kernel >= 2000) fprintf(f, "codelet-tile=%d/r2c-split", q->kernel % 100);
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);
             fprintf(f, " %s->%s%s)", q->load_col ? "col" : "row", q->store_col ? "col" : "row",

@@ -63,6 +63,90 @@ def _declare(lib):
     L._dist_declared = True
 
 
+# --------------------------------------------------------------------------
+# communicator interface (include/fftw3_b200_dist.h: fftw_b200_mpi_*)
+# --------------------------------------------------------------------------
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class CommStruct(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("allgather", ALLGATHER_FN), ("ctx", C.c_void_p)]
+
+
+def torch_comm(group=None):
+    """fftw_b200_comm whose all-gather is torch.distributed's (the launcher-specific collective the C
+    interface asks for; an MPI program would pass MPI_Allgather instead).  Keep the returned object alive as
+    long as plans made with it are being created."""
+    rank, P = dist.get_rank(group), dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+
+    def ag(ctx, send, recv, nbytes):
+        try:
+            buf = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8)
+            if on_gpu:
+                buf = buf.cuda()
+            out = [torch.empty_like(buf) for _ in range(P)]
+            dist.all_gather(out, buf, group=group)
+            data = torch.cat(out).cpu().numpy().tobytes()
+            C.memmove(recv, data, len(data))
+            return 0
+        except Exception:        # never let an exception cross the C boundary
+            return 1
+
+    cb = ALLGATHER_FN(ag)
+    cs = CommStruct(rank, P, cb, None)
+    cs._keep = cb
+    return cs
+
+
+def _declare_mpi(lib):
+    L = lib.lib
+    if getattr(L, "_mpi_declared", False):
+        return
+    P, I, U = C.c_void_p, C.c_int, C.c_uint
+    S = C.c_ssize_t
+    SP = C.POINTER(C.c_ssize_t)
+    CP = C.POINTER(CommStruct)
+    L.fftw_b200_mpi_local_size_many_transposed.restype = S
+    L.fftw_b200_mpi_local_size_many_transposed.argtypes = [I, SP, S, S, S, CP, SP, SP, SP, SP]
+    for pfx in ("fftw_b200_mpi_", "fftwf_b200_mpi_"):
+        f = getattr(L, pfx + "plan_many_dft")
+        f.restype = P
+        f.argtypes = [I, SP, S, S, S, P, P, CP, I, U]
+    L.fftw_b200_mpi_execute.argtypes = [P]
+    L.fftw_b200_mpi_destroy_plan.argtypes = [P]
+    L._mpi_declared = True
+
+
+class CommPlan:
+    """fftw_mpi_plan_many_dft through the C communicator interface: `local` is this rank's slab (device
+    memory from cudaMalloc / fftw_b200_device_malloc), transformed in place unless `out` is given."""
+
+    def __init__(self, lib, n, comm, local_ptr, out_ptr=None, howmany=1, prec="d", sign=B.FFTW_FORWARD,
+                 flags=B.FFTW_ESTIMATE, transposed_out=False):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        self.comm = comm
+        nn = (C.c_ssize_t * len(n))(*n)
+        v = [C.c_ssize_t() for _ in range(4)]
+        self.alloc = int(self.L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, 0, 0, C.byref(comm),
+                                                                        *[C.byref(x) for x in v]))
+        self.ln0, self.s0, self.ln1, self.s1 = [int(x.value) for x in v]
+        fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_dft")
+        fl = int(flags) | (FFTW_MPI_TRANSPOSED_OUT if transposed_out else 0)
+        self.plan = fn(len(n), nn, howmany, 0, 0, local_ptr, out_ptr if out_ptr is not None else local_ptr,
+                       C.byref(comm), int(sign), fl)
+
+    def execute(self):
+        self.L.fftw_b200_mpi_execute(self.plan)
+
+    def destroy(self):
+        if self.plan:
+            self.L.fftw_b200_mpi_destroy_plan(self.plan)
+            self.plan = None
+
+
 def local_size_3d(lib, n0, n1, n2, rank, nranks):
     """(alloc_elements, local_n0, local_0_start, local_n1, local_1_start)"""
     _declare(lib)

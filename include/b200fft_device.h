@@ -208,6 +208,13 @@ void *b2d_ipc_import(const unsigned char handle[64]);
 void b2d_ipc_close(void *devptr);
 int64_t b2d_alloc_offset(const void *devptr);   /* byte offset inside its allocation, -1 on failure */
 
+/* Barrier among the single-GPU processes of a job, on the launch stream, without the host: flags[d] is rank
+   d's flag array (nranks x 8 bytes, zeroed, peer-mapped); the kernel stores `epoch` into slot `rank` of every
+   peer's array (system-scope release) and spins until all slots of its own array have reached `epoch`.
+   Everything enqueued before it on this stream -- remote stores of pass kernels included -- is complete and
+   visible to the peers when they leave the barrier. */
+int  b2d_peer_barrier(void *const *flags, int rank, int nranks, unsigned long long epoch);
+
 /* timing on the launch stream (planner measurements) */
 int  b2d_timer_start(void);
 int  b2d_timer_stop(float *ms);

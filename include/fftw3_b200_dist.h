@@ -102,6 +102,83 @@ void fftw_b200_dist_execute_chunk(const fftw_b200_dist_plan p, int stage, int ch
 void fftw_b200_dist_join(const fftw_b200_dist_plan p);
 void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);
 
+/* ======================================================================================================
+ * Communicator interface: the fftw_mpi_* shapes (mpi/fftw3-mpi.h:58-215) with the MPI_Comm replaced by the
+ * ONE collective the library needs from the launcher -- a blocking all-gather of a few hundred bytes of
+ * host memory, used while planning only.  The library then allocates its exchange buffer, maps every
+ * rank's exchange buffer and slab into every other rank (CUDA IPC over NVLink), and execution owns its
+ * synchronisation: the ranks meet in device-side barriers (flags in peer memory), with no host round trip.
+ *
+ *   reference (mpi/api.c)                          here
+ *   fftw_mpi_local_size(_many)(_transposed)  ->    fftw_b200_mpi_local_size(_many)(_transposed)   :248-352
+ *   fftw_mpi_local_size_2d/_3d(_transposed)  ->    fftw_b200_mpi_local_size_2d/_3d(_transposed)
+ *   fftw_mpi_plan_many_dft / plan_dft        ->    fftw_b200_mpi_plan_many_dft / plan_dft          :560-648
+ *   fftw_mpi_plan_dft_2d / _3d               ->    fftw_b200_mpi_plan_dft_2d / _3d
+ *   fftw_execute(mpi plan)                   ->    fftw_b200_mpi_execute                           :889-907
+ *   fftwf_mpi_*                              ->    fftwf_b200_mpi_*  (single precision)
+ * Arrays are DEVICE memory obtained from cudaMalloc (or fftw_b200_device_malloc): `in` / `out` hold this
+ * rank's slab [local_n0][n1]...[howmany] with room for the number of elements local_size returns;
+ * FFTW_MPI_TRANSPOSED_OUT leaves [local_n1][n0]...; in == out for an in-place transform.  Only the default
+ * block size (FFTW_MPI_DEFAULT_BLOCK) is supported.  Planning and execution are collective.
+ * ====================================================================================================== */
+#define FFTW_MPI_DEFAULT_BLOCK (0)
+#define FFTW_MPI_SCRAMBLED_IN (1U << 27)
+#define FFTW_MPI_SCRAMBLED_OUT (1U << 28)
+#define FFTW_MPI_TRANSPOSED_IN (1U << 29)
+#define FFTW_MPI_TRANSPOSED_OUT (1U << 30)
+
+typedef struct fftw_b200_comm {
+    int rank, nranks;
+    /* gather `bytes` bytes from every rank into recv (rank order, nranks * bytes); 0 on success.  With MPI:
+       MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, *(MPI_Comm *)ctx) */
+    int (*allgather)(void *ctx, const void *send, void *recv, size_t bytes);
+    void *ctx;
+} fftw_b200_comm;
+
+typedef struct fftw_b200_mpi_plan_s *fftw_b200_mpi_plan;
+
+ptrdiff_t fftw_b200_mpi_local_size_many_transposed(int rnk, const ptrdiff_t *n, ptrdiff_t howmany,
+                                                   ptrdiff_t block0, ptrdiff_t block1, const fftw_b200_comm *comm,
+                                                   ptrdiff_t *local_n0, ptrdiff_t *local_0_start,
+                                                   ptrdiff_t *local_n1, ptrdiff_t *local_1_start);
+ptrdiff_t fftw_b200_mpi_local_size_many(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t block0,
+                                        const fftw_b200_comm *comm, ptrdiff_t *local_n0, ptrdiff_t *local_0_start);
+ptrdiff_t fftw_b200_mpi_local_size(int rnk, const ptrdiff_t *n, const fftw_b200_comm *comm,
+                                   ptrdiff_t *local_n0, ptrdiff_t *local_0_start);
+ptrdiff_t fftw_b200_mpi_local_size_2d(ptrdiff_t n0, ptrdiff_t n1, const fftw_b200_comm *comm,
+                                      ptrdiff_t *local_n0, ptrdiff_t *local_0_start);
+ptrdiff_t fftw_b200_mpi_local_size_2d_transposed(ptrdiff_t n0, ptrdiff_t n1, const fftw_b200_comm *comm,
+                                                 ptrdiff_t *local_n0, ptrdiff_t *local_0_start,
+                                                 ptrdiff_t *local_n1, ptrdiff_t *local_1_start);
+ptrdiff_t fftw_b200_mpi_local_size_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, const fftw_b200_comm *comm,
+                                      ptrdiff_t *local_n0, ptrdiff_t *local_0_start);
+ptrdiff_t fftw_b200_mpi_local_size_3d_transposed(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, const fftw_b200_comm *comm,
+                                                 ptrdiff_t *local_n0, ptrdiff_t *local_0_start,
+                                                 ptrdiff_t *local_n1, ptrdiff_t *local_1_start);
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t block,
+                                               ptrdiff_t tblock, fftw_complex *in, fftw_complex *out,
+                                               const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft(int rnk, const ptrdiff_t *n, fftw_complex *in, fftw_complex *out,
+                                          const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftw_complex *in, fftw_complex *out,
+                                             const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex *in, fftw_complex *out,
+                                             const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t block,
+                                                ptrdiff_t tblock, fftwf_complex *in, fftwf_complex *out,
+                                                const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft(int rnk, const ptrdiff_t *n, fftwf_complex *in, fftwf_complex *out,
+                                           const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_complex *in, fftwf_complex *out,
+                                              const fftw_b200_comm *comm, int sign, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in,
+                                              fftwf_complex *out, const fftw_b200_comm *comm, int sign, unsigned flags);
+/* One distributed transform, collective; returns when this rank's result is complete (or, with
+ * fftw_b200_set_async(1), once everything is enqueued on the launch stream). */
+void fftw_b200_mpi_execute(fftw_b200_mpi_plan p);
+void fftw_b200_mpi_destroy_plan(fftw_b200_mpi_plan p);
+
 /* device memory that can be shared with the other ranks of the job (CUDA IPC) */
 void *fftw_b200_device_malloc(size_t bytes);
 void  fftw_b200_device_free(void *p);

@@ -132,6 +132,55 @@ def main():
             ok &= good
             print("dist check %s P=%d r2r %s rel L2 %.2e %s" % (shape, world, "/".join(kinds), err, "OK" if good else "FAIL"),
                   flush=True)
+    # the C communicator interface (fftw_b200_mpi_*): library-owned exchange buffers, IPC mappings and device-side barriers
+    comm = D.torch_comm()
+    for n, kw in [((64, 48, 32), {}), ((64, 48, 32), {"transposed": True}), ((30, 14, 25), {"sign": 1}), ((96, 80), {}),
+                  ((45, 64), {"transposed": True}), ((32, 24, 20), {"howmany": 2}), ((8, 12, 10, 6), {}),
+                  ((64, 48, 32), {"prec": "f"}), ((34, 19, 6), {}), ((128, 128, 128), {})]:
+        howmany, prec, sign, transposed = kw.get("howmany", 1), kw.get("prec", "d"), kw.get("sign", -1), kw.get("transposed", False)
+        cdt, tdt = (np.complex64, torch.complex64) if prec == "f" else (np.complex128, torch.complex128)
+        shape = tuple(n) + ((howmany,) if howmany > 1 else ())
+        rng = np.random.default_rng(13)
+        full = (rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)).astype(cdt)
+        ref = None
+        if rank == 0:
+            ref = O.dft(np.moveaxis(full, -1, 0) if howmany > 1 else full, sign=sign, rank=len(n))
+            if howmany > 1:
+                ref = np.moveaxis(ref, 0, -1)
+        probe = D.CommPlan.__new__(D.CommPlan)      # sizes before allocation
+        D._declare(lib); D._declare_mpi(lib)
+        import ctypes as C
+        nn = (C.c_ssize_t * len(n))(*n)
+        v = [C.c_ssize_t() for _ in range(4)]
+        alloc = int(lib.lib.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, 0, 0, C.byref(comm), *[C.byref(x) for x in v]))
+        ln0, s0, ln1, s1 = [int(x.value) for x in v]
+        local = torch.zeros(max(alloc, 1), dtype=tdt, device="cuda")
+        if ln0:
+            local[:full[s0:s0 + ln0].size] = torch.from_numpy(full[s0:s0 + ln0].reshape(-1).copy()).cuda()
+        pl = D.CommPlan(lib, list(n), comm, local.data_ptr(), howmany=howmany, prec=prec, sign=sign, transposed_out=transposed)
+        assert pl.plan, "fftw_b200_mpi_plan_many_dft returned NULL"
+        pl.execute()
+        pl.execute() if False else None
+        torch.cuda.synchronize()
+        rest = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+        cnt = (ln1 * n[0] * rest) if transposed else (ln0 * n[1] * rest)
+        mine = local[:cnt].cpu().numpy()
+        pl.destroy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (s1 if transposed else s0, ln1 if transposed else ln0, mine))
+        if rank == 0:
+            got = np.zeros(shape, dtype=cdt)
+            for start, c, arr in gathered:
+                if not c:
+                    continue
+                if transposed:
+                    got[:, start:start + c] = np.moveaxis(arr.reshape((c, n[0]) + shape[2:]), 0, 1)
+                else:
+                    got[start:start + c] = arr.reshape((c, n[1]) + shape[2:])
+            err = O.rel_l2(got, ref)
+            good = err < (3e-6 if prec == "f" else 5e-15)
+            ok &= good
+            print("dist check comm-api %s P=%d %s rel L2 %.2e %s" % (n, world, kw, err, "OK" if good else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

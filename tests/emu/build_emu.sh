@@ -8,7 +8,7 @@ OUT=$ROOT/tests/_emu
 mkdir -p "$OUT"
 H=$ROOT/fftw3_b200/csrc/host
 CF="-O2 -fPIC -std=gnu11 -I$ROOT/include"
-for f in tensor tables planner exec wisdom api_common dist; do gcc $CF -c $H/$f.c -o $OUT/$f.o & done
+for f in tensor tables planner exec wisdom api_common dist dist_api; do gcc $CF -c $H/$f.c -o $OUT/$f.o & done
 gcc $CF -c $H/api.c -o $OUT/api_d.o &
 gcc $CF -DB2_SINGLE -c $H/api.c -o $OUT/api_f.o &
 g++ -O2 -fPIC -std=c++17 -c $HERE/emu_shim.cpp -o $OUT/emu_shim.o &

@@ -10,6 +10,7 @@
 // library (fftw3_b200/lib/libfftw3_b200.so) links shim.cu instead and has no
 // CPU path at all.
 #include <stdio.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
@@ -157,12 +158,30 @@ void b2d_set_stream(void *) {}
 void *b2d_get_stream(void) { return NULL; }
 void *b2d_push_stream(void *) { return NULL; }
 void b2d_pop_stream(void *) {}
+/* ranks of a unit test are THREADS of one process (tests/test_dist_comm_api.py): the same flag protocol as
+   the CUDA kernel, on ordinary memory */
+int b2d_peer_barrier(void *const *flags, int rank, int nranks, unsigned long long epoch)
+{
+    for (int d = 0; d < nranks; ++d)
+        __atomic_store_n((unsigned long long *)flags[d] + rank, epoch, __ATOMIC_RELEASE);
+    for (int d = 0; d < nranks; ++d)
+        while (__atomic_load_n((unsigned long long *)flags[rank] + d, __ATOMIC_ACQUIRE) < epoch) sched_yield();
+    return 0;
+}
 void *b2d_aux_stream(int) { return NULL; }                 /* everything is synchronous here */
 int b2d_stream_wait_stream(void *, void *) { return 0; }
-int b2d_ipc_export(void *, unsigned char *) { return -1; }     /* no IPC in the unit-test double */
-void *b2d_ipc_import(const unsigned char *) { return NULL; }
+/* "IPC" between the threads that play ranks in a unit test: the handle is the pointer itself */
+int b2d_ipc_export(void *p, unsigned char *h) { memset(h, 0, 64); memcpy(h, &p, sizeof p); return 0; }
+void *b2d_ipc_import(const unsigned char *h) { void *p; memcpy(&p, h, sizeof p); return p; }
 void b2d_ipc_close(void *) {}
-int64_t b2d_alloc_offset(const void *) { return 0; }
+int64_t b2d_alloc_offset(const void *p)
+{
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    auto it = g_dev.upper_bound((char *)p);
+    if (it == g_dev.begin()) return -1;
+    --it;
+    return (const char *)p < it->first + it->second ? (int64_t)((const char *)p - it->first) : -1;
+}
 int b2d_timer_start(void) { g_t0 = std::chrono::steady_clock::now(); return 0; }
 int b2d_timer_stop(float *ms)
 {

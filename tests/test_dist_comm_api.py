@@ -1,0 +1,140 @@
+"""The fftw_mpi_* shaped C interface (include/fftw3_b200_dist.h, fftw_b200_mpi_*): plan_many_dft / plan_dft /
+2-D / 3-D, local_size*, execute with the library's own device-side barriers.  Here every rank is a THREAD of
+this process on the emulated device layer (whose "IPC" hands pointers through and whose barrier spins on the
+same flags as the CUDA kernel); the all-gather the interface asks of its launcher is a threading.Barrier.
+The same interface runs across real GPUs in tests/dist_gpu_check.py (pytest -m gpu on a multi-GPU box).
+Reference behaviour restated: mpi/api.c:248-352 (local sizes), :560-648 (plans), doc/mpi.texi:440-463."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+from fftw3_b200 import binding as B
+from fftw3_b200 import dist as D
+from oracle import oracle as O
+
+
+class ThreadComm:
+    """all-gather among threads"""
+
+    def __init__(self, P):
+        self.P = P
+        self.bar = threading.Barrier(P)
+        self.slots = [None] * P
+
+    def comm(self, rank):
+        def ag(ctx, send, recv, nbytes):
+            self.slots[rank] = C.string_at(send, nbytes)
+            self.bar.wait()
+            data = b"".join(self.slots)
+            C.memmove(recv, data, len(data))
+            self.bar.wait()
+            return 0
+        cb = D.ALLGATHER_FN(ag)
+        cs = D.CommStruct(rank, self.P, cb, None)
+        cs._keep = cb
+        return cs
+
+
+def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True):
+    D._declare(lib)
+    L = lib.lib
+    cdt = np.complex64 if prec == "f" else np.complex128
+    rng = np.random.default_rng(3)
+    shape = tuple(n) + ((howmany,) if howmany > 1 else ())
+    full = (rng.uniform(-0.5, 0.5, shape) + 1j * rng.uniform(-0.5, 0.5, shape)).astype(cdt)
+    ref = O.dft(np.moveaxis(full, -1, 0) if howmany > 1 else full, sign=sign, rank=len(n))
+    if howmany > 1:
+        ref = np.moveaxis(ref, 0, -1)
+    tc = ThreadComm(P)
+    got = [None] * P
+    errs = []
+
+    def rank_main(r):
+        try:
+            comm = tc.comm(r)
+            # sizes first (no device memory yet)
+            nn = (C.c_ssize_t * len(n))(*n)
+            v = [C.c_ssize_t() for _ in range(4)]
+            D._declare_mpi(lib)
+            alloc = int(L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, 0, 0, C.byref(comm),
+                                                                  *[C.byref(x) for x in v]))
+            ln0, s0, ln1, s1 = [int(x.value) for x in v]
+            isz = np.dtype(cdt).itemsize
+            a = L.fftw_b200_device_malloc(max(alloc, 1) * isz)
+            b = a if inplace else L.fftw_b200_device_malloc(max(alloc, 1) * isz)
+            view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(alloc, 1) * isz,)).view(cdt)
+            if ln0:
+                view(a)[:full[s0:s0 + ln0].size] = full[s0:s0 + ln0].reshape(-1)
+            pl = D.CommPlan(lib, list(n), comm, a, None if inplace else b, howmany=howmany, prec=prec, sign=sign,
+                            transposed_out=transposed)
+            assert pl.plan, "plan_many_dft returned NULL on rank %d" % r
+            pl.execute()
+            rest = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+            if transposed:
+                got[r] = (s1, ln1, view(b)[:ln1 * n[0] * rest].copy().reshape((ln1, n[0]) + shape[2:]) if ln1 else None)
+            else:
+                got[r] = (s0, ln0, view(b)[:ln0 * n[1] * rest].copy().reshape((ln0, n[1]) + shape[2:]) if ln0 else None)
+            pl.destroy()
+            L.fftw_b200_device_free(a)
+            if not inplace:
+                L.fftw_b200_device_free(b)
+        except BaseException as e:       # noqa: surface it in the main thread
+            errs.append((r, repr(e)))
+            tc.bar.abort()
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(P)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not errs, errs
+    out = np.zeros(shape, dtype=cdt)
+    for start, cnt, arr in got:
+        if not cnt:
+            continue
+        if transposed:
+            out[:, start:start + cnt] = np.moveaxis(arr, 0, 1)
+        else:
+            out[start:start + cnt] = arr
+    return O.rel_l2(out, ref)
+
+
+@pytest.mark.parametrize("n,P,kw", [
+    ((8, 6, 10), 2, {}),                                  # fused plans of dist.c behind the communicator interface
+    ((8, 6, 10), 2, {"transposed": True}),
+    ((12, 10, 7), 3, {"sign": 1}),                        # uneven column blocks
+    ((6, 5, 4), 4, {}),                                   # idle ranks
+    ((16, 12), 2, {}),                                    # 2-D (general path)
+    ((9, 10), 3, {"transposed": True}),
+    ((8, 6, 10), 2, {"howmany": 3}),                      # plan_many_dft
+    ((4, 6, 5, 3), 2, {}),                                # rank 4
+    ((8, 6, 10), 2, {"prec": "f"}),                       # fftwf_b200_mpi_*
+    ((8, 6, 10), 2, {"inplace": False}),
+    ((17, 19, 3), 2, {}),                                 # non-smooth distributed dims
+])
+def test_comm_interface_all_ranks_as_threads(emu_lib, n, P, kw):
+    err = _run(emu_lib, n, P, **kw)
+    assert err <= (2e-6 if kw.get("prec") == "f" else 1e-14), (n, P, kw, err)
+
+
+def test_local_size_matches_the_reference_distribution(emu_lib):
+    """block = ceil(n / P) (mpi/block.c:37-50); alloc covers both the slab and the transposed slab"""
+    D._declare(emu_lib)
+    D._declare_mpi(emu_lib)
+    tc = ThreadComm(1)
+    for P in (1, 2, 3, 5, 8):
+        tot0 = tot1 = 0
+        for r in range(P):
+            cs = tc.comm(0)
+            cs.rank, cs.nranks = r, P
+            nn = (C.c_ssize_t * 3)(10, 7, 6)
+            v = [C.c_ssize_t() for _ in range(4)]
+            alloc = emu_lib.lib.fftw_b200_mpi_local_size_many_transposed(3, nn, 2, 0, 0, C.byref(cs), *[C.byref(x) for x in v])
+            ln0, s0, ln1, s1 = [int(x.value) for x in v]
+            b0, b1 = -(-10 // P), -(-7 // P)
+            assert s0 == min(b0 * r, 10) and ln0 == max(0, min(b0, 10 - b0 * r))
+            assert s1 == min(b1 * r, 7) and ln1 == max(0, min(b1, 7 - b1 * r))
+            assert alloc >= max(ln0 * 7, ln1 * 10) * 6 * 2
+            tot0 += ln0
+            tot1 += ln1
+        assert tot0 == 10 and tot1 == 7
