@@ -93,10 +93,15 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(steps, warmup, sample_n=256):
-    """The reference's own CPU implementation (oracle/_ref = unmodified FFTW
-    sources compiled codelet-less here, with its OpenMP threads) on a bounded
-    sample of the workload: one in-place c2c double transform of sample_n^3."""
+REF_BUILD_NOTE = ("reference sources (planner, Cooley-Tukey solvers, OpenMP threads, API) compiled here with scalar n1/t1 "
+                  "codelets emitted by this repo's generator in the reference's codelet ABI -- genfft needs OCaml, which "
+                  "the image lacks; no SIMD codelets")
+
+
+def cpu_reference_run(steps, warmup, sample_n=256, measure=False, timelimit=20.0):
+    """The reference's own CPU implementation (oracle/_ref = unmodified FFTW planner / solvers / threads
+    compiled here, leaves = scalar codelets from oracle/refbuild/gen_codelets.py) with its OpenMP threads:
+    one in-place c2c double transform of sample_n^3 per step."""
     import ctypes as C
     import numpy as np
     path = os.path.join(ROOT, "oracle", "_ref", "libfftw3_ref.so")
@@ -122,11 +127,18 @@ def cpu_reference_run(steps, warmup, sample_n=256):
     lib.fftw_plan_dft_3d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
     lib.fftw_execute.argtypes = [C.c_void_p]
     lib.fftw_destroy_plan.argtypes = [C.c_void_p]
+    lib.fftw_set_timelimit.argtypes = [C.c_double]
     n = sample_n
+    # a random 64^3 block tiled over the array (filling 2^30 points with an RNG would take longer than the FFTs)
     rng = np.random.default_rng(0)
-    a = (rng.uniform(-0.5, 0.5, (n, n, n)) + 1j * rng.uniform(-0.5, 0.5, (n, n, n))).astype(np.complex128)
-    p = lib.fftw_plan_dft_3d(n, n, n, a.ctypes.data, a.ctypes.data, -1, 1 << 6)   # FFTW_ESTIMATE
+    b = min(n, 64)
+    blk = (rng.uniform(-0.5, 0.5, (b, b, b)) + 1j * rng.uniform(-0.5, 0.5, (b, b, b))).astype(np.complex128)
+    a = np.tile(blk, (n // b, n // b, n // b)) if n % b == 0 else np.resize(blk, (n, n, n))
+    lib.fftw_set_timelimit(C.c_double(timelimit if measure else -1.0))
+    t0 = time.perf_counter()
+    p = lib.fftw_plan_dft_3d(n, n, n, a.ctypes.data, a.ctypes.data, -1, 0 if measure else (1 << 6))
     assert p
+    plan_s = time.perf_counter() - t0
     for _ in range(warmup):
         lib.fftw_execute(p)
     t0 = time.perf_counter()
@@ -135,9 +147,10 @@ def cpu_reference_run(steps, warmup, sample_n=256):
     dt = (time.perf_counter() - t0) / steps
     lib.fftw_destroy_plan(p)
     return {"value": flops_c2c((n, n, n)) / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
-            "sample": "%d^3 c2c double in place, FFTW_ESTIMATE, reference sources built without generated "
-                      "codelets (genfft needs OCaml), %d OpenMP threads" % (n, cores),
-            "ms_per_step": dt * 1e3}
+            "sample": "%d^3 c2c double in place, %s, %d OpenMP threads; %s" % (
+                n, ("FFTW_MEASURE (time limit %.0f s, planning took %.1f s)" % (timelimit, plan_s)) if measure else "FFTW_ESTIMATE",
+                cores, REF_BUILD_NOTE),
+            "ms_per_step": dt * 1e3, "sample_n": n}
 
 
 def cpu_vectorised_run(sample_n=256, repeats=3):
@@ -161,11 +174,22 @@ def cpu_vectorised_run(sample_n=256, repeats=3):
 
 
 def reference_sample_size(args):
-    """512^3 (BASELINE config C3, ~10 s per step on the codelet-less build) when the requested number of
-    steps keeps the whole run within a few minutes, else 256^3."""
+    """The whole workload (1024^3) when a quick probe says the requested steps fit in about four minutes of CPU
+    time, else 512^3 (BASELINE config C3), else 256^3."""
     if args.ref_sample:
         return args.ref_sample
-    return 512 if (max(1, args.steps) + 1) * 12.0 <= 200.0 and args.size >= 512 else min(256, args.size)
+    probe = cpu_reference_run(1, 1, sample_n=min(256, args.size))
+    if probe is None:
+        return min(256, args.size)
+    t256 = probe["ms_per_step"] * 1e-3
+    budget = 240.0
+    for n in (args.size, 512, 256):
+        if n > args.size:
+            continue
+        scale = (n / 256.0) ** 3 * (math.log2(n) / 8.0) * 1.5        # + memory-bound slow-down at sizes beyond the caches
+        if (max(1, args.steps) + 1) * t256 * scale + 30.0 <= budget:
+            return n
+    return min(256, args.size)
 
 
 def run_reference(args):
@@ -173,7 +197,7 @@ def run_reference(args):
     if rank != 0:
         return
     sn = reference_sample_size(args)
-    r = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), sample_n=sn)
+    r = cpu_reference_run(max(1, args.steps), max(0, min(args.warmup, 1)), sample_n=sn, measure=True, timelimit=(10.0 if sn >= 1024 else 20.0))
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfftw3_ref.so is not built"}))
         return
@@ -182,8 +206,9 @@ def run_reference(args):
         "impl": "reference", "metric": "GFLOP/s (5N log2 N), 3-D c2c double", "value": r["value"], "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%d^3 c2c double in place; this arm times the bounded sample %d^3 of it "
-                               "(same transform, 1/%d of the points) on the host CPU" % (n, sn, (n // sn) ** 3),
+        "config": {"workload": ("%d^3 c2c double in place, forward, on the host CPU" % n) if sn == n else
+                               ("%d^3 c2c double in place; this arm times the bounded sample %d^3 of it (same transform, "
+                                "1/%d of the points) on the host CPU" % (n, sn, (n // sn) ** 3)),
                    "sample_size": sn, "same_config": sn == n},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

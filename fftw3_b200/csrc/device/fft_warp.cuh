@@ -38,6 +38,7 @@ warp1024_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_ou
     __syncthreads();
     const cplx<T> *gin_base = reinterpret_cast<const cplx<T> *>(swap_in ? p.in_im : p.in_re);
     cplx<T> *gout_base = reinterpret_cast<cplx<T> *>(swap_out ? p.out_im : p.out_re);
+    const unsigned long long keep_pol = (p.cache & 4) ? b2fast::policy_evict_last() : 0ull;
     const long long wstep = (long long)gridDim.x * WARPS;
     for (long long tr = (long long)blockIdx.x * WARPS + threadIdx.x / 32; tr < ntrans; tr += wstep) {
         const int64_t b0 = tr % p.bn[0];
@@ -72,7 +73,7 @@ warp1024_kernel(const __grid_constant__ b2d_fft_pass p, int swap_in, int swap_ou
             cplx<T> o;
             o.x = swap_out ? im[r] : re[r];
             o.y = swap_out ? re[r] : im[r];
-            b2fast::st_out<T>(gout + 32 * r, o, p.cache, 0ull);
+            b2fast::st_out<T>(gout + 32 * r, o, p.cache, keep_pol);
         }
     }
 }
