@@ -192,7 +192,12 @@ template <typename T, int N, int E, int R1, int R2, int TPB, bool COL, int FLAVO
 struct FastCfg {
     static constexpr int TPX = N / E;
     static constexpr int THREADS = TPX * TPB;
-    static constexpr int SMEM_ELEMS = COL ? N * TPB : pitch_c(N) * TPB;
+    // COL layout [k][t]: rows of TPB * sizeof(cplx) bytes.  With rows shorter than 128 bytes the stage-1 exchange
+    // writes (row index j * E + r: consecutive lanes are E rows = a multiple of 1 KiB apart) land in the same banks
+    // twice per quarter-warp (ncu, round 2: L1 wavefronts 64 % of peak, mio_throttle on the 64-byte-tile kernel):
+    // one spare row per 16 skews them apart.
+    static constexpr bool PADCOL = COL && (TPB * sizeof(cplx<T>) < 128);
+    static constexpr int SMEM_ELEMS = COL ? (PADCOL ? (N + N / 16) * TPB : N * TPB) : pitch_c(N) * TPB;
     static constexpr int TW2_ELEMS = tw_nmult(R1) * E;            // stage-2 twiddles, index k < E
     static constexpr int TW3_ELEMS = tw_nmult(R2) * (N / E);      // stage-3 twiddles, index j < TPX
     static constexpr size_t SMEM_BYTES = (size_t)(SMEM_ELEMS + TW2_ELEMS + TW3_ELEMS) * sizeof(cplx<T>);
@@ -202,7 +207,9 @@ struct FastCfg {
     static constexpr int BY_THREADS = 2048 / THREADS;
     static constexpr int MINB_ = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
     static constexpr int MINB__ = (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) > 0 ? (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) : 1;
-    static constexpr int MINB = FLAVOR == 1 ? MINB__ : 1;   // flavor 1: cap registers for more resident CTAs
+    // flavor 1: cap registers for as many resident CTAs as shared memory allows; strided kernels of 256 threads: keep
+    // the two CTAs per SM that overlap each other's load and compute phases (cap 128 registers)
+    static constexpr int MINB = FLAVOR == 1 ? MINB__ : ((COL && THREADS <= 256 && BY_SMEM >= 2 && sizeof(T) == 8 && FLAVOR != 9) ? 2 : 1);
     static_assert(E * R1 * R2 == N, "radices must multiply to N");
     static_assert(E % R1 == 0 && E % R2 == 0, "later radices must divide the per-thread element count");
     static_assert(TPX % E == 0 || R2 == 1, "stage-2 twiddle index must be thread-constant");
@@ -230,7 +237,7 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
     const int tid = threadIdx.x;
     const int t = COL ? (tid % TPB) : (tid / TPX);
     const int j = COL ? (tid / TPB) : (tid % TPX);
-    auto sidx = [&](int k) -> int { return COL ? (k * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
+    auto sidx = [&](int k) -> int { return COL ? ((k + (Cfg::PADCOL ? (k >> 4) : 0)) * TPB + t) : (t * pitch_c(N) + padk_c(k)); };
 
     const b2::TileCtx c = b2::decode_block(p, block);
     // FLAVOR 10 (last pass of an even-size r2c, rdft/ct-hc2c.c:146-273 / ct-hc2c-direct.c:45-60 in the reference):

@@ -1,6 +1,7 @@
 // fft_fast_dispatch.cu -- lookup and launch of the specialised kernels whose
 // instantiations live in the generated fft_fast_table_*.cu files.
 #include <stdint.h>
+#include <stdlib.h>
 #include "fft_fast.cuh"
 #include "fft_warp.cuh"
 
@@ -108,13 +109,13 @@ int available(const b2d_fft_pass &p, int code)
 {
     b2d_fft_pass q = p;
     q.kernel = code;
-    if (code >= 3000) return code == 3001 && b2warp::applicable(q);
+    if (code >= 3000) return b2warp::applicable(q, code);
     return entry_for(q) != nullptr;
 }
 
 size_t smem_bytes(const b2d_fft_pass &p)
 {
-    if (p.kernel >= 3000) return b2warp::applicable(p) ? (p.prec == B2D_F32 ? b2warp::smem_bytes<float>() : b2warp::smem_bytes<double>()) : 0;
+    if (p.kernel >= 3000) return b2warp::smem_for(p, p.kernel);
     const FastEntry *e = entry_for(p);
     return e ? e->smem : 0;
 }

@@ -228,7 +228,7 @@ static void fill_geometry(b2d_fft_pass *f, int variant)
 }
 
 #define NVARIANTS 12          /* generic-kernel variants: factorisation x tile class */
-#define NWARP 1               /* warp-per-transform kernel */
+#define NWARP 3               /* 32 x 32 kernels: rows (warp per transform), strided with 64 B / 128 B segments */
 #define NFAST 42              /* specialised-kernel variants: tile width 1,2,4,8,16,32 x flavor 0..6
                                  (flavor 0 plain, 1 register-capped, 4-6 L2 prefetch-size loads for narrow COL tiles) */
 
@@ -236,17 +236,21 @@ static int configure_variant(b2d_fft_pass *f, int variant)
 {
     int ns;
     f->kernel = 0;
-    if (variant == NVARIANTS + NFAST) {
-        /* warp-per-transform kernel (device/fft_warp.cuh): contiguous 1024-point lines as 32 x 32 */
-        if (!b2d_fast_available(f, 3001)) return -1;
+    if (variant >= NVARIANTS + NFAST && variant < NVARIANTS + NFAST + NWARP) {
+        /* 32 x 32 kernels for 1024-point lines (device/fft_warp.cuh): warp-per-transform for contiguous lines,
+           one-exchange CTA kernels with 64- or 128-byte row segments for strided ones */
+        int k = variant - (NVARIANTS + NFAST);
+        int esz = (int)(2 * real_size(f->prec));
+        int code = k == 0 ? 3001 : 3100 + (k == 1 ? 64 : 128) / esz;
+        if (!b2d_fast_available(f, code)) return -1;
         ns = b2_factorize(f->n, f->prec, 0, f->radix);
         if (ns == 0) return -1;
         f->nstages = ns < 0 ? 0 : ns;
         fill_geometry(f, 0);            /* generic geometry stays configured: fallback for misaligned new arrays */
-        f->kernel = 3001;
+        f->kernel = code;
         return 0;
     }
-    if (variant > NVARIANTS + NFAST) return -1;
+    if (variant >= NVARIANTS + NFAST + NWARP) return -1;
     if (variant >= NVARIANTS) {
         int tpb = 1 << ((variant - NVARIANTS) % 6);
         int flavor = (variant - NVARIANTS) / 6;
@@ -1831,7 +1835,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, "\n  (fft-pass \"%s\" n=%d radix=", s->note, q->n);
             for (j = 0; j < q->nstages; ++j) fprintf(f, "%s%d", j ? "x" : "", q->radix[j]);
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
-            if (q->kernel >= 3000) fprintf(f, "warp-per-transform 32x32");
+            if (q->kernel >= 3100) fprintf(f, "32x32 one-exchange tile=%d", q->kernel - 3100);
+            else if (q->kernel >= 3000) fprintf(f, "warp-per-transform 32x32");
             else if (q->kernel >= 2000) fprintf(f, "codelet-tile=%d/r2c-split", q->kernel % 100);
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);

@@ -241,7 +241,7 @@ _VARIANT_SHAPES = (((1024,), 37, False), ((512, 30), 3, True), ((13, 1024, 20), 
                    ((1000000,), 1, False))
 
 
-@pytest.mark.parametrize("variant", list(range(12, 24)) + list(range(36, 55)))
+@pytest.mark.parametrize("variant", list(range(12, 24)) + list(range(36, 57)))
 def test_every_specialised_kernel_variant(gpu_lib, variant, monkeypatch):
     """Pin each specialised-kernel variant of the planner (tile widths x flavours of
     fft_fast.cuh) and check parity on shapes that exercise
