@@ -318,7 +318,7 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
             return;
         }
         if (FLAVOR == 2) {
-            int64_t e = (int64_t)kout * b0;
+            int64_t e = (int64_t)kout * (b0 + p.tw4_off);
             int64_t eh, el;
             if (p.tw4_shift >= 0) { e &= (p.big_n - 1); eh = e >> p.tw4_shift; el = e & (p.aux_split - 1); }
             else { e %= p.big_n; eh = e / p.aux_split; el = e - eh * p.aux_split; }

@@ -149,7 +149,7 @@ B2_HD void store_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int64_t p
     if ((op & B2D_STORE_TRUNC) && (p.idx_mul ? (int64_t)k * p.idx_mul + b0 : (int64_t)k) >= p.n_out) return;
     if (op & B2D_STORE_TWIDDLE4) {
         // exponent e = k * b0 < big_n ; W^e = hi[e / L] * lo[e % L]
-        int64_t e = ((int64_t)k * b0) % p.big_n;
+        int64_t e = ((int64_t)k * (b0 + p.tw4_off)) % p.big_n;
         int64_t eh = e / p.aux_split, el = e - eh * p.aux_split;
         cplx<T> w = cmul(((const cplx<T> *)p.aux1)[eh], ((const cplx<T> *)p.aux0)[el]);
         z = cmul(z, w);

@@ -51,6 +51,9 @@ typedef struct {
     void *in0, *in1, *out0, *out1;
     int r2r_kind[B2_MAXRANK]; /* public fftw_r2r_kind values                          */
     unsigned flags;
+    /* internal (distributed six-step, dist_api.c): rank-1 c2c whose output k of the batch column b0 (the
+       contiguous batch dimension) is multiplied by exp(-2 pi i k (b0 + tw_off) / tw_big_n); 0 = none */
+    int64_t tw_big_n, tw_off;
 } b2_problem;
 
 /* ---- plan ---- */

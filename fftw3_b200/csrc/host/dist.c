@@ -213,6 +213,15 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
                 f->npeer = nranks;
                 f->peer_rot = rank + 1;
                 for (k = 0; k < nranks; ++k) f->peer_out[k] = (double *)push_targets[k] + 2 * lo * l1 * n2;
+                /* the pass was planned as an ordinary row pass; the kernel chosen for it must also know how to
+                   scatter over peers (the warp-per-transform kernel does not): pick a block-cooperative one */
+                if (f->kernel >= 3000 || (f->kernel && !b2d_fast_available(f, f->kernel))) {
+                    static const int codes[] = { 2, 4, 1, 102, 104, 101 };
+                    size_t ci;
+                    f->kernel = 0;
+                    for (ci = 0; ci < sizeof codes / sizeof codes[0]; ++ci)
+                        if (b2d_fast_available(f, codes[ci])) { f->kernel = codes[ci]; break; }
+                }
                 p->x_fused[c] = 1;
                 break;
             }

@@ -34,10 +34,15 @@ struct fftw_b200_mpi_plan_s {
     char *zalloc;                 /* owned allocation: [flags][exchange buffer] */
     char *zbuf;
     void *peer_z[MAXP], *peer_out[MAXP], *flags[MAXP];
-    void *opened[2 * MAXP];
+    void *opened[3 * MAXP];
     int nopened;
     fftw_b200_dist_plan fused;    /* 3-D double howmany 1: the fused plan of dist.c */
     b2_plan *local, *scatter[MAXP], *z, *back[MAXP];
+    /* kind 1 (six-step 1-D) and 2 (transpose) */
+    int kind;
+    char *z2alloc;                /* second owned buffer (six-step: rows [lr][m]) */
+    void *peer_z2[MAXP];
+    b2_plan *t3[MAXP];
     unsigned long long epoch;
 };
 
@@ -131,7 +136,7 @@ static void problem(b2_problem *q, int prec, unsigned flags, void *in, void *out
     else { q->in0 = (char *)in + rs; q->in1 = in; q->out0 = (char *)out + rs; q->out1 = out; }
 }
 
-typedef struct { unsigned char hz[64], ho[64]; int64_t oz, oo; int ok; int pad; } exch;
+typedef struct { unsigned char hz[64], ho[64], hz2[64]; int64_t oz, oo; int ok; int pad; } exch;
 
 void fftw_b200_mpi_destroy_plan(fftw_b200_mpi_plan p)
 {
@@ -140,11 +145,64 @@ void fftw_b200_mpi_destroy_plan(fftw_b200_mpi_plan p)
     if (p->fused) fftw_b200_dist_destroy_plan(p->fused);
     b2_plan_destroy(p->local);
     b2_plan_destroy(p->z);
-    for (i = 0; i < MAXP; ++i) { b2_plan_destroy(p->scatter[i]); b2_plan_destroy(p->back[i]); }
+    for (i = 0; i < MAXP; ++i) { b2_plan_destroy(p->scatter[i]); b2_plan_destroy(p->back[i]); b2_plan_destroy(p->t3[i]); }
     b2d_sync();
     for (i = 0; i < p->nopened; ++i) b2d_ipc_close(p->opened[i]);
     b2d_free(p->zalloc);
+    b2d_free(p->z2alloc);
     free(p);
+}
+
+/* Allocate the exchange buffer(s), exchange CUDA-IPC handles of them and of the allocation `out` lives in, and map
+   every peer's.  Collective (one all-gather); returns 1 when every rank succeeded, 0 otherwise (same verdict on
+   every rank).  zbytes / z2bytes exclude the flag area. */
+static int setup_peers(fftw_b200_mpi_plan p, const fftw_b200_comm *comm, void *out, size_t zbytes, size_t z2bytes)
+{
+    exch mine, *all;
+    int d, P = p->nranks, r = p->rank, ok = 1;
+    memset(&mine, 0, sizeof mine);
+    p->zalloc = (char *)b2d_malloc(FLAG_BYTES + (zbytes ? zbytes : 16));
+    if (z2bytes) p->z2alloc = (char *)b2d_malloc(z2bytes);
+    if (p->zalloc && (!z2bytes || p->z2alloc)) {
+        p->zbuf = p->zalloc + FLAG_BYTES;
+        b2d_memset(p->zalloc, 0, FLAG_BYTES);
+        b2d_sync();
+        mine.oo = b2d_alloc_offset(out);
+        mine.ok = mine.oo >= 0 && !b2d_ipc_export(p->zalloc, mine.hz) && !b2d_ipc_export((char *)out - mine.oo, mine.ho) &&
+                  (!z2bytes || !b2d_ipc_export(p->z2alloc, mine.hz2));
+    }
+    all = (exch *)calloc((size_t)P, sizeof *all);
+    if (!all || comm->allgather(comm->ctx, &mine, all, sizeof mine)) { free(all); return 0; }
+    for (d = 0; d < P; ++d) if (!all[d].ok) ok = 0;
+    for (d = 0; d < P && ok; ++d) {
+        char *z, *o;
+        if (d == r) { p->flags[d] = p->zalloc; p->peer_z[d] = p->zbuf; p->peer_out[d] = out; p->peer_z2[d] = p->z2alloc; continue; }
+        z = (char *)b2d_ipc_import(all[d].hz);
+        if (!z) { ok = 0; break; }
+        p->opened[p->nopened++] = z;
+        o = (char *)b2d_ipc_import(all[d].ho);
+        if (!o) { ok = 0; break; }
+        p->opened[p->nopened++] = o;
+        p->flags[d] = z; p->peer_z[d] = z + FLAG_BYTES; p->peer_out[d] = o + all[d].oo;
+        if (z2bytes) {
+            char *z2 = (char *)b2d_ipc_import(all[d].hz2);
+            if (!z2) { ok = 0; break; }
+            p->opened[p->nopened++] = z2;
+            p->peer_z2[d] = z2;
+        }
+    }
+    free(all);
+    return ok;
+}
+
+/* collective verdict on `ok`; doubles as the barrier after which peers may write our flags and buffers */
+static int agree(const fftw_b200_comm *comm, int ok)
+{
+    int d, *every = (int *)calloc((size_t)comm->nranks, sizeof(int));
+    if (!every || comm->allgather(comm->ctx, &ok, every, sizeof ok)) { free(every); return 0; }
+    for (d = 0; d < comm->nranks; ++d) if (!every[d]) ok = 0;
+    free(every);
+    return ok;
 }
 
 /* ------------------------------------------------------------------ planning (mpi/api.c:560-648) */
@@ -152,7 +210,6 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
                                  void *in, void *out, const fftw_b200_comm *comm, int sign, unsigned flags)
 {
     fftw_b200_mpi_plan p;
-    exch mine, *all = NULL;
     int i, d, P, r, ok = 1;
     int64_t R = howmany, alloc;
     size_t cs = csize(prec);
@@ -178,33 +235,7 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
     p->in = in; p->out = out;
     alloc = p->b0 * n[1] * R;
     if (p->b1 * n[0] * R > alloc) alloc = p->b1 * n[0] * R;
-    p->zalloc = (char *)b2d_malloc(FLAG_BYTES + (size_t)(alloc > 0 ? alloc : 1) * cs);
-    memset(&mine, 0, sizeof mine);
-    if (p->zalloc) {
-        p->zbuf = p->zalloc + FLAG_BYTES;
-        b2d_memset(p->zalloc, 0, FLAG_BYTES);
-        b2d_sync();
-        mine.oo = b2d_alloc_offset(out);
-        mine.ok = mine.oo >= 0 && !b2d_ipc_export(p->zalloc, mine.hz) && !b2d_ipc_export((char *)out - mine.oo, mine.ho);
-    }
-    all = (exch *)calloc((size_t)P, sizeof *all);
-    if (!all || comm->allgather(comm->ctx, &mine, all, sizeof mine)) { free(all); fftw_b200_mpi_destroy_plan(p); return NULL; }
-    for (d = 0; d < P; ++d) if (!all[d].ok) ok = 0;            /* all ranks see the same verdict */
-    if (ok) {
-        for (d = 0; d < P && ok; ++d) {
-            if (d == r) { p->flags[d] = p->zalloc; p->peer_z[d] = p->zbuf; p->peer_out[d] = out; continue; }
-            {
-                char *z = (char *)b2d_ipc_import(all[d].hz), *o;
-                if (!z) { ok = 0; break; }
-                p->opened[p->nopened++] = z;
-                o = (char *)b2d_ipc_import(all[d].ho);
-                if (!o) { ok = 0; break; }
-                p->opened[p->nopened++] = o;
-                p->flags[d] = z; p->peer_z[d] = z + FLAG_BYTES; p->peer_out[d] = o + all[d].oo;
-            }
-        }
-    }
-    free(all);
+    ok = setup_peers(p, comm, out, (size_t)(alloc > 0 ? alloc : 1) * cs, 0);
     if (!ok) goto fail_collective;
 
     /* fused plans of dist.c: 3-D, double, one transform, in place, same pointer semantics */
@@ -278,14 +309,7 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
             }
         }
     }
-    {
-        /* collective verdict; doubles as the barrier after which peers may write our flags and buffers */
-        int *every = (int *)calloc((size_t)P, sizeof(int));
-        if (!every || comm->allgather(comm->ctx, &ok, every, sizeof ok)) { free(every); goto fail; }
-        for (d = 0; d < P; ++d) if (!every[d]) ok = 0;
-        free(every);
-    }
-    if (!ok) goto fail;
+    if (!agree(comm, ok)) goto fail;
     return p;
 fail_collective:
     {
@@ -317,6 +341,214 @@ fail:
 DEFINE_API(fftw_b200_mpi_, B2D_F64, fftw_complex)
 DEFINE_API(fftwf_b200_mpi_, B2D_F32, fftwf_complex)
 
+/* ------------------------------------------------------------------ distributed transposes (mpi/api.c:521-556)
+   fftw_mpi_plan_many_transpose: an n0 x n1 matrix of `howmany`-tuples of REAL numbers, rows block-distributed,
+   becomes the n1 x n0 matrix, rows block-distributed (mpi/transpose-alltoall.c:49-100).  One strided copy per
+   destination writes the transposed block straight into the peer's output (in place: through the exchange
+   buffer and a local copy back), then a device-side barrier. */
+static void rproblem(b2_problem *q, int prec, unsigned flags, void *in, void *out)
+{
+    memset(q, 0, sizeof *q);
+    q->prec = prec; q->kind = B2_R2R; q->flags = flags | B2F_ESTIMATE;
+    b2_tensor_init(&q->sz, 0); b2_tensor_init(&q->vecsz, 0);
+    q->in0 = in; q->out0 = out;
+}
+
+static fftw_b200_mpi_plan mktranspose(int prec, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t howmany, ptrdiff_t block0,
+                                      ptrdiff_t block1, void *in, void *out, const fftw_b200_comm *comm, unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    b2_problem q;
+    int d, P, r, ok = 1, inplace = (in == out);
+    size_t rs = prec == B2D_F32 ? 4 : 8;
+    int64_t hm = howmany, alloc;
+    if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || howmany < 1 || !in || !out || block0 || block1) return NULL;
+    P = comm->nranks; r = comm->rank;
+    if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->kind = 2; p->prec = prec; p->rank = r; p->nranks = P;
+    p->n0 = n0; p->n1 = n1; p->R = hm;
+    p->b0 = blk(n0, P); p->b1 = blk(n1, P);
+    p->ln0 = share(n0, P, r); p->ln1 = share(n1, P, r);
+    p->s0 = p->b0 * r < n0 ? p->b0 * r : n0; p->s1 = p->b1 * r < n1 ? p->b1 * r : n1;
+    p->in = in; p->out = out;
+    alloc = p->b1 * n0 * hm;
+    ok = setup_peers(p, comm, out, (size_t)(alloc > 0 ? alloc : 1) * rs, 0);
+    if (ok && p->ln0 > 0) {
+        for (d = 0; d < P && ok; ++d) {
+            /* my rows, column block d -> rank d's [ln1(d)][n0][hm] at column s0 */
+            int64_t l1 = share(n1, P, d);
+            char *dst = (char *)(inplace ? p->peer_z[d] : p->peer_out[d]) + rs * (size_t)(p->s0 * hm);
+            if (!l1) continue;
+            rproblem(&q, prec, flags, (char *)in + rs * (size_t)(p->b1 * d * hm), dst);
+            dim(&q.vecsz, p->ln0, n1 * hm, hm);
+            dim(&q.vecsz, l1, hm, n0 * hm);
+            if (hm > 1) dim(&q.vecsz, hm, 1, 1);
+            p->scatter[d] = b2_mkplan(&q);
+            if (!p->scatter[d]) ok = 0;
+        }
+    }
+    if (ok && inplace && p->ln1 > 0) {
+        rproblem(&q, prec, flags, p->zbuf, out);
+        dim(&q.vecsz, p->ln1 * n0 * hm, 1, 1);
+        p->back[0] = b2_mkplan(&q);
+        if (!p->back[0]) ok = 0;
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_transpose(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t howmany, ptrdiff_t block0,
+                                                     ptrdiff_t block1, double *in, double *out,
+                                                     const fftw_b200_comm *comm, unsigned flags)
+{ return mktranspose(B2D_F64, n0, n1, howmany, block0, block1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftw_b200_mpi_plan_transpose(ptrdiff_t n0, ptrdiff_t n1, double *in, double *out,
+                                                const fftw_b200_comm *comm, unsigned flags)
+{ return mktranspose(B2D_F64, n0, n1, 1, 0, 0, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_transpose(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t howmany, ptrdiff_t block0,
+                                                      ptrdiff_t block1, float *in, float *out,
+                                                      const fftw_b200_comm *comm, unsigned flags)
+{ return mktranspose(B2D_F32, n0, n1, howmany, block0, block1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_transpose(ptrdiff_t n0, ptrdiff_t n1, float *in, float *out,
+                                                 const fftw_b200_comm *comm, unsigned flags)
+{ return mktranspose(B2D_F32, n0, n1, 1, 0, 0, in, out, comm, flags); }
+
+/* ------------------------------------------------------------------ distributed 1-D transform
+   fftw_mpi_plan_dft_1d (mpi/dft-rank1.c:81-148,224-340, mpi/choose-radix.c:50): n = r * m, the "six-step"
+   algorithm with three global transposes.  x is viewed as the r x m matrix [j1][j2] (j = j1 m + j2), rows
+   block-distributed:
+     T1  every rank sends the columns of block d to rank d: Z1 = [j1 (all r)][j2 in my block]   (plain row segments)
+     A   FFT_r along j1 (strided pass over Z1, in place) with the twiddle exp(-2 pi i k1 j2 / n) in its store
+     T2  rows k1 of block d go to rank d: Z2 = [k1 in my block][j2 (all m)]
+     B   FFT_m along the contiguous rows of Z2: element (k1, k2) is X[k1 + r k2]
+     T3  transposing copies: rank d receives [k2 in its block][k1 (all r)] = natural order, rows block-distributed
+         over m (FFTW_MPI_SCRAMBLED_OUT: skipped, the output stays [k1][k2] over this rank's k1 block)
+   Each transpose is a set of strided copies into peer memory followed by a device-side barrier. */
+static int64_t choose_r(int64_t n, int prec)
+{
+    int64_t d, best = -1;
+    int radix[64];
+    for (d = 2; d * d <= n; ++d) {
+        if (n % d) continue;
+        if (d <= b2_max_single_pass(prec) && b2_factorize(d, prec, 0, radix) > 0) best = d;        /* closest to sqrt(n) from below */
+    }
+    return best;
+}
+
+ptrdiff_t fftw_b200_mpi_local_size_1d(ptrdiff_t n0, const fftw_b200_comm *comm, int sign, unsigned flags,
+                                      ptrdiff_t *local_ni, ptrdiff_t *local_i_start,
+                                      ptrdiff_t *local_no, ptrdiff_t *local_o_start)
+{
+    int64_t r, m, br, bm, lr, lm, sr, sm, a, b;
+    int P, k;
+    (void)sign;
+    if (!comm || n0 < 4) return 0;
+    r = choose_r(n0, B2D_F64);
+    if (r < 0) return 0;                       /* n0 must be composite (as in the reference, mpi/dft-rank1.c:285) */
+    m = n0 / r; P = comm->nranks; k = comm->rank;
+    br = blk(r, P); bm = blk(m, P);
+    lr = share(r, P, k); lm = share(m, P, k);
+    sr = br * k < r ? br * k : r; sm = bm * k < m ? bm * k : m;
+    if (local_ni) *local_ni = (ptrdiff_t)(lr * m);
+    if (local_i_start) *local_i_start = (ptrdiff_t)(sr * m);
+    if (flags & FFTW_MPI_SCRAMBLED_OUT) {
+        if (local_no) *local_no = (ptrdiff_t)(lr * m);
+        if (local_o_start) *local_o_start = (ptrdiff_t)(sr * m);
+    } else {
+        if (local_no) *local_no = (ptrdiff_t)(lm * r);
+        if (local_o_start) *local_o_start = (ptrdiff_t)(sm * r);
+    }
+    a = br * m; b = bm * r;
+    return (ptrdiff_t)(a > b ? a : b);
+}
+
+static fftw_b200_mpi_plan mkplan1d(int prec, ptrdiff_t n0, void *in, void *out, const fftw_b200_comm *comm, int sign, unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    b2_problem q;
+    int d, P, k, ok = 1, scrambled = (flags & FFTW_MPI_SCRAMBLED_OUT) != 0;
+    size_t cs = csize(prec);
+    unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
+    int64_t r, m, br, bm, lr, lm, sr, sm;
+    if (!comm || !comm->allgather || n0 < 4 || !in || !out || (sign != -1 && sign != 1)) return NULL;
+    if (flags & (FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_TRANSPOSED_OUT)) return NULL;
+    P = comm->nranks; k = comm->rank;
+    if (P < 1 || P > MAXP || k < 0 || k >= P) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    r = choose_r(n0, prec);
+    if (r < 0) return NULL;
+    m = n0 / r;
+    br = blk(r, P); bm = blk(m, P);
+    lr = share(r, P, k); lm = share(m, P, k);
+    sr = br * k < r ? br * k : r; sm = bm * k < m ? bm * k : m;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->kind = 1; p->prec = prec; p->rank = k; p->nranks = P; p->sign = sign;
+    p->n0 = r; p->n1 = m; p->R = 1; p->ln0 = lr; p->ln1 = lm; p->s0 = sr; p->s1 = sm; p->b0 = br; p->b1 = bm;
+    p->in = in; p->out = out;
+    ok = setup_peers(p, comm, out, (size_t)(r * bm > 0 ? r * bm : 1) * cs, (size_t)(br * m > 0 ? br * m : 1) * cs);
+    if (ok) {
+        for (d = 0; d < P && ok && lr > 0; ++d) {
+            /* T1: my rows, columns of block d -> rank d's Z1 [r][lm(d)] at row sr */
+            int64_t lmd = share(m, P, d), smd = bm * d < m ? bm * d : m;
+            if (!lmd) continue;
+            problem(&q, prec, pflags | B2F_ESTIMATE, (char *)in + cs * (size_t)smd, (char *)p->peer_z[d] + cs * (size_t)(sr * lmd), -1);
+            dim(&q.vecsz, lr, 2 * m, 2 * lmd);
+            dim(&q.vecsz, lmd, 2, 2);
+            p->scatter[d] = b2_mkplan(&q);
+            if (!p->scatter[d]) ok = 0;
+        }
+        if (ok && lm > 0) {
+            /* A: FFT_r down the columns of Z1 [r][lm], in place, twiddle exp(-2 pi i k1 (sm + j2) / n) in the store */
+            problem(&q, prec, pflags, p->zbuf, p->zbuf, sign);
+            dim(&q.sz, r, 2 * lm, 2 * lm);
+            dim(&q.vecsz, lm, 2, 2);
+            q.tw_big_n = n0; q.tw_off = sm;
+            p->local = b2_mkplan(&q);
+            if (!p->local) ok = 0;
+            for (d = 0; d < P && ok; ++d) {
+                /* T2: rows k1 of block d -> rank d's Z2 [lr(d)][m] at column sm */
+                int64_t lrd = share(r, P, d), srd = br * d < r ? br * d : r;
+                if (!lrd) continue;
+                problem(&q, prec, pflags | B2F_ESTIMATE, p->zbuf + cs * (size_t)(srd * lm), (char *)p->peer_z2[d] + cs * (size_t)sm, -1);
+                dim(&q.vecsz, lrd, 2 * lm, 2 * m);
+                dim(&q.vecsz, lm, 2, 2);
+                p->back[d] = b2_mkplan(&q);
+                if (!p->back[d]) ok = 0;
+            }
+        }
+        if (ok && lr > 0) {
+            /* B: FFT_m along the rows of Z2 [lr][m] (scrambled output: straight into `out`) */
+            problem(&q, prec, pflags, p->z2alloc, scrambled ? out : (void *)p->z2alloc, sign);
+            dim(&q.sz, m, 2, 2);
+            dim(&q.vecsz, lr, 2 * m, 2 * m);
+            p->z = b2_mkplan(&q);
+            if (!p->z) ok = 0;
+            for (d = 0; d < P && ok && !scrambled; ++d) {
+                /* T3: columns k2 of block d, transposed -> rank d's out [lm(d)][r] at column sr */
+                int64_t lmd = share(m, P, d), smd = bm * d < m ? bm * d : m;
+                if (!lmd) continue;
+                problem(&q, prec, pflags | B2F_ESTIMATE, p->z2alloc + cs * (size_t)smd, (char *)p->peer_out[d] + cs * (size_t)sr, -1);
+                dim(&q.vecsz, lr, 2 * m, 2);
+                dim(&q.vecsz, lmd, 2, 2 * r);
+                p->t3[d] = b2_mkplan(&q);
+                if (!p->t3[d]) ok = 0;
+            }
+        }
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_1d(ptrdiff_t n0, fftw_complex *in, fftw_complex *out, const fftw_b200_comm *comm,
+                                             int sign, unsigned flags)
+{ return mkplan1d(B2D_F64, n0, in, out, comm, sign, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_1d(ptrdiff_t n0, fftwf_complex *in, fftwf_complex *out, const fftw_b200_comm *comm,
+                                              int sign, unsigned flags)
+{ return mkplan1d(B2D_F32, n0, in, out, comm, sign, flags); }
+
 /* ------------------------------------------------------------------ execution */
 static void run(b2_plan *pl)
 {
@@ -334,6 +566,26 @@ void fftw_b200_mpi_execute(fftw_b200_mpi_plan p)
 {
     int d;
     if (!p) return;
+    if (p->kind == 2) {
+        for (d = 0; d < p->nranks; ++d) run(p->scatter[(p->rank + 1 + d) % p->nranks]);
+        barrier(p);
+        run(p->back[0]);
+        barrier(p);                                     /* nobody overwrites an exchange buffer still being copied back */
+        if (!b2_async_mode) b2d_sync();
+        return;
+    }
+    if (p->kind == 1) {
+        for (d = 0; d < p->nranks; ++d) run(p->scatter[(p->rank + 1 + d) % p->nranks]);      /* T1 */
+        barrier(p);
+        run(p->local);                                                                         /* A */
+        for (d = 0; d < p->nranks; ++d) run(p->back[(p->rank + 1 + d) % p->nranks]);          /* T2 */
+        barrier(p);
+        run(p->z);                                                                             /* B */
+        for (d = 0; d < p->nranks; ++d) run(p->t3[(p->rank + 1 + d) % p->nranks]);            /* T3 */
+        barrier(p);
+        if (!b2_async_mode) b2d_sync();
+        return;
+    }
     /* the peers may still be reading their exchange buffers / writing our slab from the previous call */
     if (p->fused) {
         fftw_b200_dist_execute_stage(p->fused, 0);

@@ -195,6 +195,7 @@ typedef struct {
     int r2r_kind;             /* LOAD_R2R / STORE_R2R */
     int64_t idx_mul;          /* four-step halves: logical index rule for HERMCONJ / TRUNC (b2d_fft_pass.idx_mul) */
     int force_kernel;         /* pass shapes served by exactly one specialised kernel (STORE_R2C_SPLIT): its code */
+    int64_t tw4_off;          /* STORE_TWIDDLE4: global index of batch column 0 (b2d_fft_pass.tw4_off) */
 } b2_ops;
 
 static void fill_geometry(b2d_fft_pass *f, int variant)
@@ -465,6 +466,7 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     }
     if (f->post_op & B2D_STORE_TWIDDLE4) {
         f->big_n = ops.big_n; f->aux_split = ops.tw4_split;
+        f->tw4_off = ops.tw4_off;
         f->tw4_shift = -1;
         if ((ops.big_n & (ops.big_n - 1)) == 0 && (ops.tw4_split & (ops.tw4_split - 1)) == 0) {
             int sh = 0;
@@ -1106,6 +1108,22 @@ static int plan_c2c(b2_plan *p)
         rc = emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_OUT0, 0), &q->vecsz, 1);
         if (rc) return rc;
         return emit_copy(p, q->prec, mkref(BUF_IN1, 0), mkref(BUF_OUT1, 0), &q->vecsz, 1);
+    }
+    if (q->tw_big_n) {
+        /* one strided rank-1 pass with the six-step's twiddle in its store (dist_api.c) */
+        b2_tensor batch;
+        b2_view in, out;
+        b2_ops tw;
+        int64_t L = 1;
+        int radix[64];
+        if (q->sz.rnk != 1 || !b2_factorize(q->sz.d[0].n, q->prec, 0, radix) || !single_pass_fits(q->sz.d[0].n, q->prec)) return -1;
+        memset(&tw, 0, sizeof tw);
+        while (L * L < q->tw_big_n) L <<= 1;
+        tw.post_op = B2D_STORE_TWIDDLE4; tw.big_n = q->tw_big_n; tw.tw4_split = L; tw.tw4_off = q->tw_off;
+        other_dims(q, 0, 0, &batch);
+        in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN1, 0); in.stride = q->sz.d[0].is;
+        out.re = mkref(BUF_OUT0, 0); out.im = mkref(BUF_OUT1, 0); out.stride = q->sz.d[0].os;
+        return emit_fft1d(p, q->prec, q->sz.d[0].n, in, out, &batch, tw, 1, "dft + six-step twiddle");
     }
     /* L2-resident pass pairs.  The pass over the last (contiguous) dim and the pass over one other dim
        only couple elements that share every remaining index, so the two can be run group by group over a

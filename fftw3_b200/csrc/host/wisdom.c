@@ -60,7 +60,7 @@ b2_sig b2_sig_of_pass(const b2d_fft_pass *p, int inplace)
     v[k++] = p->bluestein; v[k++] = p->n_in; v[k++] = p->n_out;
     v[k++] = (p->pre_op & B2D_LOAD_R2R) ? p->r2r_kind + 16 * p->r2r_pair : -1;
     v[k++] = p->is; v[k++] = p->os; v[k++] = inplace;
-    v[k++] = p->load_col; v[k++] = p->store_col; v[k++] = p->idx_mul;
+    v[k++] = p->load_col; v[k++] = p->store_col; v[k++] = p->idx_mul;   /* tw4_off does not change the work */
     for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) { v[k++] = p->bn[i]; v[k++] = p->bis[i]; v[k++] = p->bos[i]; }
     s.h[0] = fnv(0xcbf29ce484222325ULL, v, (size_t)k * sizeof(int64_t));
     s.h[1] = fnv(0x84222325cbf29ce4ULL ^ s.h[0], v, (size_t)k * sizeof(int64_t));

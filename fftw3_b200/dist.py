@@ -113,9 +113,56 @@ def _declare_mpi(lib):
         f = getattr(L, pfx + "plan_many_dft")
         f.restype = P
         f.argtypes = [I, SP, S, S, S, P, P, CP, I, U]
+    L.fftw_b200_mpi_local_size_1d.restype = S
+    L.fftw_b200_mpi_local_size_1d.argtypes = [S, CP, I, U, SP, SP, SP, SP]
+    for pfx in ("fftw_b200_mpi_", "fftwf_b200_mpi_"):
+        f = getattr(L, pfx + "plan_dft_1d")
+        f.restype = P
+        f.argtypes = [S, P, P, CP, I, U]
+        f = getattr(L, pfx + "plan_many_transpose")
+        f.restype = P
+        f.argtypes = [S, S, S, S, S, P, P, CP, U]
     L.fftw_b200_mpi_execute.argtypes = [P]
     L.fftw_b200_mpi_destroy_plan.argtypes = [P]
     L._mpi_declared = True
+
+
+def local_size_1d(lib, n0, comm, sign=B.FFTW_FORWARD, flags=0):
+    """(alloc, local_ni, local_i_start, local_no, local_o_start) of fftw_b200_mpi_local_size_1d"""
+    _declare_mpi(lib)
+    v = [C.c_ssize_t() for _ in range(4)]
+    alloc = lib.lib.fftw_b200_mpi_local_size_1d(n0, C.byref(comm), int(sign), int(flags), *[C.byref(x) for x in v])
+    return (int(alloc),) + tuple(int(x.value) for x in v)
+
+
+class CommPlan1D:
+    """fftw_mpi_plan_dft_1d through the communicator interface (six-step over the ranks)"""
+
+    def __init__(self, lib, n0, comm, in_ptr, out_ptr, prec="d", sign=B.FFTW_FORWARD, flags=B.FFTW_ESTIMATE, scrambled_out=False):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_dft_1d")
+        self.plan = fn(n0, in_ptr, out_ptr, C.byref(comm), int(sign), int(flags) | ((1 << 28) if scrambled_out else 0))
+
+    def execute(self):
+        self.L.fftw_b200_mpi_execute(self.plan)
+
+    def destroy(self):
+        if self.plan:
+            self.L.fftw_b200_mpi_destroy_plan(self.plan)
+            self.plan = None
+
+
+class CommTranspose(CommPlan1D):
+    """fftw_mpi_plan_many_transpose: n0 x n1 matrix of howmany-tuples of reals, rows block-distributed"""
+
+    def __init__(self, lib, n0, n1, comm, in_ptr, out_ptr, howmany=1, prec="d", flags=B.FFTW_ESTIMATE):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_transpose")
+        self.plan = fn(n0, n1, howmany, 0, 0, in_ptr, out_ptr, C.byref(comm), int(flags))
 
 
 class CommPlan:
@@ -560,6 +607,8 @@ def _nvlink_tx_kib(index):
     except (OSError, subprocess.SubprocessError):
         return None
     vals = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    if not vals:
+        _nvlink_tx_kib.raw = out[:400]
     return sum(vals) if vals else None
 
 
@@ -753,6 +802,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                                 "if_serialised_gbs": nv_bytes / (ms * 1e-3) / 1e9, "peak_gbs": 900.0,
                                 "counter_tx_bytes_per_step": (None if tx0 is None or tx1 is None else
                                                               (tx1 - tx0) * 1024.0 / (args.steps + max(3, args.warmup))),
+                                "counter_raw": getattr(_nvlink_tx_kib, "raw", None),
                                 "stage_ms": stage_ms,
                                 "stage_exchange_gbs": (None if not stage_ms else
                                                        [nv_bytes / 2 / (t * 1e-3) / 1e9 for t in stage_ms]),

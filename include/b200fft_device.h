@@ -93,6 +93,8 @@ typedef struct b2d_fft_pass {
     int64_t aux_split;        /* TWIDDLE4: lo-table length L (e = hi*L + lo)          */
     int64_t big_n;            /* TWIDDLE4: N of the enclosing transform               */
     int tw4_shift;            /* log2(aux_split) when big_n and aux_split are powers of two, else -1 */
+    int64_t tw4_off;          /* TWIDDLE4: batch dim 0 index b0 stands for global column b0 + tw4_off (a rank's block
+                                 of the columns of a distributed six-step 1-D transform) */
     double scale;
     /* peer scatter (multi-GPU exchange fused into the pass): when npeer > 0 batch
        dim 2 does not stride the output but selects peer_out[b2], an interleaved

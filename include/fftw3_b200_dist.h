@@ -174,6 +174,31 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_
                                               const fftw_b200_comm *comm, int sign, unsigned flags);
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in,
                                               fftwf_complex *out, const fftw_b200_comm *comm, int sign, unsigned flags);
+/* Distributed 1-D transform of n0 = r * m points (six-step with three global transposes; mpi/dft-rank1.c:81-148,
+ * mpi/api.c:248-352 local_size_1d).  Input: this rank's local_ni consecutive points starting at local_i_start;
+ * output: local_no points starting at local_o_start (the two distributions differ: rows of the r x m view on
+ * input, rows of the m x r view on output).  FFTW_MPI_SCRAMBLED_OUT skips the last transpose (output element
+ * X[k1 + r k2] stays at [k1][k2] in this rank's k1 block); SCRAMBLED_IN is not supported (NULL).  n0 must be
+ * composite with a smooth factor <= the one-pass limit, else 0 / NULL (as the reference, n0 must be composite). */
+ptrdiff_t fftw_b200_mpi_local_size_1d(ptrdiff_t n0, const fftw_b200_comm *comm, int sign, unsigned flags,
+                                      ptrdiff_t *local_ni, ptrdiff_t *local_i_start,
+                                      ptrdiff_t *local_no, ptrdiff_t *local_o_start);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_1d(ptrdiff_t n0, fftw_complex *in, fftw_complex *out, const fftw_b200_comm *comm,
+                                             int sign, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_1d(ptrdiff_t n0, fftwf_complex *in, fftwf_complex *out, const fftw_b200_comm *comm,
+                                              int sign, unsigned flags);
+/* Distributed transpose of an n0 x n1 matrix of howmany-tuples of reals (mpi/api.c:521-556): rows block-distributed
+ * on input ([local_n0][n1][howmany]) and on output ([local_n1][n0][howmany]); in == out allowed. */
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_transpose(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t howmany, ptrdiff_t block0,
+                                                     ptrdiff_t block1, double *in, double *out,
+                                                     const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_transpose(ptrdiff_t n0, ptrdiff_t n1, double *in, double *out,
+                                                const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_transpose(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t howmany, ptrdiff_t block0,
+                                                      ptrdiff_t block1, float *in, float *out,
+                                                      const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_transpose(ptrdiff_t n0, ptrdiff_t n1, float *in, float *out,
+                                                 const fftw_b200_comm *comm, unsigned flags);
 /* One distributed transform, collective; returns when this rank's result is complete (or, with
  * fftw_b200_set_async(1), once everything is enqueued on the launch stream). */
 void fftw_b200_mpi_execute(fftw_b200_mpi_plan p);

@@ -181,6 +181,58 @@ def main():
             good = err < (3e-6 if prec == "f" else 5e-15)
             ok &= good
             print("dist check comm-api %s P=%d %s rel L2 %.2e %s" % (n, world, kw, err, "OK" if good else "FAIL"), flush=True)
+    # distributed 1-D transform (six-step) and distributed transposes
+    for n0, kw in [(1 << 20, {}), (1 << 20, {"sign": 1}), (1000 * 1024, {}), (1 << 16, {"prec": "f"}), (6 * 35 * 11, {}),
+                   (1 << 18, {"inplace": True})]:
+        prec, sign, inplace = kw.get("prec", "d"), kw.get("sign", -1), kw.get("inplace", False)
+        cdt, tdt = (np.complex64, torch.complex64) if prec == "f" else (np.complex128, torch.complex128)
+        rng = np.random.default_rng(17)
+        x = (rng.uniform(-0.5, 0.5, n0) + 1j * rng.uniform(-0.5, 0.5, n0)).astype(cdt)
+        ref = O.dft(x, sign=sign, rank=1) if rank == 0 else None
+        alloc, lni, si, lno, so = D.local_size_1d(lib, n0, comm, sign, 0)
+        a = torch.zeros(max(alloc, 1), dtype=tdt, device="cuda")
+        b = a if inplace else torch.zeros(max(alloc, 1), dtype=tdt, device="cuda")
+        a[:lni] = torch.from_numpy(x[si:si + lni].copy()).cuda()
+        pl = D.CommPlan1D(lib, n0, comm, a.data_ptr(), b.data_ptr(), prec=prec, sign=sign)
+        assert pl.plan, "fftw_b200_mpi_plan_dft_1d returned NULL"
+        pl.execute()
+        torch.cuda.synchronize()
+        mine = b[:lno].cpu().numpy()
+        pl.destroy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (so, mine))
+        if rank == 0:
+            got = np.zeros(n0, cdt)
+            for start, arr in gathered:
+                got[start:start + len(arr)] = arr
+            err = O.rel_l2(got, ref)
+            good = err < (4e-6 if prec == "f" else 2e-14)
+            ok &= good
+            print("dist check 1-d six-step n=%d P=%d %s rel L2 %.2e %s" % (n0, world, kw, err, "OK" if good else "FAIL"), flush=True)
+    for n0, n1, hm, inplace in [(96, 80, 1, False), (45, 64, 3, False), (128, 64, 1, True), (1024, 2048, 2, False)]:
+        full = np.arange(n0 * n1 * hm, dtype=np.float64).reshape(n0, n1, hm)
+        b0, b1 = -(-n0 // world), -(-n1 // world)
+        ln0, s0 = max(0, min(b0, n0 - b0 * rank)), min(b0 * rank, n0)
+        ln1, s1 = max(0, min(b1, n1 - b1 * rank)), min(b1 * rank, n1)
+        cnt = max(b0 * n1, b1 * n0) * hm
+        a = torch.zeros(max(cnt, 1), dtype=torch.float64, device="cuda")
+        b = a if inplace else torch.zeros(max(cnt, 1), dtype=torch.float64, device="cuda")
+        a[:ln0 * n1 * hm] = torch.from_numpy(full[s0:s0 + ln0].reshape(-1).copy()).cuda()
+        pl = D.CommTranspose(lib, n0, n1, comm, a.data_ptr(), b.data_ptr(), howmany=hm)
+        assert pl.plan, "fftw_b200_mpi_plan_many_transpose returned NULL"
+        pl.execute()
+        torch.cuda.synchronize()
+        mine = b[:ln1 * n0 * hm].cpu().numpy().reshape(ln1, n0, hm)
+        pl.destroy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (s1, mine))
+        if rank == 0:
+            got = np.zeros((n1, n0, hm))
+            for start, arr in gathered:
+                got[start:start + arr.shape[0]] = arr
+            good = np.array_equal(got, full.transpose(1, 0, 2))
+            ok &= good
+            print("dist check transpose %dx%dx%d P=%d inplace=%d %s" % (n0, n1, hm, world, inplace, "OK" if good else "FAIL"), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

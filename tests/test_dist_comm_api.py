@@ -138,3 +138,110 @@ def test_local_size_matches_the_reference_distribution(emu_lib):
             tot0 += ln0
             tot1 += ln1
         assert tot0 == 10 and tot1 == 7
+
+
+def _threads(P, fn):
+    tc = ThreadComm(P)
+    errs, res = [], [None] * P
+
+    def main(r):
+        try:
+            res[r] = fn(r, tc.comm(r))
+        except BaseException as e:       # noqa
+            errs.append((r, repr(e)))
+            tc.bar.abort()
+    th = [threading.Thread(target=main, args=(r,)) for r in range(P)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not errs, errs
+    return res
+
+
+@pytest.mark.parametrize("n0,P,kw", [
+    (4096, 2, {}), (4096, 2, {"sign": 1}), (1000, 3, {}), (6 * 35, 4, {}), (4096, 2, {"scrambled": True}),
+    (2048, 2, {"prec": "f"}), (1024, 2, {"inplace": True}), (34 * 3, 2, {}),
+])
+def test_distributed_1d_six_step(emu_lib, n0, P, kw):
+    """fftw_mpi_plan_dft_1d (mpi/dft-rank1.c:81-148): input block-distributed in natural order, output
+    block-distributed in natural order (or [k1][k2]-scrambled), against the oracle."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    prec, sign, scr, inplace = kw.get("prec", "d"), kw.get("sign", -1), kw.get("scrambled", False), kw.get("inplace", False)
+    cdt = np.complex64 if prec == "f" else np.complex128
+    isz = np.dtype(cdt).itemsize
+    rng = np.random.default_rng(5)
+    x = (rng.uniform(-0.5, 0.5, n0) + 1j * rng.uniform(-0.5, 0.5, n0)).astype(cdt)
+    ref = O.dft(x, sign=sign, rank=1)
+
+    def rank_main(r, comm):
+        alloc, lni, si, lno, so = D.local_size_1d(lib, n0, comm, sign, (1 << 28) if scr else 0)
+        assert alloc >= max(lni, lno)
+        a = L.fftw_b200_device_malloc(max(alloc, 1) * isz)
+        b = a if inplace else L.fftw_b200_device_malloc(max(alloc, 1) * isz)
+        view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(alloc, 1) * isz,)).view(cdt)
+        view(a)[:lni] = x[si:si + lni]
+        pl = D.CommPlan1D(lib, n0, comm, a, b, prec=prec, sign=sign, scrambled_out=scr)
+        assert pl.plan, "plan_dft_1d returned NULL"
+        pl.execute()
+        out = (so, view(b)[:lno].copy())
+        pl.destroy()
+        L.fftw_b200_device_free(a)
+        if not inplace:
+            L.fftw_b200_device_free(b)
+        return out
+
+    res = _threads(P, rank_main)
+    got = np.zeros(n0, cdt)
+    for so, arr in res:
+        got[so:so + len(arr)] = arr
+    if scr:
+        # scrambled: position k1 * m + k2 holds X[k1 + r k2]; recover r from the first rank's block
+        r_ = None
+        for cand in range(2, n0):
+            if n0 % cand == 0:
+                m_ = n0 // cand
+                y = got.reshape(cand, m_).T.reshape(-1)
+                if O.rel_l2(y, ref) < 1e-5:
+                    r_ = cand
+                    got = y
+                    break
+        assert r_ is not None, "no r x m un-scrambling matches"
+    assert O.rel_l2(got, ref) <= (3e-6 if prec == "f" else 2e-14), (n0, P, kw)
+
+
+@pytest.mark.parametrize("n0,n1,P,hm,inplace,prec", [(12, 10, 2, 1, False, "d"), (7, 9, 3, 2, False, "d"), (8, 6, 2, 1, True, "d"),
+                                                     (5, 16, 4, 3, True, "f"), (64, 48, 2, 1, False, "d")])
+def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec):
+    """fftw_mpi_plan_many_transpose (mpi/api.c:521-556): bit-exact"""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    rdt = np.float32 if prec == "f" else np.float64
+    isz = np.dtype(rdt).itemsize
+    full = np.arange(n0 * n1 * hm, dtype=rdt).reshape(n0, n1, hm)
+
+    def rank_main(r, comm):
+        b0, b1 = -(-n0 // P), -(-n1 // P)
+        ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
+        ln1, s1 = max(0, min(b1, n1 - b1 * r)), min(b1 * r, n1)
+        cnt = max(b0 * n1, b1 * n0) * hm
+        a = L.fftw_b200_device_malloc(max(cnt, 1) * isz)
+        b = a if inplace else L.fftw_b200_device_malloc(max(cnt, 1) * isz)
+        view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(cnt, 1) * isz,)).view(rdt)
+        view(a)[:ln0 * n1 * hm] = full[s0:s0 + ln0].reshape(-1)
+        pl = D.CommTranspose(lib, n0, n1, comm, a, b, howmany=hm, prec=prec)
+        assert pl.plan
+        pl.execute()
+        out = (s1, view(b)[:ln1 * n0 * hm].copy().reshape(ln1, n0, hm))
+        pl.destroy()
+        L.fftw_b200_device_free(a)
+        if not inplace:
+            L.fftw_b200_device_free(b)
+        return out
+
+    res = _threads(P, rank_main)
+    got = np.zeros((n1, n0, hm), rdt)
+    for s1, arr in res:
+        got[s1:s1 + arr.shape[0]] = arr
+    assert np.array_equal(got, full.transpose(1, 0, 2))
