@@ -164,6 +164,20 @@ int b2d_memcpy_d2d(void *d, const void *s, size_t n)
     cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g_stream);
     return e == cudaSuccess ? 0 : fail(e, "memcpy d2d");
 }
+int b2d_memcpy2d_async(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (!width || !height) return 0;
+    if (width == dpitch && width == spitch)
+        e = cudaMemcpyAsync(d, s, width * height, cudaMemcpyDeviceToDevice, st);
+    else if (dpitch < ((size_t)1 << 31) && spitch < ((size_t)1 << 31))
+        e = cudaMemcpy2DAsync(d, dpitch, s, spitch, width, height, cudaMemcpyDeviceToDevice, st);
+    else
+        for (size_t r = 0; r < height && e == cudaSuccess; ++r)
+            e = cudaMemcpyAsync((char *)d + r * dpitch, (const char *)s + r * spitch, width, cudaMemcpyDeviceToDevice, st);
+    return e == cudaSuccess ? 0 : fail(e, "memcpy 2d");
+}
 int b2d_memset(void *d, int byte, size_t n)
 {
     cudaError_t e = cudaMemsetAsync(d, byte, n, g_stream);

@@ -9,12 +9,14 @@
  * + local transpose (mpi/transpose-alltoall.c:49-100).  Here both local
  * transposes are folded into FFT passes and the exchange into their stores:
  *   stage 0  Y: FFT along n1, in place (strided pass)
- *            X: FFT along n2 (contiguous rows), stored straight into the block
- *               layout of the exchange -- [dest][i0][k1'][k2] -- i.e. into the
- *               peers' buffers over NVLink, or into a local send buffer.
- *               The slab is cut into chunks of planes: X of chunk c (NVLink
- *               bound) runs on a side stream while Y of chunk c+1 (HBM bound)
- *               runs on the main stream.
+ *            X: FFT along n2 (contiguous rows).  The slab is cut into chunks of planes and the
+ *               block layout of the exchange -- [dest][i0][k1'][k2] -- is reached either
+ *               (default, device-resident slabs) by the copy engines: X of chunk c runs in place
+ *               at full speed (the rows this rank keeps go straight into its own exchange
+ *               buffer), one strided copy per peer then moves the chunk's blocks over NVLink on
+ *               side streams while the SMs are already on Y/X of chunk c+1, so no SM ever waits
+ *               for a link; or (FFTW3_B200_DIST_EXCHANGE=stores) by X's own stores into the
+ *               peers' buffers, X of chunk c on a side stream next to Y of chunk c+1.
  *   stage 1  Z: FFT along n0 reading the received blocks, which already form
  *               [n0][local_n1][n2]; written in place (natural order follows) or
  *               as [local_n1][n0][n2] into `local` (TRANSPOSED_OUT)
@@ -44,6 +46,12 @@ struct fftw_b200_dist_plan_s {
     int zcopy;               /* real-data plans whose dim-0 pass cannot split its stores by row (Bluestein / Rader /
                                 multi-pass n0): z[] transforms in place, g[s] then copies the rows to their owner s */
     b2_plan *pre, *post;     /* real-data plans: local r2c rows before stage 0 / local c2r rows as the last stage */
+    /* stage-0 exchange by the copy engines (see mkdist): X runs in place at full speed, the blocks then
+       travel as 2-D copies on side streams while the SMs are already on the next chunk */
+    int ce;
+    int64_t ce_n1, ce_n2, ce_ln0;
+    double *ce_local;
+    void *ce_targets[B2D_MAX_PEERS];
 };
 typedef struct fftw_b200_dist_plan_s *dplan;
 
@@ -121,6 +129,17 @@ static void limit_grid(b2_plan *pl, int limit)
     }
 }
 
+/* How the first exchange travels.  "stores": fused into the stores of the X pass (one kernel computes and
+   scatters; its CTAs wait on NVLink and hold their SMs while they do).  "copy": X stores locally and the copy
+   engines move the blocks, so no SM ever waits for a link; costs no extra HBM traffic for the block a rank
+   keeps (X writes that one straight into its own exchange buffer) and one extra read of the rest. */
+static int exchange_by_copy(void)
+{
+    const char *e = getenv("FFTW3_B200_DIST_EXCHANGE");
+    if (e && !strcmp(e, "stores")) return 0;
+    return 1;
+}
+
 static int chunks_for(int64_t n)
 {
     const char *e = getenv("FFTW3_B200_DIST_CHUNKS");
@@ -171,6 +190,12 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
     p->nranks = nranks; p->rank = rank;
     if (out_targets && (pull_sources || nranks > B2D_MAX_PEERS || b2d_pointer_is_device(zbuf) != 1)) { free(p); return NULL; }
     p->nstages = pull_sources ? 3 : 2;
+    p->ce = nranks > 1 && nranks <= B2D_MAX_PEERS && exchange_by_copy() && b2d_pointer_is_device(local) == 1
+            && b2d_pointer_is_device(push_targets[rank]) == 1;
+    if (p->ce) {
+        p->ce_n1 = n1; p->ce_n2 = n2; p->ce_ln0 = ln0; p->ce_local = (double *)local;
+        for (d = 0; d < nranks; ++d) p->ce_targets[d] = push_targets[d];
+    }
     p->c0 = ln0 > 0 ? chunks_for(ln0) : 1;
     p->c1 = pull_sources ? chunks_for(b1) : 1;     /* from the block size: identical on every rank */
     p->y = (b2_plan **)calloc((size_t)p->c0, sizeof(b2_plan *));
@@ -190,6 +215,29 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
         set_ptrs(&q, lin, lin, sign);
         p->y[c] = b2_mkplan(&q);
         if (!p->y[c]) goto fail;
+        if (p->ce) {
+            /* X by pieces: the rows of this rank's own block go straight into its exchange buffer, the rows of
+               the blocks before / after it are transformed in place and handed to the copy engines */
+            int64_t l1 = share(n1, nranks, rank), first[3], count[3];
+            int k, slot = 0;
+            first[0] = rank * b1; count[0] = l1;
+            first[1] = 0; count[1] = rank * b1 < n1 ? rank * b1 : n1;
+            first[2] = rank * b1 + l1; count[2] = n1 - first[2];
+            for (k = 0; k < 3; ++k) {
+                b2_plan *xp;
+                if (count[k] <= 0 || cnt <= 0) continue;
+                init_problem(&q, flags);
+                dim(&q.sz, n2, 2, 2);
+                dim(&q.vecsz, cnt, 2 * n1 * n2, k == 0 ? 2 * l1 * n2 : 2 * n1 * n2);
+                dim(&q.vecsz, count[k], 2 * n2, 2 * n2);
+                set_ptrs(&q, lin + 2 * first[k] * n2,
+                         k == 0 ? (double *)push_targets[rank] + 2 * lo * l1 * n2 : lin + 2 * first[k] * n2, sign);
+                xp = b2_mkplan(&q);
+                if (!xp) goto fail;
+                p->x[c * nranks + slot++] = xp;      /* nranks >= 2 slots; at most 2 pieces are non-empty when nranks == 2 */
+            }
+            continue;
+        }
         /* X: FFT along n2, rows (i0, k1 in block d) -> push_targets[d] as [i0][k1'][k2] */
         for (d = 0; d < nranks; ++d) {
             int64_t l1 = share(n1, nranks, d);
@@ -510,6 +558,7 @@ fail:
 ptrdiff_t fftw_b200_ipc_offset(void *devptr) { return (ptrdiff_t)b2d_alloc_offset(devptr); }
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
+int fftw_b200_dist_exchange_by_copy(const dplan p) { return p->ce; }
 int fftw_b200_dist_num_chunks(const dplan p, int stage) { return stage == 0 ? p->c0 : p->c1; }
 
 static void run(b2_plan *pl)
@@ -538,6 +587,22 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
         void *aux = b2d_aux_stream(0);
         if (c == 0) run(p->pre);
         run(p->y[c]);
+        if (p->ce) {
+            int64_t n1 = p->ce_n1, n2 = p->ce_n2, b1 = blk(n1, p->nranks);
+            int64_t lo = p->ce_ln0 * c / p->c0, cnt = p->ce_ln0 * (c + 1) / p->c0 - lo;
+            for (d = 0; d < p->nranks && d < 3; ++d) run(p->x[c * p->nranks + d]);
+            for (d = 1; d < p->nranks && cnt > 0; ++d) {
+                int t = (p->rank + d) % p->nranks;
+                int64_t l1 = share(n1, p->nranks, t);
+                void *cs = b2d_aux_stream(2 + (d - 1) % 6);
+                if (l1 <= 0) continue;
+                if (cs) b2d_stream_wait_stream(cs, mainst);
+                b2d_memcpy2d_async((double *)p->ce_targets[t] + 2 * lo * l1 * n2, (size_t)(l1 * n2) * sizeof(C),
+                                   p->ce_local + 2 * (lo * n1 + t * b1) * n2, (size_t)(n1 * n2) * sizeof(C),
+                                   (size_t)(l1 * n2) * sizeof(C), (size_t)cnt, cs ? cs : mainst);
+            }
+            return;
+        }
         if (aux) { b2d_stream_wait_stream(aux, mainst); prev = b2d_push_stream(aux); }
         if (p->x_fused[c]) run(p->x[c * p->nranks]);
         else for (d = 0; d < p->nranks; ++d) run(p->x[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
@@ -559,7 +624,7 @@ void fftw_b200_dist_join(const dplan p)
     void *mainst = b2d_get_stream();
     int i;
     (void)p;
-    for (i = 0; i < 2; ++i) {
+    for (i = 0; i < 8; ++i) {
         void *aux = b2d_aux_stream(i);
         if (aux) b2d_stream_wait_stream(mainst, aux);
     }

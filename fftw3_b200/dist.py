@@ -50,6 +50,7 @@ def _declare(lib):
     L.fftw_b200_dist_num_stages.argtypes = [P]
     L.fftw_b200_dist_execute_stage.argtypes = [P, I]
     L.fftw_b200_dist_num_chunks.argtypes = [P, I]
+    L.fftw_b200_dist_exchange_by_copy.argtypes = [P]
     L.fftw_b200_dist_execute_chunk.argtypes = [P, I, I]
     L.fftw_b200_dist_join.argtypes = [P]
     L.fftw_b200_dist_destroy_plan.argtypes = [P]
@@ -765,6 +766,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                "api": "fftw3_b200.dist.SlabPlan3D.execute on pinned host slabs (one per rank)"}
     lib.lib.fftw_b200_set_async(0)
     pushed = plan.push
+    by_copy = bool(lib.lib.fftw_b200_dist_exchange_by_copy(plan.plan))
     check = None
     if impulse_expected is not None and not getattr(args, "no_check", False):
         check = _self_check_slab(lib, n, world, rank, local, plan, flags, exchange, impulse_expected)
@@ -790,7 +792,9 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d^3 c2c double in place, forward, slab-decomposed over %d GPUs, natural-order "
                                "output (two exchanges)" % (n, world),
-                   "exchange": exchange + (", both exchanges fused into pass stores (no gather stage)" if pushed
+                   "exchange": exchange + ((", first exchange = copy engines under the next chunk's transforms, second "
+                                            "fused into the dim-0 pass's stores (no gather stage)" if by_copy else
+                                            ", both exchanges fused into pass stores (no gather stage)") if pushed
                                            else ", second exchange = gather stage"), "l2": "slabs are larger than L2, no flush needed",
                    "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
                    "transposed_out_ms_per_step": ms_t,
@@ -806,7 +810,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                                 "stage_ms": stage_ms,
                                 "stage_exchange_gbs": (None if not stage_ms else
                                                        [nv_bytes / 2 / (t * 1e-3) / 1e9 for t in stage_ms]),
-                                "note": "each of the two stages pushes sent_bytes/2 over NVLink inside a pass; "
+                                "note": "each of the two stages moves sent_bytes/2 over NVLink; "
                                         "stage_exchange_gbs = that / the stage's time (a lower bound of the link rate "
                                         "while the store pass runs)"}},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "check": check,

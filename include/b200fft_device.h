@@ -192,6 +192,8 @@ void b2d_free_host(void *p);
 int  b2d_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int  b2d_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int  b2d_memcpy_d2d(void *dst, const void *src, size_t bytes);
+/* `height` rows of `width` bytes between device (or peer-mapped) arrays, enqueued on `stream` for the copy engines */
+int  b2d_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
 int  b2d_memset(void *dst, int byte, size_t bytes);
 int  b2d_sync(void);
 void b2d_set_stream(void *cuda_stream);  /* NULL = legacy default stream              */

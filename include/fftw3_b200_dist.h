@@ -98,6 +98,10 @@ void fftw_b200_dist_execute_stage(const fftw_b200_dist_plan p, int stage);
  * and finally fftw_b200_dist_join(p): the gather of chunk c (side stream, NVLink
  * bound) then overlaps the dim-0 transforms of chunk c+1. */
 int  fftw_b200_dist_num_chunks(const fftw_b200_dist_plan p, int stage);
+/* how the first exchange of this plan travels: 1 = the copy engines move the blocks of a finished chunk while the SMs
+ * transform the next one (default for device-resident slabs), 0 = fused into the stores of the row pass
+ * (FFTW3_B200_DIST_EXCHANGE=stores, and every plan whose arrays live on the host) */
+int  fftw_b200_dist_exchange_by_copy(const fftw_b200_dist_plan p);
 void fftw_b200_dist_execute_chunk(const fftw_b200_dist_plan p, int stage, int chunk);
 void fftw_b200_dist_join(const fftw_b200_dist_plan p);
 void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);

@@ -152,6 +152,11 @@ void b2d_free_host(void *p) { free(p); }
 int b2d_memcpy_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int b2d_memcpy_d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int b2d_memcpy_d2d(void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }
+int b2d_memcpy2d_async(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, void *)
+{
+    for (size_t r = 0; r < height; ++r) memmove((char *)d + r * dpitch, (const char *)s + r * spitch, width);
+    return 0;
+}
 int b2d_memset(void *d, int b, size_t n) { memset(d, b, n); return 0; }
 int b2d_sync(void) { return 0; }
 void b2d_set_stream(void *) {}
