@@ -133,11 +133,22 @@ static void limit_grid(b2_plan *pl, int limit)
    scatters; its CTAs wait on NVLink and hold their SMs while they do).  "copy": X stores locally and the copy
    engines move the blocks, so no SM ever waits for a link; costs no extra HBM traffic for the block a rank
    keeps (X writes that one straight into its own exchange buffer) and one extra read of the rest. */
-static int exchange_by_copy(void)
+static int exchange_by_copy(int nranks)
 {
     const char *e = getenv("FFTW3_B200_DIST_EXCHANGE");
     if (e && !strcmp(e, "stores")) return 0;
-    return 1;
+    if (e && !strcmp(e, "copy")) return 1;
+    /* Measured on B200s behind NVSwitch (profiles/r02_dist_exchange_modes.log): with one peer the copy engines
+       keep up with the links and stage 0 becomes HBM-bound (8.27 vs 8.96 ms at 1024^3); with 3 or 7 peers their
+       strided copies reach only ~450 GB/s against ~700 for the pass's own stores, so the fused stores stay. */
+    return nranks == 2;
+}
+
+static int copy_pieces(int nranks)
+{
+    const char *e = getenv("FFTW3_B200_DIST_COPY_SPLIT");
+    int k = e ? atoi(e) : 1;             /* more streams per block bought nothing (same log) */
+    return k < 1 ? 1 : k > 6 ? 6 : k;
 }
 
 static int chunks_for(int64_t n)
@@ -190,7 +201,7 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
     p->nranks = nranks; p->rank = rank;
     if (out_targets && (pull_sources || nranks > B2D_MAX_PEERS || b2d_pointer_is_device(zbuf) != 1)) { free(p); return NULL; }
     p->nstages = pull_sources ? 3 : 2;
-    p->ce = nranks > 1 && nranks <= B2D_MAX_PEERS && exchange_by_copy() && b2d_pointer_is_device(local) == 1
+    p->ce = nranks > 1 && nranks <= B2D_MAX_PEERS && exchange_by_copy(nranks) && b2d_pointer_is_device(local) == 1
             && b2d_pointer_is_device(push_targets[rank]) == 1;
     if (p->ce) {
         p->ce_n1 = n1; p->ce_n2 = n2; p->ce_ln0 = ln0; p->ce_local = (double *)local;
@@ -592,14 +603,20 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
             int64_t lo = p->ce_ln0 * c / p->c0, cnt = p->ce_ln0 * (c + 1) / p->c0 - lo;
             for (d = 0; d < p->nranks && d < 3; ++d) run(p->x[c * p->nranks + d]);
             for (d = 1; d < p->nranks && cnt > 0; ++d) {
-                int t = (p->rank + d) % p->nranks;
+                int t = (p->rank + d) % p->nranks, k;
                 int64_t l1 = share(n1, p->nranks, t);
-                void *cs = b2d_aux_stream(2 + (d - 1) % 6);
+                /* one copy engine does not fill the links: cut the planes of a block over several streams */
+                int pieces = copy_pieces(p->nranks);
                 if (l1 <= 0) continue;
-                if (cs) b2d_stream_wait_stream(cs, mainst);
-                b2d_memcpy2d_async((double *)p->ce_targets[t] + 2 * lo * l1 * n2, (size_t)(l1 * n2) * sizeof(C),
-                                   p->ce_local + 2 * (lo * n1 + t * b1) * n2, (size_t)(n1 * n2) * sizeof(C),
-                                   (size_t)(l1 * n2) * sizeof(C), (size_t)cnt, cs ? cs : mainst);
+                if (pieces > cnt) pieces = (int)cnt;
+                for (k = 0; k < pieces; ++k) {
+                    int64_t a = cnt * k / pieces, b = cnt * (k + 1) / pieces;
+                    void *cs = b2d_aux_stream(2 + ((d - 1) * pieces + k) % 6);
+                    if (cs) b2d_stream_wait_stream(cs, mainst);
+                    b2d_memcpy2d_async((double *)p->ce_targets[t] + 2 * (lo + a) * l1 * n2, (size_t)(l1 * n2) * sizeof(C),
+                                       p->ce_local + 2 * ((lo + a) * n1 + t * b1) * n2, (size_t)(n1 * n2) * sizeof(C),
+                                       (size_t)(l1 * n2) * sizeof(C), (size_t)(b - a), cs ? cs : mainst);
+                }
             }
             return;
         }
