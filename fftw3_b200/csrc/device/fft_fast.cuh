@@ -209,7 +209,10 @@ struct FastCfg {
     static constexpr int MINB__ = (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) > 0 ? (MINB_ < BY_THREADS ? MINB_ : BY_THREADS) : 1;
     // flavor 1: cap registers for as many resident CTAs as shared memory allows; strided kernels of 256 threads: keep
     // the two CTAs per SM that overlap each other's load and compute phases (cap 128 registers)
-    static constexpr int MINB = FLAVOR == 1 ? MINB__ : ((COL && THREADS <= 256 && BY_SMEM >= 2 && sizeof(T) == 8 && FLAVOR != 9) ? 2 : 1);
+    // r2r line kernels (flavor 9, ROW) of 256 threads: one CTA per SM leaves every phase (staged loads, three
+    // exchanges, POST map) exposed -- 150 registers uncapped, 248 us for 4096 x 4096 REDFT10 rows against 167 with
+    // two lines pairs per CTA (profiles/r02_c5b_pieces.txt); capped at 128 two CTAs overlap
+    static constexpr int MINB = FLAVOR == 1 ? MINB__ : (((COL ? FLAVOR != 9 : FLAVOR == 9) && THREADS <= 256 && BY_SMEM >= 2 && sizeof(T) == 8) ? 2 : 1);
     static_assert(E * R1 * R2 == N, "radices must multiply to N");
     static_assert(E % R1 == 0 && E % R2 == 0, "later radices must divide the per-thread element count");
     static_assert(TPX % E == 0 || R2 == 1, "stage-2 twiddle index must be thread-constant");
@@ -351,8 +354,32 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
         if (FLAVOR == 9) {
             if (!p.r2r_pair) return;
             __syncthreads();
-            if (!valid) return;
             const cplx<T> *qt = reinterpret_cast<const cplx<T> *>(p.aux0);
+            if (!COL && p.store_col && p.pair_os == 1 && p.bos[0] == 2 && !((p.os | p.bos[1] | p.bos[2]) & 1) &&
+                !(reinterpret_cast<uintptr_t>(p.out_re) % (2 * sizeof(T)))) {
+                // lines stored transposed: element k of the tile's 2 * TPB neighbouring lines is one contiguous
+                // piece of the output.  Every thread takes whole pieces (all lines of a k) and writes each pair
+                // of lines as one vector, piece by piece -- full sectors instead of one scalar per sector.
+                T *ob = reinterpret_cast<T *>(p.out_re) + (c.tile0 * TPB) * p.bos[0] + c.b1 * p.bos[1] + c.b2 * p.bos[2];
+                for (int k = tid; k < N; k += Cfg::THREADS) {
+#pragma unroll
+                    for (int tt = 0; tt < TPB; ++tt) {
+                        if (c.tile0 * TPB + tt >= p.bn[0]) break;
+                        cplx<T> u, v;
+                        b2::r2r_unpack_pair<T>(sm[tt * pitch_c(N) + padk_c(k)], sm[tt * pitch_c(N) + padk_c(k ? N - k : 0)], u, v);
+                        b2::StashOut<T> sa, sb;
+                        sa.cnt = sb.cnt = 0;
+                        b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, u, qt, sa);
+                        b2::r2r_post_scatter<T>(r2r_kind, p.n_out, k, v, qt, sb);
+                        for (int w = 0; w < sa.cnt; ++w) {
+                            cplx<T> o; o.x = sa.val[w]; o.y = sb.val[w];
+                            st_plain(reinterpret_cast<cplx<T> *>(ob + (int64_t)sa.idx[w] * p.os + 2 * tt), o);
+                        }
+                    }
+                }
+                return;
+            }
+            if (!valid) return;
             b2::RealLineOut<T> ya = { reinterpret_cast<T *>(p.out_re) + boff_out, p.os };
             b2::RealLineOut<T> yb = { reinterpret_cast<T *>(p.out_re) + boff_out + p.pair_os, p.os };
 #pragma unroll
@@ -431,6 +458,34 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
         const int nl = p.r2r_pair ? 2 : 1, nin = p.n_in;
         const int total = TPB * nl * nin;
         const T *gbase = reinterpret_cast<const T *>(p.in_re) + c.b1 * p.bis[1] + c.b2 * p.bis[2];
+        // lines of an even number of reals at even offsets: whole vectors (two reals), sixteen in flight -- the
+        // tile of a 4096-point double pass arrives in ONE round trip instead of four
+        const bool vec = !((nin | p.bis[0] | p.bis[1] | p.bis[2] | (p.r2r_pair ? p.pair_is : 0)) & 1) &&
+                         !(reinterpret_cast<uintptr_t>(p.in_re) % (2 * sizeof(T)));
+        if (vec) {
+            const int nin2 = nin / 2, total2 = total / 2;
+            const cplx<T> *g2 = reinterpret_cast<const cplx<T> *>(gbase);
+            cplx<T> *raw2 = reinterpret_cast<cplx<T> *>(raw);
+            for (int base = 0; base < total2; base += 16 * Cfg::THREADS) {
+                cplx<T> v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * Cfg::THREADS + tid;
+                    v[u].x = T(0); v[u].y = T(0);
+                    if (idx < total2) {
+                        const int tt = idx / (nl * nin2), rem = idx - tt * (nl * nin2);
+                        const int ln = rem / nin2, e = rem - ln * nin2;
+                        const int64_t bb = c.tile0 * TPB + tt;
+                        if (bb < p.bn[0]) v[u] = ld_stream(g2 + (bb * p.bis[0] + (ln ? p.pair_is : 0)) / 2 + e);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = base + u * Cfg::THREADS + tid;
+                    if (idx < total2) raw2[idx] = v[u];
+                }
+            }
+        } else
         for (int base = 0; base < total; base += 8 * Cfg::THREADS) {
             T v[8];
 #pragma unroll

@@ -71,10 +71,12 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
     if (flavor == 9) {
         // r2r kinds fused into the pass: real lines, so strides are in single reals
         if (p.pre_op != B2D_LOAD_R2R || p.post_op != B2D_STORE_R2R || p.bluestein || p.npeer) return nullptr;
-        if (p.load_col != p.store_col || col != p.load_col) return nullptr;
+        // ROW kernels read contiguous lines; their stores go through the line's own stride, so the lines may
+        // also be stored transposed (row -> col)
+        if ((p.load_col && !p.store_col) || col != p.load_col) return nullptr;
         const int64_t unit = p.r2r_pair ? 2 : 1;          // paired lines: batch dim 0 steps over two adjacent reals
         if (col ? (p.bis[0] != unit || p.bos[0] != unit || (p.r2r_pair && (p.pair_is != 1 || p.pair_os != 1)))
-                : (p.is != 1 || p.os != 1)) return nullptr;
+                : (p.is != 1 || (p.os != 1 && !p.store_col))) return nullptr;
         const FastEntry *e9 = find(p.prec, p.n, col, p.kernel, p.r2r_kind);
         if (e9 && (int)e9->smem > g_max_smem && g_max_smem) return nullptr;
         return e9;

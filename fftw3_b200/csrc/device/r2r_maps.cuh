@@ -30,6 +30,14 @@ struct RealLineOut {
     B2_HD void operator()(int k, T v) const { p[(int64_t)k * s] = v; }
 };
 
+// collects what a POST map writes for one spectrum element (at most two (index, value) pairs), so that the
+// values of neighbouring lines can leave in one vector store
+template <typename T>
+struct StashOut {
+    mutable int idx[2]; mutable T val[2]; mutable int cnt;
+    B2_HD void operator()(int k, T v) const { idx[cnt] = k; val[cnt] = v; ++cnt; }
+};
+
 // complex work length M for a kind of physical size n
 B2_HD int r2r_work_len(int kind, int n)
 {

@@ -261,9 +261,9 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         else
         /* pass shapes with their own specialised flavour (see device/fft_fast.cuh) */
         if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
+        else if (f->pre_op == B2D_LOAD_R2R && f->post_op == B2D_STORE_R2R) { if (flavor) return -1; flavor = 9; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
         else if (f->bluestein) { if (flavor) return -1; flavor = 7; }
-        else if (f->pre_op == B2D_LOAD_R2R && f->post_op == B2D_STORE_R2R) { if (flavor) return -1; flavor = 9; }
         code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
@@ -313,6 +313,21 @@ static int estimate_variant(b2d_fft_pass *f)
         while (((size_t)1 << lg) * esz < (size_t)want) ++lg;
         v = NVARIANTS + ((want == 64 && !(f->cache & 1)) ? 6 * 6 : 0) + lg;
         { b2d_fft_pass t = *f; if (!configure_variant(&t, v)) return v; }
+    }
+    if (!f->load_col && (f->pre_op & B2D_LOAD_R2R) && f->prec == B2D_F64) {
+        /* double r2r lines so long that two transforms per CTA leave room for one CTA per SM only: one transform
+           per CTA, two resident CTAs overlap each other's phases (160 vs 168 us per 4096 x 4096 pass, 182 vs 204
+           with transposed stores, profiles/r02_c5b_pieces.txt) */
+        int64_t pitch = f->n + (f->n >> 4) + 9;
+        if ((size_t)(2 * pitch) * 16 > 113 * 1024) {
+            b2d_fft_pass t = *f;
+            if (!configure_variant(&t, NVARIANTS + 0)) return NVARIANTS + 0;
+        }
+    }
+    if (!f->load_col && f->store_col && (f->pre_op & B2D_LOAD_R2R)) {
+        /* long r2r lines stored transposed: the line kernels, widest tile first (more adjacent lines per store) */
+        static const int t_pref[] = { 2, 1, 0 };
+        pref = t_pref; npref = 3;
     }
     for (i = 0; i < npref; ++i) {
         b2d_fft_pass t = *f;
@@ -1490,6 +1505,42 @@ static int plan_r2r(b2_plan *p)
     if (q->sz.rnk == 0) {
         if (p->inplace) return 0;
         return emit_copy(p, q->prec, mkref(BUF_IN0, 0), mkref(BUF_OUT0, 0), &q->vecsz, 1);
+    }
+    /* Dense row-major 2-d array whose columns are too long for a tile of them to share a CTA: both passes read
+       contiguous lines and store them transposed (pass 1 into scratch as [k1][i0], pass 2 from there into the
+       user's [k0][k1]), instead of bracketing the column pass with two transposes -- two launches, each array
+       read and written once per dimension */
+    if (q->sz.rnk == 2 && b2_tensor_count(&q->vecsz) == 1 && !getenv("FFTW3_B200_R2R_UNFUSED") &&
+        !getenv("FFTW3_B200_R2R_TRANSPOSES")) {
+        int64_t n0 = q->sz.d[0].n, n1 = q->sz.d[1].n, m0, m1;
+        size_t esz = 2 * real_size(q->prec);
+        int radix[64], k0 = q->r2r_kind[0], k1 = q->r2r_kind[1];
+        if (k0 >= 0 && k0 <= 10 && k1 >= 0 && k1 <= 10 && !r2r_work_len(k0, n0, &m0) && !r2r_work_len(k1, n1, &m1) &&
+            q->sz.d[1].is == 1 && q->sz.d[1].os == 1 && q->sz.d[0].is == n1 && q->sz.d[0].os == n1 &&
+            m0 >= 2 && m1 >= 2 && b2_factorize(m0, q->prec, 0, radix) != 0 && b2_factorize(m1, q->prec, 0, radix) != 0 &&
+            single_pass_fits(m0, q->prec) && single_pass_fits(m1, q->prec) && (size_t)m0 * 4 * esz > 131072) {
+            b2_view vin, vout;
+            b2_tensor ub;
+            b2_ops ops;
+            int mark = p->nsteps;
+            need_scratch(p, 0, (size_t)(n0 * n1) * real_size(q->prec));
+            memset(&ops, 0, sizeof ops);
+            ops.pre_op = B2D_LOAD_R2R; ops.post_op = B2D_STORE_R2R;
+            ops.n_in = ops.n_out = (int)n1; ops.r2r_kind = k1;
+            vin.re = vin.im = mkref(BUF_IN0, 0); vin.stride = 1;
+            vout.re = vout.im = mkref(BUF_SCRATCH0, 0); vout.stride = n0;
+            b2_tensor_init(&ub, 1); ub.d[0].n = n0; ub.d[0].is = n1; ub.d[0].os = 1;
+            rc = emit_fft1d(p, q->prec, m1, vin, vout, &ub, ops, 1, "r2r (maps fused, lines stored transposed)");
+            if (!rc) {
+                ops.n_in = ops.n_out = (int)n0; ops.r2r_kind = k0;
+                vin.re = vin.im = mkref(BUF_SCRATCH0, 0); vin.stride = 1;
+                vout.re = vout.im = mkref(BUF_OUT0, 0); vout.stride = n1;
+                ub.d[0].n = n1; ub.d[0].is = n0; ub.d[0].os = 1;
+                rc = emit_fft1d(p, q->prec, m0, vin, vout, &ub, ops, 1, "r2r (maps fused, lines stored transposed)");
+            }
+            if (!rc) return 0;
+            p->nsteps = mark;       /* could not be emitted that way: the general path below */
+        }
     }
     for (d = q->sz.rnk - 1; d >= 0; --d) {
         int kind = q->r2r_kind[d];

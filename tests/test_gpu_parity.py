@@ -371,11 +371,15 @@ def test_wisdom_tool_produces_importable_wisdom(gpu_lib, tmp_path):
     ((256, 100, 64), ("RODFT10", "REDFT01", "DHT"), False),
     ((1024, 1024), ("RODFT11", "RODFT00"), False),
 ])
-def test_r2r_fused_maps_and_long_strided_lines(gpu_lib, prec, shape, kinds, inplace):
+@pytest.mark.parametrize("transposes", [False, True])
+def test_r2r_fused_maps_and_long_strided_lines(gpu_lib, prec, shape, kinds, inplace, transposes, monkeypatch):
     """The r2r PRE/POST maps ride in the load/store of one FFT pass per dimension
     (device/r2r_maps.cuh; specialised kernels flavour 9 and the generic kernel); strided lines
-    too long for a tile go through transposed scratch lines.  Same oracle and bound as the
-    other r2r tests."""
+    too long for a tile: two line passes with transposed stores for a dense 2-d array, transposed
+    scratch lines around the pass otherwise (forced by FFTW3_B200_R2R_TRANSPOSES).  Same oracle and
+    bound as the other r2r tests."""
+    if transposes:
+        monkeypatch.setenv("FFTW3_B200_R2R_TRANSPOSES", "1")
     err, tol = F.r2r(gpu_lib, prec, shape, list(kinds), inplace=inplace)
     assert err <= tol, (prec, shape, kinds, err, tol)
 

@@ -260,10 +260,15 @@ def test_inplace_with_different_strides(emu_lib):
     ((2, 2500, 3), ("DHT", "RODFT11", "HC2R"), False),
     ((2049, 4), ("REDFT00", "REDFT11"), True),
 ])
-def test_r2r_long_strided_lines(emu_lib, shape, kinds, inplace):
-    """r2r dimensions whose strided lines are too long for a tile of them to share a CTA go
-    through transposed scratch lines (dft/indirect-transpose.c strategy) around the fused pass;
-    the other dimensions run the PRE/POST maps inside one pass (device/r2r_maps.cuh)."""
+@pytest.mark.parametrize("transposes", [False, True])
+def test_r2r_long_strided_lines(emu_lib, shape, kinds, inplace, transposes, monkeypatch):
+    """r2r dimensions whose strided lines are too long for a tile of them to share a CTA: a dense 2-d array
+    runs two line passes that store their lines transposed (through scratch and back); the general case
+    (batches, more dimensions, or FFTW3_B200_R2R_TRANSPOSES) brackets the fused pass with transposed scratch
+    lines (dft/indirect-transpose.c strategy).  The other dimensions run the PRE/POST maps inside one pass
+    (device/r2r_maps.cuh)."""
+    if transposes:
+        monkeypatch.setenv("FFTW3_B200_R2R_TRANSPOSES", "1")
     err, tol = F.r2r(emu_lib, "d", shape, list(kinds), inplace=inplace)
     assert err <= tol, (shape, kinds, err)
 

@@ -27,6 +27,15 @@ for force in (None, 12, 13, 18, 19):
     print("rows REDFT10 force=%s: %.1f us  %s" % (force, 1e3 * timed(lib, "d", p), " ".join(lib.sprint_plan("d", p).split())[:150]), flush=True)
     lib.destroy_plan("d", p)
 os.environ.pop("FFTW3_B200_FORCE_VARIANT", None)
+# the same row pass storing its lines transposed (output stride n, line distance 1): two of these make the 2-D
+# transform without the two transposes
+for force in (None, 12):
+    if force is None: os.environ.pop("FFTW3_B200_FORCE_VARIANT", None)
+    else: os.environ["FFTW3_B200_FORCE_VARIANT"] = str(force)
+    p = lib.plan_many_r2r("d", [n], n, x.data_ptr(), None, 1, n, y.data_ptr(), None, n, 1, ["REDFT10"], B.FFTW_ESTIMATE)
+    print("rows REDFT10 -> transposed stores force=%s: %.1f us  %s" % (force, 1e3 * timed(lib, "d", p), " ".join(lib.sprint_plan("d", p).split())[:150]), flush=True)
+    lib.destroy_plan("d", p)
+os.environ.pop("FFTW3_B200_FORCE_VARIANT", None)
 h = (B.Iodim * 2)(B.Iodim(n, n, 1), B.Iodim(n, 1, n))
 p = lib.fn("d", "plan_guru_r2r")(0, None, 2, C.cast(h, C.c_void_p), x.data_ptr(), y.data_ptr(), None, B.FFTW_ESTIMATE)
 print("transpose 4096^2 f64: %.1f us" % (1e3 * timed(lib, "d", p)), flush=True)
