@@ -320,7 +320,7 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
             }
             return;
         }
-        if (FLAVOR == 2) {
+        if (FLAVOR == 2 || FLAVOR == 11) {
             int64_t e = (int64_t)kout * (b0 + p.tw4_off);
             int64_t eh, el;
             if (p.tw4_shift >= 0) { e &= (p.big_n - 1); eh = e >> p.tw4_shift; el = e & (p.aux_split - 1); }
@@ -533,6 +533,23 @@ __device__ __forceinline__ void fast_tile(const b2d_fft_pass &p, int swap_in, in
         } else if (FLAVOR == 7) {
             const int k = j + r * TPX;
             if (valid && k < p.n_in) v = ld_stream(gin + (int64_t)k * is2);
+        } else if (FLAVOR == 11) {
+            // first pass of an even-size c2r (B2D_LOAD_C2R_MERGE): element k of column b0 is logical index
+            // jl = k * idx_mul + b0 of the Hermitian half X[0..m]; its mirror X[m - jl] lies (m - 2 jl) complex
+            // elements on (columns are adjacent).  Consecutive lanes read consecutive X and, backwards, consecutive
+            // mirrors; the mirror tile is some other CTA's own tile, so one of the two reads hits L2.
+            if (valid) {
+                const int64_t m = p.n_in;
+                const int64_t jl = (int64_t)(j + r * TPX) * p.idx_mul + b0;
+                const cplx<T> *pa = gin + (int64_t)(j + r * TPX) * is2;
+                cplx<T> a = ld_plain(pa), cm = ld_plain(pa + (m - 2 * jl));      // no evict-first: the other read of each is still to come
+                cplx<T> w = ldg_c(reinterpret_cast<const cplx<T> *>(p.aux2) + jl);
+                if (jl == 0) { a.y = T(0); cm.y = T(0); }
+                const T sr = a.x + cm.x, si = a.y - cm.y, dr = a.x - cm.x, di = a.y + cm.y;
+                w.y = -w.y;
+                v.x = si + (w.x * dr - w.y * di);        // swapped (Im Z, Re Z): the forward stages then run the
+                v.y = sr - (w.x * di + w.y * dr);        // backward transform
+            }
         } else if (valid) {
             // flavors 4-6 (narrow COL tiles): 4 = L2::256B loads + write-back stores,
             // 5 = L2::128B loads + streaming stores, 6 = L2::256B loads + streaming stores

@@ -49,8 +49,9 @@ void init(int max_smem)
 // flavor 2 = COL kernel with the four-step twiddle fused in its store, flavor 3 = ROW load
 // with COL (transposed) store.
 // kernel code = tile + 100 * flavor (+ 1000 for COL kernels), flavors 0-9; codes 2000 + tile = flavor 10 (ROW)
-static inline int code_col(int code) { return code >= 1000 && code < 2000; }
-static inline int code_flavor(int code) { return code >= 2000 ? 10 : (code / 100) % 10; }
+// codes 2100 + tile = flavor 11 (COL: four-step first pass with the c2r merge on its load)
+static inline int code_col(int code) { return (code >= 1000 && code < 2000) || (code >= 2100 && code < 2200); }
+static inline int code_flavor(int code) { return code >= 2100 ? 11 : (code >= 2000 ? 10 : (code / 100) % 10); }
 
 static const FastEntry *entry_for(const b2d_fft_pass &p)
 {
@@ -67,6 +68,16 @@ static const FastEntry *entry_for(const b2d_fft_pass &p)
         if (!e10 || ((int)e10->smem > g_max_smem && g_max_smem)) return nullptr;
         if (p.bn[0] < e10->tpb || p.bn[0] % e10->tpb) return nullptr;
         return e10;
+    }
+    if (flavor == 11) {
+        if (p.pre_op != B2D_LOAD_C2R_MERGE || p.post_op != B2D_STORE_TWIDDLE4 || p.bluestein || p.npeer ||
+            !p.load_col || !p.store_col || !p.idx_mul || !p.aux2) return nullptr;
+        if ((p.is & 1) || (p.os & 1) || p.bis[0] != 2 || p.bos[0] != 2) return nullptr;
+        for (int i = 1; i < B2D_MAX_BATCH_DIMS; ++i)
+            if ((p.bis[i] & 1) || (p.bos[i] & 1)) return nullptr;
+        const FastEntry *e11 = find(p.prec, p.n, 1, p.kernel);
+        if (e11 && (int)e11->smem > g_max_smem && g_max_smem) return nullptr;
+        return e11;
     }
     if (flavor == 9) {
         // r2r kinds fused into the pass: real lines, so strides are in single reals
@@ -144,6 +155,7 @@ int try_launch(const b2d_fft_pass &p, cudaStream_t st)
     int64_t tiles0 = (p.bn[0] + e->tpb - 1) / e->tpb;
     b2d_fft_pass q = p;
     q.tpb = e->tpb;                  // decode_block() uses the tile width
+    if (code_flavor(p.kernel) == 11 && swap_in) return 1;     // the merge defines its own (swapped) load
     if (code_flavor(p.kernel) == 10) {
         if (swap_in || swap_out) return 1;
         // tiles of HALF = tpb / 2 rows + their mirrors over rows 1 .. n1/2, plus one tile for row 0

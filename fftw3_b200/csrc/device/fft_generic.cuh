@@ -98,6 +98,21 @@ B2_HD cplx<T> load_elem(const b2d_fft_pass &p, int64_t boff, int64_t b0, int k)
         return u;
     }
     cplx<T> z;
+    if (op & B2D_LOAD_C2R_MERGE) {
+        // logical index j of this element in the half-size line; its mirror m - j sits (m - 2j) logical steps on
+        const int64_t m = p.n_in;
+        const int64_t j = p.idx_mul ? (int64_t)k * p.idx_mul + b0 : (int64_t)k;
+        const int64_t o = boff + (int64_t)k * p.is;
+        const int64_t om = o + (m - 2 * j) * (p.idx_mul ? p.bis[0] : p.is);
+        cplx<T> a, c;
+        a.x = re[o]; a.y = im[o]; c.x = re[om]; c.y = im[om];
+        if (j == 0) { a.y = T(0); c.y = T(0); }
+        const T sr = a.x + c.x, si = a.y - c.y, dr = a.x - c.x, di = a.y + c.y;
+        cplx<T> w = ((const cplx<T> *)p.aux2)[j]; w.y = -w.y;        // conj(w^j)
+        z.x = si + (w.x * dr - w.y * di);                            // swapped: (Im Z_j, Re Z_j)
+        z.y = sr - (w.x * di + w.y * dr);
+        return z;
+    }
     if (op & B2D_LOAD_RADER) k = ((const int *)p.aux0)[k];          // a_q = x[g^q mod n]
     if ((op & B2D_LOAD_PAD) && k >= p.n_in) { z.x = T(0); z.y = T(0); return z; }
     if (op & B2D_LOAD_REAL) {

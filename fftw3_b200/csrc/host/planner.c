@@ -196,6 +196,7 @@ typedef struct {
     int64_t idx_mul;          /* four-step halves: logical index rule for HERMCONJ / TRUNC (b2d_fft_pass.idx_mul) */
     int force_kernel;         /* pass shapes served by exactly one specialised kernel (STORE_R2C_SPLIT): its code */
     int64_t tw4_off;          /* STORE_TWIDDLE4: global index of batch column 0 (b2d_fft_pass.tw4_off) */
+    int64_t merge_n;          /* LOAD_C2R_MERGE: the real length n = 2m whose roots of unity the merge uses */
 } b2_ops;
 
 static void fill_geometry(b2d_fft_pass *f, int variant)
@@ -260,11 +261,16 @@ static int configure_variant(b2d_fft_pass *f, int variant)
         if (f->npeer && f->peer_rows > 0) { if (flavor) return -1; flavor = 8; }      /* row-split peer stores */
         else
         /* pass shapes with their own specialised flavour (see device/fft_fast.cuh) */
-        if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
+        if (f->pre_op == B2D_LOAD_C2R_MERGE) {
+            if (flavor || f->post_op != B2D_STORE_TWIDDLE4 || !f->load_col || !f->store_col) return -1;
+            flavor = 11;
+        }
+        else if (f->post_op == B2D_STORE_TWIDDLE4 && f->load_col && f->store_col) { if (flavor) return -1; flavor = 2; }
         else if (f->pre_op == B2D_LOAD_R2R && f->post_op == B2D_STORE_R2R) { if (flavor) return -1; flavor = 9; }
         else if (!f->load_col && f->store_col) { if (flavor) return -1; flavor = 3; }
         else if (f->bluestein) { if (flavor) return -1; flavor = 7; }
         code = ((f->load_col) ? 1000 : 0) + 100 * flavor + tpb;
+        if (flavor == 11) code = 2100 + tpb;
         if (!b2d_fast_available(f, code)) return -1;
         /* generic geometry stays configured: it is the fallback for misaligned new arrays */
         ns = b2_factorize(f->n, f->prec, 0, f->radix);
@@ -324,6 +330,12 @@ static int estimate_variant(b2d_fft_pass *f)
             if (!configure_variant(&t, NVARIANTS + 0)) return NVARIANTS + 0;
         }
     }
+    if (!f->load_col && f->store_col && !f->pre_op && f->prec == B2D_F32) {
+        /* contiguous lines stored transposed (second pass of a four-step): 128-byte store segments, i.e. 16 single
+           precision lines per CTA (C2 c2r 1.60 vs 1.68 ms with 8, profiles/r02_c2_fused.log) */
+        static const int s_pref[] = { 4, 3, 2, 5 };
+        pref = s_pref; npref = 4;
+    }
     if (!f->load_col && f->store_col && (f->pre_op & B2D_LOAD_R2R)) {
         /* long r2r lines stored transposed: the line kernels, widest tile first (more adjacent lines per store) */
         static const int t_pref[] = { 2, 1, 0 };
@@ -346,6 +358,10 @@ static void pass_span(const b2d_fft_pass *f, int out, int64_t *lo, int64_t *hi)
     int64_t e = (len - 1) * s;
     if (e < 0) mn += e; else mx += e;
     if (f->r2r_pair) { e = out ? f->pair_os : f->pair_is; if (e < 0) mn += e; else mx += e; }
+    if (!out && (f->pre_op & B2D_LOAD_C2R_MERGE)) {      /* one element past the m the pass walks: X[m] */
+        e = f->idx_mul ? f->bis[0] : f->is;
+        if (e < 0) mn += e; else mx += e;
+    }
     for (i = 0; i < B2D_MAX_BATCH_DIMS; ++i) {
         int64_t bs = out ? f->bos[i] : f->bis[i];
         e = (f->bn[i] - 1) * bs;
@@ -495,6 +511,10 @@ static int emit_single(b2_plan *p, int prec, int64_t n, b2_view in, b2_view out,
     if (f->post_op & B2D_STORE_R2C_SPLIT) {
         f->aux0 = plan_table(p, prec, TAB_R2C, ops.big_n, 0);      /* exp(-2 pi i q / n), q <= n / 2 */
         if (!f->aux0) return -1;
+    }
+    if (f->pre_op & B2D_LOAD_C2R_MERGE) {
+        f->aux2 = plan_table(p, prec, TAB_R2C, ops.merge_n, 0);
+        if (!f->aux2) return -1;
     }
     s->r[0] = in.re; s->r[1] = in.im; s->r[2] = out.re; s->r[3] = out.im;
     snprintf(s->note, sizeof s->note, "%s", note);
@@ -745,6 +765,9 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
     int smooth = b2_factorize(n, c->prec, 0, radix) != 0;
 
     if ((c->ops.post_op & B2D_STORE_R2C_SPLIT) && (!smooth || single_pass_fits(n, c->prec))) return -4;   /* only on a four-step's second pass */
+    /* ... and the c2r merge only on the load of a (two-pass) four-step's first pass */
+    if ((c->ops.pre_op & B2D_LOAD_C2R_MERGE) &&
+        (!smooth || single_pass_fits(n, c->prec) || two_factor_split(n, c->prec) < 0 || (in.stride & 1))) return -4;
     if (smooth && single_pass_fits(n, c->prec)) {
         int ra, rb;
         if (split_wanted(p, c, in, out, bd, brank, &ra, &rb)) return emit_split(p, c, in, out, bd, brank, ra, rb);
@@ -910,8 +933,8 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
             oa_v.stride = 2 * n2;
             L = 1; while (L * L < n) L <<= 1;
             oa = c->ops; oa.post_op = B2D_STORE_TWIDDLE4; oa.n_out = 0;
-            if (!(oa.pre_op & B2D_LOAD_HERMCONJ)) oa.n_in = 0;
-            else { oa.n_in = (int)n; oa.idx_mul = n2; }
+            if (oa.pre_op & (B2D_LOAD_HERMCONJ | B2D_LOAD_C2R_MERGE)) { oa.n_in = (int)n; oa.idx_mul = n2; }
+            else oa.n_in = 0;
             oa.big_n = n; oa.tw4_split = L;
             rc = emit_single(p, c->prec, n1, ia, oa_v, ba, brank + 1, oa, 0, "four-step A");
             if (rc) return rc;
@@ -1450,6 +1473,26 @@ static int plan_c2r(b2_plan *p)
         b2_view wv;
         size_t esz = 2 * real_size(q->prec);
         int i;
+        {
+            b2_view iv;
+            iv.re = mkref(src_re, 0); iv.im = mkref(src_im, im_off); iv.stride = is;
+            if (!getenv("FFTW3_B200_C2R_UNFUSED") && !(q->flags & B2F_UNALIGNED) && src_re == BUF_IN0 && im_off == 0 &&
+                view_interleaved(p, iv) && (const char *)p->prob.in1 - (const char *)p->prob.in0 == (ptrdiff_t)real_size(q->prec)) {
+                /* long lines (the half-size transform is a four-step): the merge rides on the load of its first
+                   pass, so the line crosses HBM twice, not three times -- the mirror image of the r2c split that
+                   rides on the last store */
+                b2_ops mo;
+                b2_view ov;
+                int s0 = p->nsteps;
+                memset(&mo, 0, sizeof mo);
+                mo.pre_op = B2D_LOAD_C2R_MERGE; mo.merge_n = n;
+                ov.re = mkref(BUF_OUT0, os); ov.im = mkref(BUF_OUT0, 0); ov.stride = 2 * os;
+                rc = emit_fft1d(p, q->prec, m, iv, ov, &batch, mo, 1, "c2r merge + half-size dft");
+                if (rc == 0 && p->nsteps > s0) return 0;
+                if (rc != -4 && rc != 0) return rc;
+                p->nsteps = s0;
+            }
+        }
         make_work_batch(&wb, m);       /* sorted by INPUT (complex) strides */
         need_scratch(p, 0, (size_t)(b2_tensor_count(&wb) > 0 ? b2_tensor_count(&wb) : 1) * (size_t)m * esz);
         memset(&c, 0, sizeof c);
@@ -1906,6 +1949,7 @@ void b2_plan_print(const b2_plan *p, FILE *f)
             fprintf(f, " batch=%lldx%lldx%lld ", (long long)q->bn[0], (long long)q->bn[1], (long long)q->bn[2]);
             if (q->kernel >= 3100) fprintf(f, "32x32 one-exchange tile=%d", q->kernel - 3100);
             else if (q->kernel >= 3000) fprintf(f, "warp-per-transform 32x32");
+            else if (q->kernel >= 2100) fprintf(f, "codelet-tile=%d/c2r-merge", q->kernel % 100);
             else if (q->kernel >= 2000) fprintf(f, "codelet-tile=%d/r2c-split", q->kernel % 100);
             else if (q->kernel) fprintf(f, "codelet-tile=%d/f%d", q->kernel % 100, (q->kernel / 100) % 10);
             else fprintf(f, "generic tpb=%d tpx=%d", q->tpb, q->tpx);

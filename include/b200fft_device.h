@@ -34,8 +34,12 @@ enum {
     B2D_LOAD_CHIRP = 8,     /* multiply by aux0[k] (Bluestein chirp)                 */
     B2D_LOAD_RADER = 32,    /* element k comes from input index perm[k] (aux0: int32 perm_in[n], perm_out[n]);
                                Rader's prime-size algorithm, bluestein == 2            */
-    B2D_LOAD_R2R = 16       /* real line of n_in elements -> complex work sequence of length n by
+    B2D_LOAD_R2R = 16,      /* real line of n_in elements -> complex work sequence of length n by
                                the PRE map of r2r_kind (aux0 = quarter-wave table)     */
+    B2D_LOAD_C2R_MERGE = 64 /* first pass of the half-size transform of an even-size c2r (rdft/ct-hc2c.c:146-273 run
+                               backwards): the input is the Hermitian half X[0..m], m = n_in, and logical element j
+                               loads as swap(Z_j), Z_j = (X_j + conj X_{m-j}) + i conj(w)^j (X_j - conj X_{m-j}),
+                               w = exp(-2 pi i / 2m) from aux2 -- the merge rides on the load, no pass of its own */
 };
 
 /* element-wise operations fused into the store side of an FFT pass (bit mask) */
@@ -90,6 +94,7 @@ typedef struct b2d_fft_pass {
     void *out_re, *out_im;
     const void *tw;           /* n complex: exp(-2 pi i k / n)                       */
     const void *aux0, *aux1;  /* op tables                                           */
+    const void *aux2;         /* LOAD_C2R_MERGE: exp(-2 pi i q / 2m), q < m           */
     int64_t aux_split;        /* TWIDDLE4: lo-table length L (e = hi*L + lo)          */
     int64_t big_n;            /* TWIDDLE4: N of the enclosing transform               */
     int tw4_shift;            /* log2(aux_split) when big_n and aux_split are powers of two, else -1 */

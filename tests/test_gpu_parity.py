@@ -63,6 +63,23 @@ def test_r2c_c2r(gpu_lib, prec, shape, inplace):
     assert err <= tol
 
 
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("unfused", [False, True])
+@pytest.mark.parametrize("shape,howmany", [((1 << 17,), 5), ((4 * 3 ** 9,), 2), ((3, 1 << 16), 2), ((1 << 21,), 1)])
+def test_long_even_real_lines_split_and_merge_fused(gpu_lib, prec, unfused, shape, howmany, monkeypatch):
+    """Even-size real transforms whose half-size transform is a four-step: c2r merge on the first pass's load
+    (fft_fast.cuh flavour 11 / generic kernel), r2c split on the last pass's store (flavour 10), against the same
+    oracle and bound; also with both kept as passes of their own."""
+    if unfused:
+        monkeypatch.setenv("FFTW3_B200_C2R_UNFUSED", "1")
+        monkeypatch.setenv("FFTW3_B200_R2C_UNFUSED", "1")
+    for inplace in (False, True):
+        err, tol = F.c2r(gpu_lib, prec, shape, howmany=howmany, inplace=inplace)
+        assert err <= tol, ("c2r", prec, shape, inplace, err, tol)
+        err, tol = F.r2c(gpu_lib, prec, shape, howmany=howmany, inplace=inplace)
+        assert err <= tol, ("r2c", prec, shape, inplace, err, tol)
+
+
 def test_config2_r2c_c2r_2e20_float(gpu_lib):
     """BASELINE config 2 (N = 2^20 single precision) at batch 2."""
     err, tol = F.r2c(gpu_lib, "f", (1 << 20,), howmany=2)

@@ -48,6 +48,34 @@ def test_r2c_c2r(emu_lib, prec, shape, inplace):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("unfused", [False, True])
+@pytest.mark.parametrize("shape,howmany", [((1 << 16,), 3), ((4 * 3 ** 9,), 2), ((3, 1 << 15), 1)])
+def test_long_even_real_lines_split_and_merge_fused(emu_lib, prec, unfused, shape, howmany, monkeypatch):
+    """Even-size real transforms whose half-size complex transform is a four-step: the c2r merge rides on the
+    load of the first pass (B2D_LOAD_C2R_MERGE), the r2c split on the store of the last (specialised kernels
+    only, so the emulator keeps that one apart) -- rdft/ct-hc2c.c:146-273 fuses them into the twiddle codelets
+    the same way.  FFTW3_B200_C2R_UNFUSED / _R2C_UNFUSED keep them as passes of their own."""
+    if unfused:
+        monkeypatch.setenv("FFTW3_B200_C2R_UNFUSED", "1")
+        monkeypatch.setenv("FFTW3_B200_R2C_UNFUSED", "1")
+    err, tol = F.c2r(emu_lib, prec, shape, howmany=howmany)
+    assert err <= tol
+    err, tol = F.c2r(emu_lib, prec, shape, howmany=howmany, inplace=True)
+    assert err <= tol
+    err, tol = F.r2c(emu_lib, prec, shape, howmany=howmany)
+    assert err <= tol
+    n = shape[-1]
+    dt, cdt = (np.float64, np.complex128) if prec == "d" else (np.float32, np.complex64)
+    x = np.zeros(n // 2 + 1, dtype=cdt)
+    y = np.zeros(n, dtype=dt)
+    p = emu_lib.plan_many_dft_c2r(prec, [n], 1, x.ctypes.data, None, 1, n // 2 + 1, y.ctypes.data, None, 1, n, B.FFTW_ESTIMATE)
+    txt = emu_lib.sprint_plan(prec, p)
+    emu_lib.destroy_plan(prec, p)
+    assert ("realop" in txt) == unfused, txt
+    assert txt.count("fft-pass") == 2, txt
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("kind", list(B.R2R_KINDS))
 @pytest.mark.parametrize("n", [2, 3, 8, 9, 16, 37])
 def test_r2r_1d(emu_lib, prec, kind, n):
