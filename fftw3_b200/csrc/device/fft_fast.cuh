@@ -212,6 +212,8 @@ struct FastCfg {
     // r2r line kernels (flavor 9, ROW) of 256 threads: one CTA per SM leaves every phase (staged loads, three
     // exchanges, POST map) exposed -- 150 registers uncapped, 248 us for 4096 x 4096 REDFT10 rows against 167 with
     // two lines pairs per CTA (profiles/r02_c5b_pieces.txt); capped at 128 two CTAs overlap
+    // (one-CTA Bluestein, flavor 7, stays uncapped: at 168 registers a third 128-thread CTA fits but the spills cost
+    // more than it hides -- 618 vs 573 us for 1009 x 16384 double, profiles/r02_c5a_experiment.log)
     static constexpr int MINB = FLAVOR == 1 ? MINB__ : (((COL ? FLAVOR != 9 : FLAVOR == 9) && THREADS <= 256 && BY_SMEM >= 2 && sizeof(T) == 8) ? 2 : 1);
     static_assert(E * R1 * R2 == N, "radices must multiply to N");
     static_assert(E % R1 == 0 && E % R2 == 0, "later radices must divide the per-thread element count");

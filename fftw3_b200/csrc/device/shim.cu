@@ -1,6 +1,7 @@
 // shim.cu -- implementation of the C-ABI in include/b200fft_device.h on CUDA.
 // Everything the C host layer needs from the device goes through here.
 // There is NO CPU fallback: without a usable device every entry point fails.
+#include <cuda.h>            /* types of the green-context entry points only: no link dependency on libcuda */
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -118,6 +119,13 @@ const char *b2d_last_error(void) { return g_err; }
 size_t b2d_max_smem_per_block(void) { ensure_init(); return g_max_smem; }
 uint64_t b2d_launch_count(void) { return g_launches.load(); }
 
+int b2d_current_device(void)
+{
+    int dev = -1;
+    if (ensure_init() || cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
 int b2d_pointer_is_device(const void *p)
 {
     if (ensure_init()) return -1;
@@ -215,6 +223,63 @@ void *b2d_aux_stream(int idx)
         if (cudaStreamCreateWithPriority(&aux[idx], cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
     }
     return (void *)aux[idx];
+}
+
+static void *driver_entry_raw(const char *name)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return fn;
+}
+#define driver_entry_as(T, name) ((T)driver_entry_raw(name))
+
+int b2d_partition_streams(int comm_sms, void **comm_stream, void **compute_stream)
+{
+    struct Part { int dev, sms, ok; cudaStream_t comm, comp; };
+    static Part parts[8];
+    static int nparts = 0;
+    static std::mutex mu;
+    if (ensure_init() || comm_sms < 8) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < nparts; ++i)
+        if (parts[i].dev == dev && parts[i].sms == comm_sms) {
+            if (!parts[i].ok) return -1;
+            *comm_stream = parts[i].comm; *compute_stream = parts[i].comp;
+            return 0;
+        }
+    if (nparts == 8) return -1;
+    Part &P = parts[nparts++];
+    P.dev = dev; P.sms = comm_sms; P.ok = 0;
+    auto getres = driver_entry_as(CUresult (*)(CUdevice, CUdevResource *, CUdevResourceType), "cuDeviceGetDevResource");
+    auto split = driver_entry_as(CUresult (*)(CUdevResource *, unsigned *, const CUdevResource *, CUdevResource *, unsigned, unsigned), "cuDevSmResourceSplitByCount");
+    auto gendesc = driver_entry_as(CUresult (*)(CUdevResourceDesc *, CUdevResource *, unsigned), "cuDevResourceGenerateDesc");
+    auto gcreate = driver_entry_as(CUresult (*)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned), "cuGreenCtxCreate");
+    auto gstream = driver_entry_as(CUresult (*)(CUstream *, CUgreenCtx, unsigned, int), "cuGreenCtxStreamCreate");
+    auto devget = driver_entry_as(CUresult (*)(CUdevice *, int), "cuDeviceGet");
+    if (!getres || !split || !gendesc || !gcreate || !gstream || !devget) return -1;
+    CUdevice cudev;
+    CUdevResource all, part, rest;
+    CUdevResourceDesc d0, d1;
+    CUgreenCtx g0, g1;
+    CUstream s0, s1;
+    unsigned n = 1;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (devget(&cudev, dev) || getres(cudev, &all, CU_DEV_RESOURCE_TYPE_SM)) return -1;
+    if ((int)all.sm.smCount < comm_sms + 8) return -1;
+    if (split(&part, &n, &all, &rest, 0, (unsigned)comm_sms) || n != 1 || rest.sm.smCount == 0) return -1;
+    if (gendesc(&d0, &part, 1) || gendesc(&d1, &rest, 1)) return -1;
+    if (gcreate(&g0, d0, cudev, CU_GREEN_CTX_DEFAULT_STREAM) || gcreate(&g1, d1, cudev, CU_GREEN_CTX_DEFAULT_STREAM)) return -1;
+    if (gstream(&s0, g0, CU_STREAM_NON_BLOCKING, hi) || gstream(&s1, g1, CU_STREAM_NON_BLOCKING, 0)) return -1;
+    P.comm = (cudaStream_t)s0; P.comp = (cudaStream_t)s1; P.ok = 1;
+    *comm_stream = P.comm; *compute_stream = P.comp;
+    return 0;
 }
 
 int b2d_stream_wait_stream(void *waiter, void *signaler)

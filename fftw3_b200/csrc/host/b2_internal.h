@@ -79,6 +79,7 @@ typedef struct b2_table {     /* device-resident constant table, refcounted & sh
     struct b2_table *next;
     int prec, kind;
     int64_t n, aux;
+    int device;               /* CUDA device the table lives on: a process that switches GPUs gets one per device */
     void *dev;
     size_t bytes;
     int refs;

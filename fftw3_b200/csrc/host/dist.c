@@ -48,6 +48,7 @@ struct fftw_b200_dist_plan_s {
     b2_plan *pre, *post;     /* real-data plans: local r2c rows before stage 0 / local c2r rows as the last stage */
     /* stage-0 exchange by the copy engines (see mkdist): X runs in place at full speed, the blocks then
        travel as 2-D copies on side streams while the SMs are already on the next chunk */
+    int part_sms;            /* > 0: stage 0 runs X (NVLink-bound) on that many SMs of their own and Y on the rest */
     int ce;
     int64_t ce_n1, ce_n2, ce_ln0;
     double *ce_local;
@@ -136,12 +137,29 @@ static void limit_grid(b2_plan *pl, int limit)
 static int exchange_by_copy(int nranks)
 {
     const char *e = getenv("FFTW3_B200_DIST_EXCHANGE");
-    if (e && !strcmp(e, "stores")) return 0;
+    (void)nranks;
     if (e && !strcmp(e, "copy")) return 1;
-    /* Measured on B200s behind NVSwitch (profiles/r02_dist_exchange_modes.log): with one peer the copy engines
-       keep up with the links and stage 0 becomes HBM-bound (8.27 vs 8.96 ms at 1024^3); with 3 or 7 peers their
-       strided copies reach only ~450 GB/s against ~700 for the pass's own stores, so the fused stores stay. */
-    return nranks == 2;
+    /* Measured on B200s behind NVSwitch (profiles/r02_dist_exchange_modes.log, r02_dist_partition.log): with one
+       peer the copy engines keep up with the links (stage 0 = 8.27 ms at 1024^3 against 8.94 for fused stores sharing
+       the SMs, 8.09 for fused stores on SMs of their own); with 3 or 7 peers their strided copies reach only
+       ~450 GB/s against ~700 for the pass's own stores.  The fused stores on partitioned SMs win everywhere. */
+    return 0;
+}
+
+/* SMs set aside for the NVLink-bound scatter pass of stage 0 (CUDA green contexts), the HBM-bound Y pass of the next
+   chunk getting the others.  Sharing every SM between the two does not overlap them: the scatter's CTAs hold their
+   stores behind the links and the Y CTAs next to them queue behind those (stage 0 = the sum of the two passes,
+   profiles/r02_dist_overlap_sweep*_p2.log).  The scatter needs enough SMs to transform its rows at the link rate.
+   Measured at 1024^3 on 148 SMs (profiles/r02_dist_partition.log): P = 2: 56 / 64 / 72 / 80 / 88 SMs -> stage 0 =
+   9.39 / 8.47 / 8.09 / 8.70 / 9.55 ms (8.94 shared); P = 4: 40 / 56 / 72 -> 6.31 / 5.06 / 5.13 ms (5.81 shared). */
+static int partition_sms(int nranks)
+{
+    const char *e = getenv("FFTW3_B200_DIST_PARTITION");
+    int sms = b2d_sm_count(), k;
+    if (e) return atoi(e);
+    if (sms < 64) return 0;
+    k = nranks == 2 ? (sms * 49) / 100 : (sms * 38) / 100;       /* 148 SMs: 72 / 56 */
+    return (k / 8) * 8;
 }
 
 static int copy_pieces(int nranks)
@@ -209,6 +227,11 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
     }
     p->c0 = ln0 > 0 ? chunks_for(ln0) : 1;
     p->c1 = pull_sources ? chunks_for(b1) : 1;     /* from the block size: identical on every rank */
+    if (!p->ce && nranks > 1 && p->c0 > 1 && b2d_pointer_is_device(local) == 1) {
+        void *a, *b;
+        int k = partition_sms(nranks);
+        if (k >= 8 && !b2d_partition_streams(k, &a, &b)) p->part_sms = k;
+    }
     p->y = (b2_plan **)calloc((size_t)p->c0, sizeof(b2_plan *));
     p->x = (b2_plan **)calloc((size_t)p->c0 * nranks, sizeof(b2_plan *));
     p->z = (b2_plan **)calloc((size_t)p->c1, sizeof(b2_plan *));
@@ -261,7 +284,7 @@ static dplan mkdist(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, int rank, int nran
             xp = b2_mkplan(&q);
             if (!xp) goto fail;
             p->x[c * nranks + d] = xp;
-            if (nranks > 1 && p->c0 > 1) limit_grid(xp, comm_ctas());
+            if (nranks > 1 && p->c0 > 1 && !p->part_sms) limit_grid(xp, comm_ctas());
             if (d == 0 && even1 && nranks > 1 && cnt > 1 && l1 > 1 && xp->nsteps == 1 && xp->steps[0].kind == STEP_FFT
                 && xp->steps[0].u.fft.bn[2] == 1 && xp->steps[0].u.fft.bn[0] == l1) {
                 /* all destinations get equal blocks: let batch dim 2 walk the destinations and
@@ -570,6 +593,7 @@ ptrdiff_t fftw_b200_ipc_offset(void *devptr) { return (ptrdiff_t)b2d_alloc_offse
 
 int fftw_b200_dist_num_stages(const dplan p) { return p->nstages; }
 int fftw_b200_dist_exchange_by_copy(const dplan p) { return p->ce; }
+int fftw_b200_dist_partition_sms(const dplan p) { return p->part_sms; }
 int fftw_b200_dist_num_chunks(const dplan p, int stage) { return stage == 0 ? p->c0 : p->c1; }
 
 static void run(b2_plan *pl)
@@ -597,6 +621,23 @@ void fftw_b200_dist_execute_chunk(const dplan p, int stage, int c)
     } else if (stage == 0 && c < p->c0) {
         void *aux = b2d_aux_stream(0);
         if (c == 0) run(p->pre);
+        if (p->part_sms) {
+            /* partitioned SMs: Y of every chunk on the compute partition's stream, X (fused scatter) of the chunk on
+               the communication partition's stream right behind its Y; the caller's stream joins both at the end */
+            void *cs = NULL, *ys = NULL;
+            if (!b2d_partition_streams(p->part_sms, &cs, &ys)) {
+                if (c == 0) b2d_stream_wait_stream(ys, mainst);
+                prev = b2d_push_stream(ys);
+                run(p->y[c]);
+                b2d_pop_stream(prev);
+                b2d_stream_wait_stream(cs, ys);
+                prev = b2d_push_stream(cs);
+                if (p->x_fused[c]) run(p->x[c * p->nranks]);
+                else for (d = 0; d < p->nranks; ++d) run(p->x[c * p->nranks + (p->rank + 1 + d) % p->nranks]);
+                b2d_pop_stream(prev);
+                return;
+            }
+        }
         run(p->y[c]);
         if (p->ce) {
             int64_t n1 = p->ce_n1, n2 = p->ce_n2, b1 = blk(n1, p->nranks);
@@ -640,10 +681,16 @@ void fftw_b200_dist_join(const dplan p)
 {
     void *mainst = b2d_get_stream();
     int i;
-    (void)p;
     for (i = 0; i < 8; ++i) {
         void *aux = b2d_aux_stream(i);
         if (aux) b2d_stream_wait_stream(mainst, aux);
+    }
+    if (p->part_sms) {
+        void *cs = NULL, *ys = NULL;
+        if (!b2d_partition_streams(p->part_sms, &cs, &ys)) {
+            b2d_stream_wait_stream(mainst, cs);
+            b2d_stream_wait_stream(mainst, ys);
+        }
     }
     if (!b2_async_mode) b2d_sync();
 }

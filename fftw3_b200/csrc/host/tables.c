@@ -76,9 +76,10 @@ b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux)
     size_t esz = (prec == B2D_F32) ? 8 : 16;
     void *host;
     long double c, s;
+    const int device = b2d_current_device();
 
     for (t = g_tables; t; t = t->next)
-        if (t->prec == prec && t->kind == kind && t->n == n && t->aux == aux) { t->refs++; return t; }
+        if (t->prec == prec && t->kind == kind && t->n == n && t->aux == aux && t->device == device) { t->refs++; return t; }
 
     switch (kind) {
     case TAB_TWIDDLE: count = n; break;
@@ -137,7 +138,7 @@ b2_table *b2_table_get(int prec, int kind, int64_t n, int64_t aux)
     }
     t = (b2_table *)calloc(1, sizeof *t);
     if (!t) { free(host); return NULL; }
-    t->prec = prec; t->kind = kind; t->n = n; t->aux = aux;
+    t->prec = prec; t->kind = kind; t->n = n; t->aux = aux; t->device = device;
     t->bytes = (size_t)(count ? count : 1) * esz;
     t->dev = b2d_malloc(t->bytes);
     if (!t->dev || b2d_memcpy_h2d(t->dev, host, (size_t)count * esz) || b2d_sync()) {

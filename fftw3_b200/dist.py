@@ -51,6 +51,7 @@ def _declare(lib):
     L.fftw_b200_dist_execute_stage.argtypes = [P, I]
     L.fftw_b200_dist_num_chunks.argtypes = [P, I]
     L.fftw_b200_dist_exchange_by_copy.argtypes = [P]
+    L.fftw_b200_dist_partition_sms.argtypes = [P]
     L.fftw_b200_dist_execute_chunk.argtypes = [P, I, I]
     L.fftw_b200_dist_join.argtypes = [P]
     L.fftw_b200_dist_destroy_plan.argtypes = [P]
@@ -767,6 +768,7 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
     lib.lib.fftw_b200_set_async(0)
     pushed = plan.push
     by_copy = bool(lib.lib.fftw_b200_dist_exchange_by_copy(plan.plan))
+    part_sms = int(lib.lib.fftw_b200_dist_partition_sms(plan.plan))
     check = None
     if impulse_expected is not None and not getattr(args, "no_check", False):
         check = _self_check_slab(lib, n, world, rank, local, plan, flags, exchange, impulse_expected)
@@ -794,7 +796,9 @@ def bench_slab_3d(args, lib, n, world, rank, local_rank, ClockSampler, flops_c2c
                                "output (two exchanges)" % (n, world),
                    "exchange": exchange + ((", first exchange = copy engines under the next chunk's transforms, second "
                                             "fused into the dim-0 pass's stores (no gather stage)" if by_copy else
-                                            ", both exchanges fused into pass stores (no gather stage)") if pushed
+                                            ", both exchanges fused into pass stores (no gather stage)" +
+                                            ("; stage 0: scatter pass on %d SMs of its own, Y pass of the next chunk on "
+                                             "the rest (green contexts)" % part_sms if part_sms else "")) if pushed
                                            else ", second exchange = gather stage"), "l2": "slabs are larger than L2, no flush needed",
                    "planner": "FFTW_ESTIMATE" if args.estimate else "FFTW_MEASURE", "plan_seconds": plan_s,
                    "transposed_out_ms_per_step": ms_t,

@@ -189,6 +189,7 @@ int  b2d_device_count(void);            /* 0 if no usable CUDA device           
 const char *b2d_device_name(void);
 int  b2d_sm_count(void);
 const char *b2d_last_error(void);
+int  b2d_current_device(void);            /* ordinal of the calling thread's current CUDA device, -1 without one */
 int  b2d_pointer_is_device(const void *p);   /* 1 device/managed, 0 host, -1 error     */
 void *b2d_malloc(size_t bytes);
 void b2d_free(void *p);
@@ -208,6 +209,11 @@ void *b2d_push_stream(void *cuda_stream);
 void b2d_pop_stream(void *prev);
 /* side streams for overlapping NVLink-bound kernels with HBM-bound ones */
 void *b2d_aux_stream(int idx);                           /* lazily created, non-blocking  */
+/* Two streams bound to disjoint sets of SMs of the current device (CUDA green contexts): `comm_sms` SMs (a multiple of
+ * 8) for an NVLink-bound kernel and the remaining SMs for the HBM-bound kernel that runs next to it, so that neither
+ * waits behind the other inside an SM.  Created once per (device, comm_sms); 0 on success, -1 when the driver cannot
+ * partition (the caller then shares the SMs as before). */
+int  b2d_partition_streams(int comm_sms, void **comm_stream, void **compute_stream);
 int  b2d_stream_wait_stream(void *waiter, void *signaler); /* event edge signaler -> waiter */
 size_t b2d_max_smem_per_block(void);
 

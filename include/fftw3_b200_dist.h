@@ -102,6 +102,9 @@ int  fftw_b200_dist_num_chunks(const fftw_b200_dist_plan p, int stage);
  * transform the next one (default for device-resident slabs), 0 = fused into the stores of the row pass
  * (FFTW3_B200_DIST_EXCHANGE=stores, and every plan whose arrays live on the host) */
 int  fftw_b200_dist_exchange_by_copy(const fftw_b200_dist_plan p);
+/* > 0: stage 0 of this plan runs its NVLink-bound scatter pass on that many SMs of their own (a CUDA green context)
+ * and the HBM-bound pass of the next chunk on the remaining SMs (FFTW3_B200_DIST_PARTITION=0 turns it off) */
+int  fftw_b200_dist_partition_sms(const fftw_b200_dist_plan p);
 void fftw_b200_dist_execute_chunk(const fftw_b200_dist_plan p, int stage, int chunk);
 void fftw_b200_dist_join(const fftw_b200_dist_plan p);
 void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);

@@ -125,6 +125,7 @@ int b2d_sm_count(void) { return 148; }
 const char *b2d_last_error(void) { return g_err; }
 size_t b2d_max_smem_per_block(void) { return 232448; }
 uint64_t b2d_launch_count(void) { return g_launches.load(); }
+int b2d_current_device(void) { return 0; }
 int b2d_pointer_is_device(const void *p)
 {
     // interior pointers count too (cudaPointerGetAttributes resolves them on the real device)
@@ -173,6 +174,7 @@ int b2d_peer_barrier(void *const *flags, int rank, int nranks, unsigned long lon
         while (__atomic_load_n((unsigned long long *)flags[rank] + d, __ATOMIC_ACQUIRE) < epoch) sched_yield();
     return 0;
 }
+int b2d_partition_streams(int, void **, void **) { return -1; }   /* no SMs to partition here */
 void *b2d_aux_stream(int) { return NULL; }                 /* everything is synchronous here */
 int b2d_stream_wait_stream(void *, void *) { return 0; }
 /* "IPC" between the threads that play ranks in a unit test: the handle is the pointer itself */

@@ -34,6 +34,27 @@ def test_exports_every_declared_symbol():
         assert os.path.exists(os.path.join(os.path.dirname(path), alias))
 
 
+def test_exports_every_symbol_of_the_distributed_header_and_binding():
+    """Everything include/fftw3_b200_dist.h declares is exported, and the ctypes prototypes of fftw3_b200/dist.py
+    (slab plans and the communicator interface) bind against the product library -- no compute call."""
+    from fftw3_b200 import binding, dist
+    path = binding.default_library_path()
+    lib = C.CDLL(path)
+    hdr = open(os.path.join(ROOT, "include", "fftw3_b200_dist.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fftwf?_b200_\w+)\s*\(", hdr)))
+    assert len(names) >= 40, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+    class _L:            # what dist._declare* need of binding.Lib
+        pass
+    shell = _L()
+    shell.lib = lib
+    dist._declare(shell)
+    dist._declare_mpi(shell)
+
+
 def test_exports_nothing_but_the_fftw_namespace():
     """A libfftw3.so.3 stand-in must not leak internals (C++ kernel templates, b2_* / b2d_* helpers):
     the linker version script fftw3_b200/csrc/exports.map keeps fftw_* and fftwf_* only."""

@@ -87,6 +87,21 @@ def test_peer_plans_all_ranks_in_one_process(emu_lib, mode, shape, P, sign):
     assert err <= 1e-14, (mode, shape, P, err)
 
 
+@pytest.mark.parametrize("mode", ["push", "transposed"])
+@pytest.mark.parametrize("shape,P,sign", [
+    ((8, 6, 10), 2, -1),
+    ((12, 10, 8), 3, +1),       # uneven column blocks (4, 4, 2): strided copies of different widths
+    ((6, 5, 4), 4, -1),         # the last rank owns no planes: nothing to copy from it
+    ((16, 16, 16), 4, -1),
+])
+def test_first_exchange_by_copy_engines(emu_lib, mode, shape, P, sign, monkeypatch):
+    """FFTW3_B200_DIST_EXCHANGE=copy: X runs in place (the rows a rank keeps go straight into its own exchange
+    buffer) and one strided copy per peer moves each chunk's blocks (csrc/host/dist.c, exchange_by_copy)."""
+    monkeypatch.setenv("FFTW3_B200_DIST_EXCHANGE", "copy")
+    err = _run(emu_lib, shape, P, mode, sign)
+    assert err <= 1e-14, (mode, shape, P, err)
+
+
 def _run_real(lib, shape, P, inplace):
     """r2c then c2r of a real n0 x n1 x n2 array over P simulated ranks; returns (err_fwd, err_roundtrip)."""
     D._declare(lib)
