@@ -96,6 +96,11 @@ typedef struct {
     int split_mode;           /* strided pass as two register-only sub-passes: 0 never, 1 when rows are >= 1 MiB apart, 2 whenever applicable */
     size_t split_bytes;       /* its group size                                                  */
     int split_lanes;
+    int real_unfused;         /* bit 0: even-size r2c keeps its split as a pass of its own, bit 1: c2r its merge   */
+    int r2r_transposes;       /* dense 2-d r2r with long columns: transposes around the column pass instead of two
+                                 line passes with transposed stores                                                */
+    int prime_mode;           /* prime sizes: 0 = rule (register-resident Bluestein kernel if any, else Rader),
+                                 1 = Rader, 2 = Bluestein                                                          */
 } b2_plan_opts;
 
 typedef struct b2_plan {

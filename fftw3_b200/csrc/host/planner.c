@@ -40,13 +40,18 @@ static void opts_from_env(b2_plan_opts *o)
     if ((e = getenv("FFTW3_B200_SPLIT_MB"))) o->split_bytes = (size_t)atol(e) << 20;
     if ((e = getenv("FFTW3_B200_SPLIT_KB"))) o->split_bytes = (size_t)atol(e) << 10;
     if ((e = getenv("FFTW3_B200_SPLIT_LANES"))) o->split_lanes = atoi(e);
+    if (getenv("FFTW3_B200_R2C_UNFUSED")) o->real_unfused |= 1;
+    if (getenv("FFTW3_B200_C2R_UNFUSED")) o->real_unfused |= 2;
+    if (getenv("FFTW3_B200_R2R_TRANSPOSES")) o->r2r_transposes = 1;
+    if ((e = getenv("FFTW3_B200_PRIME"))) o->prime_mode = !strcmp(e, "rader") ? 1 : (!strcmp(e, "bluestein") ? 2 : 0);
 }
 
 static int opts_pinned_by_env(void)
 {
     static const char *names[] = { "FFTW3_B200_L2_BLOCK_MB", "FFTW3_B200_L2_BLOCK_KB", "FFTW3_B200_L2_LANES",
         "FFTW3_B200_L2_KEEP", "FFTW3_B200_L2_PAIR", "FFTW3_B200_SPLIT", "FFTW3_B200_SPLIT_MB", "FFTW3_B200_SPLIT_KB",
-        "FFTW3_B200_SPLIT_LANES", "FFTW3_B200_FORCE_VARIANT" };
+        "FFTW3_B200_SPLIT_LANES", "FFTW3_B200_FORCE_VARIANT", "FFTW3_B200_R2C_UNFUSED", "FFTW3_B200_C2R_UNFUSED",
+        "FFTW3_B200_R2R_TRANSPOSES", "FFTW3_B200_R2R_UNFUSED", "FFTW3_B200_PRIME" };
     size_t i;
     for (i = 0; i < sizeof names / sizeof names[0]; ++i) if (getenv(names[i])) return 1;
     return 0;
@@ -786,7 +791,7 @@ static int fft1d_inner(b2_plan *p, void *vctx, const b2_dim *bd, int brank, int6
            Bluestein.  Taken when no register-resident Bluestein kernel exists for M (those beat the
            generic kernel by more than the length ratio); FFTW3_B200_PRIME=rader|bluestein overrides. */
         {
-            const char *force = getenv("FFTW3_B200_PRIME");
+            const char *force = p->opt.prime_mode == 1 ? "rader" : (p->opt.prime_mode == 2 ? "bluestein" : NULL);
             int rr[64];
             int can = !c->ops.pre_op && !c->ops.post_op && n >= 5 && n < 2000000000 && b2_is_prime(n) &&
                       b2_factorize(n - 1, c->prec, 0, rr) != 0 && single_pass_fits(n - 1, c->prec);
@@ -1338,7 +1343,7 @@ static int plan_r2c(b2_plan *p)
         size_t esz = 2 * real_size(q->prec);
         int i;
         in.re = mkref(BUF_IN0, 0); in.im = mkref(BUF_IN0, is); in.stride = 2 * is;
-        if (!getenv("FFTW3_B200_R2C_UNFUSED") && !(q->flags & B2F_UNALIGNED) && view_interleaved(p, out) && src0 == BUF_IN0) {
+        if (!(p->opt.real_unfused & 1) && !(q->flags & B2F_UNALIGNED) && view_interleaved(p, out) && src0 == BUF_IN0) {
             /* long lines (the half-size transform is a four-step): the split rides on the store of its second
                pass, so the line crosses HBM twice, not three times (rdft/ct-hc2c.c:146-273 fuses it the same way
                into the last twiddle codelet) */
@@ -1476,7 +1481,7 @@ static int plan_c2r(b2_plan *p)
         {
             b2_view iv;
             iv.re = mkref(src_re, 0); iv.im = mkref(src_im, im_off); iv.stride = is;
-            if (!getenv("FFTW3_B200_C2R_UNFUSED") && !(q->flags & B2F_UNALIGNED) && src_re == BUF_IN0 && im_off == 0 &&
+            if (!(p->opt.real_unfused & 2) && !(q->flags & B2F_UNALIGNED) && src_re == BUF_IN0 && im_off == 0 &&
                 view_interleaved(p, iv) && (const char *)p->prob.in1 - (const char *)p->prob.in0 == (ptrdiff_t)real_size(q->prec)) {
                 /* long lines (the half-size transform is a four-step): the merge rides on the load of its first
                    pass, so the line crosses HBM twice, not three times -- the mirror image of the r2c split that
@@ -1554,7 +1559,7 @@ static int plan_r2r(b2_plan *p)
        user's [k0][k1]), instead of bracketing the column pass with two transposes -- two launches, each array
        read and written once per dimension */
     if (q->sz.rnk == 2 && b2_tensor_count(&q->vecsz) == 1 && !getenv("FFTW3_B200_R2R_UNFUSED") &&
-        !getenv("FFTW3_B200_R2R_TRANSPOSES")) {
+        !p->opt.r2r_transposes) {
         int64_t n0 = q->sz.d[0].n, n1 = q->sz.d[1].n, m0, m1;
         size_t esz = 2 * real_size(q->prec);
         int radix[64], k0 = q->r2r_kind[0], k1 = q->r2r_kind[1];
@@ -1756,16 +1761,50 @@ static double time_plan(b2_plan *pl, int reps)
    the same problem reuse it. */
 static int plan_alternatives(const b2_problem *prob, const b2_plan_opts *base, b2_plan_opts *alts, int max)
 {
-    int n = 0, i;
-    int64_t bytes = 2 * (int64_t)real_size(prob->prec);
+    int n = 0, i, last = prob->sz.rnk - 1;
+    int64_t bytes = 2 * (int64_t)real_size(prob->prec), min_bytes;
+    const char *e = getenv("FFTW3_B200_ALT_MIN_KB");      /* tests: let small problems have alternatives */
     alts[n++] = *base;
-    if (prob->kind != B2_C2C || prob->sz.rnk < 2 || opts_pinned_by_env()) return n;
+    if (prob->sz.rnk < 1 || opts_pinned_by_env()) return n;
     for (i = 0; i < prob->sz.rnk; ++i) bytes *= prob->sz.d[i].n;
     for (i = 0; i < prob->vecsz.rnk; ++i) bytes *= prob->vecsz.d[i].n > 0 ? prob->vecsz.d[i].n : 1;
-    {
-        const char *e = getenv("FFTW3_B200_ALT_MIN_KB");      /* tests: let small problems have alternatives */
-        if (bytes < (e ? (int64_t)atol(e) << 10 : (int64_t)512 << 20)) return n;   /* arrays that (nearly) fit L2 gain nothing */
+    if (prob->kind != B2_C2C) bytes /= 2;
+    /* the decompositions below only differ on arrays of some size; timing them costs a few executes each */
+    min_bytes = e ? (int64_t)atol(e) << 10 : (int64_t)32 << 20;
+    if (prob->kind == B2_R2C || prob->kind == B2_C2R) {
+        /* even last dimension whose half-size transform is a four-step: split / merge fused into its outer
+           pass (the default) or as a pass of its own */
+        int64_t nl = prob->sz.d[last].n;
+        int tmp[64];
+        if (bytes >= min_bytes && nl % 2 == 0 && b2_factorize(nl / 2, prob->prec, 0, tmp) != 0 &&
+            !single_pass_fits(nl / 2, prob->prec) && n < max) {
+            alts[n] = *base; alts[n].real_unfused = 3; ++n;
+        }
+        return n;
     }
+    if (prob->kind == B2_R2R) {
+        /* dense 2-d array with long columns: two line passes with transposed stores (the default) or transposes
+           around the column pass */
+        if (bytes >= min_bytes && prob->sz.rnk == 2 && b2_tensor_count(&prob->vecsz) == 1 &&
+            (size_t)prob->sz.d[0].n * 8 * real_size(prob->prec) > 131072 && n < max) {
+            alts[n] = *base; alts[n].r2r_transposes = 1; ++n;
+        }
+        return n;
+    }
+    if (prob->kind != B2_C2C) return n;
+    /* prime dimensions: the rule's choice, Rader, Bluestein (dft/rader.c vs dft/bluestein.c -- the reference's
+       planner times both solvers too) */
+    if (bytes >= min_bytes) {
+        int has_prime = 0;
+        for (i = 0; i < prob->sz.rnk; ++i) if (prob->sz.d[i].n > 13 && b2_is_prime(prob->sz.d[i].n)) has_prime = 1;
+        if (has_prime) {
+            if (n < max) { alts[n] = *base; alts[n].prime_mode = 1; ++n; }
+            if (n < max) { alts[n] = *base; alts[n].prime_mode = 2; ++n; }
+            return n;
+        }
+    }
+    if (prob->sz.rnk < 2) return n;
+    if (bytes < (e ? (int64_t)atol(e) << 10 : (int64_t)512 << 20)) return n;   /* arrays that (nearly) fit L2 gain nothing */
     {
         /* group sizes relative to the array so that the same code paths run on the tests' small problems */
         size_t g32 = (size_t)32 << 20, g16 = (size_t)16 << 20;
@@ -1811,8 +1850,10 @@ static b2_plan *mkplan_locked(const b2_problem *prob)
         if (!pl) continue;
         t = pl->is_nop ? 0.0 : time_plan(pl, 3);
         if (getenv("FFTW3_B200_VERBOSE"))
-            fprintf(stderr, "[b200 planner] whole-plan alternative %d (l2 %zu MiB x %d lanes, split %d): %d steps, %.3f ms\n", a,
-                    alts[a].l2_block_bytes >> 20, alts[a].l2_lanes, alts[a].split_mode, pl->nsteps, t);
+            fprintf(stderr, "[b200 planner] whole-plan alternative %d (l2 %zu MiB x %d lanes, split %d, real-unfused %d, "
+                            "r2r-transposes %d, prime-mode %d): %d steps, %.3f ms\n", a,
+                    alts[a].l2_block_bytes >> 20, alts[a].l2_lanes, alts[a].split_mode, alts[a].real_unfused,
+                    alts[a].r2r_transposes, alts[a].prime_mode, pl->nsteps, t);
         if (t >= 0 && t < bestt) { if (best) plan_destroy_locked(best); best = pl; bestt = t; chosen = a; }
         else plan_destroy_locked(pl);
     }
