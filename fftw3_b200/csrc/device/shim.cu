@@ -167,6 +167,11 @@ int b2d_memcpy_d2h(void *d, const void *s, size_t n)
     e = cudaStreamSynchronize(g_stream);
     return e == cudaSuccess ? 0 : fail(e, "memcpy d2h sync");
 }
+int b2d_memcpy_d2h_async(void *d, const void *s, size_t n)
+{
+    cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, g_stream);
+    return e == cudaSuccess ? 0 : fail(e, "memcpy d2h");
+}
 int b2d_memcpy_d2d(void *d, const void *s, size_t n)
 {
     cudaError_t e = cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, g_stream);
@@ -211,6 +216,14 @@ void b2d_pop_stream(void *prev)
 {
     if (t_stream_depth > 0) --t_stream_depth;
     t_stream = (cudaStream_t)prev;
+}
+
+void *b2d_pipe_stream(int idx)
+{
+    static cudaStream_t ps[3] = { nullptr, nullptr, nullptr };
+    if (ensure_init() || idx < 0 || idx >= 3) return nullptr;
+    if (!ps[idx] && cudaStreamCreateWithFlags(&ps[idx], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (void *)ps[idx];
 }
 
 void *b2d_aux_stream(int idx)

@@ -123,8 +123,17 @@ typedef struct b2_plan {
     /* host staging state (execute on host pointers) */
     void *stage_dev[4];
     size_t stage_cap[4];
+    /* host arrays, batched problem: the outermost batch dimension is cut into pipe_chunks chunks that run through
+       three copies of a chunk-sized plan on three streams, so that the upload of chunk c + 1, the passes of chunk c
+       and the download of chunk c - 1 overlap (PCIe is full duplex); offsets per chunk in reals */
+    struct b2_plan *pipe[3];
+    int pipe_chunks;
+    int64_t pipe_in_off, pipe_out_off;
     void *lock;               /* pthread_mutex_t* */
 } b2_plan;
+
+/* exec.c: first / last real reached through user pointer `which` (0, 1 = in; 2, 3 = out) */
+void b2_problem_span(const b2_problem *q, int which, int64_t *lo, int64_t *hi);
 
 /* tensor.c */
 void b2_tensor_init(b2_tensor *t, int rnk);

@@ -114,6 +114,8 @@ static void touched_span(const b2_problem *q, int which /*0..3*/, int64_t *lo, i
     b2_tensor_span(&t, is_out, lo, hi);
 }
 
+void b2_problem_span(const b2_problem *q, int which, int64_t *lo, int64_t *hi) { touched_span(q, which, lo, hi); }
+
 static int64_t touched_count(const b2_problem *q, int which)
 {
     int is_out = which >= 2;
@@ -123,7 +125,8 @@ static int64_t touched_count(const b2_problem *q, int which)
     return b2_tensor_count(&t) * b2_tensor_count(&q->vecsz);
 }
 
-static int execute_host(b2_plan *p, void *const user[4])
+/* async: enqueue only (upload, passes, download all on the current stream); the caller synchronises */
+static int execute_host(b2_plan *p, void *const user[4], int async)
 {
     const b2_problem *q = &p->prob;
     size_t rs = real_size(q->prec);
@@ -189,9 +192,34 @@ static int execute_host(b2_plan *p, void *const user[4])
         dev_user[i] = (map[i] >= 0) ? (char *)p->stage_dev[map[i]] + ((char *)user[i] - reg[map[i]].lo) : NULL;
     if (!rc) rc = run_steps(p, dev_user);
     for (i = 0; i < nreg && !rc; ++i)
-        if (reg[i].has_out) rc |= b2d_memcpy_d2h(reg[i].lo, p->stage_dev[i], (size_t)(reg[i].hi - reg[i].lo));
-    if (!rc) rc = b2d_sync();
+        if (reg[i].has_out) rc |= (async ? b2d_memcpy_d2h_async : b2d_memcpy_d2h)(reg[i].lo, p->stage_dev[i], (size_t)(reg[i].hi - reg[i].lo));
+    if (!rc && !async) rc = b2d_sync();
     if (rc) fprintf(stderr, "fftw3_b200: execute failed: %s\n", b2d_last_error());
+    return rc;
+}
+
+/* batched problem on host arrays: chunk c goes through chunk plan c % 3 on stream c % 3 (upload, passes, download in
+   stream order), so consecutive chunks overlap each other's transfers and passes; every chunk plan has its own
+   staging and scratch buffers, and a stream reuses them only after its previous chunk has left */
+static int execute_host_pipelined(b2_plan *p, void *const user[4])
+{
+    size_t rs = real_size(p->prob.prec);
+    int c, k, rc = 0;
+    for (c = 0; c < p->pipe_chunks && !rc; ++c) {
+        void *u[4], *st = b2d_pipe_stream(c % 3), *prev = NULL;
+        for (k = 0; k < 4; ++k)
+            u[k] = user[k] ? (char *)user[k] + (int64_t)c * (k < 2 ? p->pipe_in_off : p->pipe_out_off) * (int64_t)rs : NULL;
+        if (st) prev = b2d_push_stream(st);
+        rc = execute_host(p->pipe[c % 3], u, st != NULL);
+        if (st) b2d_pop_stream(prev);
+    }
+    for (k = 0; k < 3; ++k) {
+        void *st = b2d_pipe_stream(k), *prev;
+        if (!st) continue;
+        prev = b2d_push_stream(st);
+        rc |= b2d_sync();
+        b2d_pop_stream(prev);
+    }
     return rc;
 }
 
@@ -220,7 +248,7 @@ void b2_execute_ex(b2_plan *p, void *in0, void *in1, void *out0, void *out1, int
         if (rc) { fprintf(stderr, "fftw3_b200: %s\n", b2d_last_error()); abort(); }
     } else {
         if (m) pthread_mutex_lock(m);
-        rc = execute_host(p, user);
+        rc = p->pipe_chunks > 1 ? execute_host_pipelined(p, user) : execute_host(p, user, 0);
         if (m) pthread_mutex_unlock(m);
         if (rc) abort();
     }

@@ -1716,11 +1716,63 @@ void b2_planner_unlock(void) { pthread_mutex_unlock(&g_planner_mu); }
 static b2_plan *mkplan_locked(const b2_problem *prob);
 static void plan_destroy_locked(b2_plan *p);
 
+static b2_plan *build_plan(const b2_problem *prob, const b2_plan_opts *opt, int alt);
+
+/* Host arrays and a batch: cut the outermost batch dimension into chunks and build three chunk-sized plans for
+   exec.c's pipeline (upload of chunk c + 1 | passes of chunk c | download of chunk c - 1).  Only when consecutive
+   chunks touch disjoint, consecutive pieces of the user's arrays on both sides; a transform without a batch (the 3-d
+   headline) depends on all of its input and cannot be pipelined this way. */
+static void make_pipeline(b2_plan *p)
+{
+    const b2_problem *q = &p->prob;
+    static const int tries[] = { 8, 6, 5, 7, 4, 3, 2 };
+    const char *e;
+    b2_problem sub;
+    int d = -1, i, k, K = 0;
+    int64_t n, lo, hi, span_in = 0, span_out = 0, in_off, out_off, min_bytes;
+    size_t rs = real_size(q->prec);
+    if (p->is_nop || q->vecsz.rnk < 1 || q->vecsz.rnk == B2_RNK_MINFTY || q->vecsz.rnk > B2_MAXRANK) return;
+    if ((e = getenv("FFTW3_B200_PIPELINE")) && !atoi(e)) return;
+    if (b2d_pointer_is_device(q->in0 ? q->in0 : q->out0) != 0) return;
+    for (i = 0; i < q->vecsz.rnk; ++i)
+        if (q->vecsz.d[i].n > 1 && (d < 0 || q->vecsz.d[i].is > q->vecsz.d[d].is)) d = i;
+    if (d < 0 || q->vecsz.d[d].is <= 0 || q->vecsz.d[d].os <= 0) return;
+    n = q->vecsz.d[d].n;
+    for (i = 0; i < (int)(sizeof tries / sizeof tries[0]) && !K; ++i) if (n % tries[i] == 0) K = tries[i];
+    if (!K) return;
+    sub = *q;
+    sub.vecsz.d[d].n = n / K;
+    for (k = 0; k < 4; ++k) {
+        const void *ptr = k == 0 ? q->in0 : k == 1 ? q->in1 : k == 2 ? q->out0 : q->out1;
+        int64_t sp;
+        if (!ptr) continue;
+        b2_problem_span(&sub, k, &lo, &hi);
+        sp = hi - lo + 1;
+        /* the re and im pointers of one interleaved array together reach one real further than either alone */
+        if (k < 2 ? (q->in0 && q->in1 && q->in0 != q->in1) : (q->out0 && q->out1 && q->out0 != q->out1)) ++sp;
+        if (k < 2) { if (sp > span_in) span_in = sp; } else { if (sp > span_out) span_out = sp; }
+    }
+    in_off = q->vecsz.d[d].is * (n / K);
+    out_off = q->vecsz.d[d].os * (n / K);
+    if (in_off < span_in || out_off < span_out) return;          /* chunks would interleave in memory */
+    min_bytes = (e = getenv("FFTW3_B200_PIPE_MIN_KB")) ? (int64_t)atol(e) << 10 : (int64_t)32 << 20;
+    if ((span_in + span_out) * (int64_t)rs * K < min_bytes) return;
+    for (k = 0; k < 3; ++k) {
+        p->pipe[k] = build_plan(&sub, &p->opt, p->alt);
+        if (!p->pipe[k] || p->pipe[k]->is_nop) {
+            for (i = 0; i <= k; ++i) { plan_destroy_locked(p->pipe[i]); p->pipe[i] = NULL; }
+            return;
+        }
+    }
+    p->pipe_chunks = K; p->pipe_in_off = in_off; p->pipe_out_off = out_off;
+}
+
 b2_plan *b2_mkplan(const b2_problem *prob)
 {
     b2_plan *p;
     b2_planner_lock();
     p = mkplan_locked(prob);
+    if (p) make_pipeline(p);
     b2_planner_unlock();
     return p;
 }
@@ -1966,6 +2018,7 @@ static void plan_destroy_locked(b2_plan *p)
     free(p->tables);
     for (i = 0; i < B2_NSCRATCH; ++i) b2d_free(p->scratch[i]);
     for (i = 0; i < 4; ++i) b2d_free(p->stage_dev[i]);
+    for (i = 0; i < 3; ++i) plan_destroy_locked(p->pipe[i]);
     free(p->steps);
     free(p);
 }
@@ -1975,6 +2028,8 @@ void b2_plan_print(const b2_plan *p, FILE *f)
     int i, j;
     if (p->is_nop) { fprintf(f, "(b200-nop)"); return; }
     fprintf(f, "(b200-plan");
+    if (p->pipe_chunks > 1)
+        fprintf(f, " [host arrays: %d chunks pipelined through 3 streams]", p->pipe_chunks);
     if (p->opt.l2_block_bytes && p->prob.kind == B2_C2C && p->prob.sz.rnk >= 2)
         fprintf(f, " [L2-resident pass pairs: %zu KiB groups, %d lanes]", p->opt.l2_block_bytes >> 10, p->opt.l2_lanes);
     for (i = 0; i < p->nsteps; ++i) {

@@ -197,6 +197,7 @@ void *b2d_malloc_host(size_t bytes);     /* pinned */
 void b2d_free_host(void *p);
 int  b2d_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int  b2d_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int  b2d_memcpy_d2h_async(void *dst, const void *src, size_t bytes);   /* enqueue only: the caller synchronises the stream */
 int  b2d_memcpy_d2d(void *dst, const void *src, size_t bytes);
 /* `height` rows of `width` bytes between device (or peer-mapped) arrays, enqueued on `stream` for the copy engines */
 int  b2d_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, void *stream);
@@ -209,6 +210,7 @@ void *b2d_push_stream(void *cuda_stream);
 void b2d_pop_stream(void *prev);
 /* side streams for overlapping NVLink-bound kernels with HBM-bound ones */
 void *b2d_aux_stream(int idx);                           /* lazily created, non-blocking  */
+void *b2d_pipe_stream(int idx);                          /* 3 streams of the host-array pipeline (exec.c); NULL = none */
 /* Two streams bound to disjoint sets of SMs of the current device (CUDA green contexts): `comm_sms` SMs (a multiple of
  * 8) for an NVLink-bound kernel and the remaining SMs for the HBM-bound kernel that runs next to it, so that neither
  * waits behind the other inside an SM.  Created once per (device, comm_sms); 0 on success, -1 when the driver cannot

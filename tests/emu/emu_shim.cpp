@@ -152,6 +152,7 @@ void *b2d_malloc_host(size_t n) { void *p = NULL; if (posix_memalign(&p, 64, n ?
 void b2d_free_host(void *p) { free(p); }
 int b2d_memcpy_h2d(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int b2d_memcpy_d2h(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
+int b2d_memcpy_d2h_async(void *d, const void *s, size_t n) { memcpy(d, s, n); return 0; }
 int b2d_memcpy_d2d(void *d, const void *s, size_t n) { memmove(d, s, n); return 0; }
 int b2d_memcpy2d_async(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, void *)
 {
@@ -175,6 +176,7 @@ int b2d_peer_barrier(void *const *flags, int rank, int nranks, unsigned long lon
     return 0;
 }
 int b2d_partition_streams(int, void **, void **) { return -1; }   /* no SMs to partition here */
+void *b2d_pipe_stream(int) { return NULL; }                /* chunks then simply run one after the other */
 void *b2d_aux_stream(int) { return NULL; }                 /* everything is synchronous here */
 int b2d_stream_wait_stream(void *, void *) { return 0; }
 /* "IPC" between the threads that play ranks in a unit test: the handle is the pointer itself */

@@ -316,3 +316,68 @@ def test_rader_primes(emu_lib, prec, n, monkeypatch):
     p = emu_lib.plan_many_dft(prec, [n], 1, x.ctypes.data, None, 1, n, x.ctypes.data, None, 1, n, -1, B.FFTW_ESTIMATE)
     assert ("rader" in emu_lib.sprint_plan(prec, p)) == (n > 13)      # radices up to 13 are direct butterflies
     emu_lib.destroy_plan(prec, p)
+
+
+def test_host_arrays_batch_pipeline(emu_lib, monkeypatch):
+    """Batched problems on host arrays are cut along the outermost batch dimension into chunks that run through three
+    chunk plans (upload | passes | download overlap on the GPU; here the chunks run one after the other, which checks
+    offsets, regions and staging).  Batches that interleave in memory are not cut."""
+    monkeypatch.setenv("FFTW3_B200_PIPE_MIN_KB", "1")
+    rng = np.random.default_rng(11)
+    # c2c, out of place and in place, 24 transforms -> 8 chunks of 3
+    for inplace in (False, True):
+        x = F.rand_complex(rng, (24, 96), "d")
+        x0 = x.copy()
+        y = x if inplace else np.zeros_like(x)
+        p = emu_lib.plan_many_dft("d", [96], 24, x.ctypes.data, None, 1, 96, y.ctypes.data, None, 1, 96, -1, B.FFTW_ESTIMATE)
+        assert "8 chunks pipelined" in emu_lib.sprint_plan("d", p)
+        emu_lib.execute("d", p)
+        assert O.rel_l2(y, O.dft(x0, rank=1)) < 1e-15
+        # new-array execute on other host arrays goes through the same pipeline
+        a = F.rand_complex(rng, (24, 96), "d")
+        a0 = a.copy()
+        b = a if inplace else np.zeros_like(a)
+        emu_lib.fn("d", "execute_dft")(p, a.ctypes.data, b.ctypes.data)
+        assert O.rel_l2(b, O.dft(a0, rank=1)) < 1e-15
+        emu_lib.destroy_plan("d", p)
+    # in-place r2c with padded rows, 2-d transforms, batch of 10 -> 5 chunks
+    n0, n1, hm = 6, 10, 10
+    buf = np.zeros((hm, n0, 2 * (n1 // 2 + 1)), dtype=np.float32)
+    xr = F.rand_real(rng, (hm, n0, n1), "f")
+    buf[:, :, :n1] = xr
+    p = emu_lib.plan_many_dft_r2c("f", [n0, n1], hm, buf.ctypes.data, None, 1, n0 * 2 * (n1 // 2 + 1),
+                                  buf.ctypes.data, None, 1, n0 * (n1 // 2 + 1), B.FFTW_ESTIMATE)
+    assert "5 chunks pipelined" in emu_lib.sprint_plan("f", p)
+    emu_lib.execute("f", p)
+    emu_lib.destroy_plan("f", p)
+    got = buf.view(np.complex64).reshape(hm, n0, n1 // 2 + 1)
+    assert O.rel_l2(got, np.fft.rfftn(xr.astype(np.float64), axes=(1, 2))) < 1e-6
+    # out-of-place r2c / c2r of contiguous lines (one pointer per real array: no re / im slack)
+    n, hm = 512, 16
+    xr = F.rand_real(rng, (hm, n), "d")
+    X = np.zeros((hm, n // 2 + 1), dtype=np.complex128)
+    p = emu_lib.plan_many_dft_r2c("d", [n], hm, xr.ctypes.data, None, 1, n, X.ctypes.data, None, 1, n // 2 + 1, B.FFTW_ESTIMATE)
+    assert "8 chunks pipelined" in emu_lib.sprint_plan("d", p)
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(X, np.fft.rfft(xr, axis=1)) < 1e-15
+    back = np.zeros_like(xr)
+    p = emu_lib.plan_many_dft_c2r("d", [n], hm, X.ctypes.data, None, 1, n // 2 + 1, back.ctypes.data, None, 1, n, B.FFTW_ESTIMATE)
+    assert "8 chunks pipelined" in emu_lib.sprint_plan("d", p)
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(back / n, xr) < 1e-15
+    # the batch index is the fastest one in memory: chunks would interleave, so the plan is not cut
+    z = F.rand_complex(rng, (64, 16), "d")          # element j of transform b at z[j][b]
+    z0 = z.copy()
+    p = emu_lib.plan_many_dft("d", [64], 16, z.ctypes.data, None, 16, 1, z.ctypes.data, None, 16, 1, -1, B.FFTW_ESTIMATE)
+    assert "pipelined" not in emu_lib.sprint_plan("d", p)
+    emu_lib.execute("d", p)
+    emu_lib.destroy_plan("d", p)
+    assert O.rel_l2(z, np.fft.fft(z0, axis=0)) < 1e-15
+    # switched off
+    monkeypatch.setenv("FFTW3_B200_PIPELINE", "0")
+    x = F.rand_complex(rng, (24, 96), "d")
+    p = emu_lib.plan_many_dft("d", [96], 24, x.ctypes.data, None, 1, 96, x.ctypes.data, None, 1, 96, -1, B.FFTW_ESTIMATE)
+    assert "pipelined" not in emu_lib.sprint_plan("d", p)
+    emu_lib.destroy_plan("d", p)

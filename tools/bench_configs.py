@@ -43,17 +43,48 @@ def timeit(lib, prec, plan, reps, scale_fn=None):
     return best, launches
 
 
-def run_configs(lib, flags, peak, only="", echo=False):
+def e2e_host(lib, prec, make_plan, nbytes_in, nbytes_out, reps=3):
+    """The same transform through the public call on PINNED HOST arrays (fftw_malloc): upload, passes and download
+    inside the timed region, wall clock.  Batched problems go through the chunk pipeline of csrc/host/exec.c (upload of
+    chunk c + 1 | passes of chunk c | download of chunk c - 1); FFTW3_B200_PIPELINE=0 gives the serial path."""
+    import ctypes as C
+    mal, fre = lib.fn(prec, "malloc"), lib.fn(prec, "free")
+    mal.restype, mal.argtypes, fre.argtypes = C.c_void_p, [C.c_size_t], [C.c_void_p]
+    hin, hout = mal(nbytes_in), mal(nbytes_out)
+    C.memset(hin, 0, nbytes_in)
+    out = {}
+    for label, env in (("pipelined", None), ("serial", "0")):
+        if env is None:
+            os.environ.pop("FFTW3_B200_PIPELINE", None)
+        else:
+            os.environ["FFTW3_B200_PIPELINE"] = env
+        p = make_plan(hin, hout)
+        lib.execute(prec, p)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.execute(prec, p)
+        out[label] = (time.perf_counter() - t0) / reps * 1e3
+        out[label + "_plan"] = " ".join(lib.sprint_plan(prec, p).split())[:90]
+        lib.destroy_plan(prec, p)
+    os.environ.pop("FFTW3_B200_PIPELINE", None)
+    fre(hin); fre(hout)
+    return {"e2e_host_ms": out["pipelined"], "e2e_host_serial_ms": out["serial"], "e2e_h2d_bytes": nbytes_in,
+            "e2e_d2h_bytes": nbytes_out, "e2e_plan": out["pipelined_plan"]}
+
+
+def run_configs(lib, flags, peak, only="", echo=False, e2e=True):
     """Times the BASELINE.json configs other than the bench workload; returns one dict per config.
     `roofline_frac_1pass` = (one read + one write of the arrays) / time / peak: the fraction of the
     speed of light a plan that touched HBM exactly once would reach."""
     dev = "cuda"
     out = []
 
-    def report(name, flops, bytes_1pass, ms, launches, plan, prec):
+    def report(name, flops, bytes_1pass, ms, launches, plan, prec, extra=None):
         line = {"config": name, "ms": ms, "gflops": flops / ms / 1e6, "ideal_gbs_1pass": bytes_1pass / ms / 1e6,
                 "roofline_frac_1pass": bytes_1pass / ms / 1e6 / peak, "launches": launches,
                 "plan": " ".join(lib.sprint_plan(prec, plan).split())[:600]}
+        if extra:
+            line.update(extra)
         if echo:
             print(json.dumps(line), flush=True)
         out.append(line)
@@ -67,7 +98,9 @@ def run_configs(lib, flags, peak, only="", echo=False):
         y = torch.empty_like(x)
         p = lib.plan_many_dft("d", [n], hm, x.data_ptr(), None, 1, n, y.data_ptr(), None, 1, n, -1, flags)
         ms, l = timeit(lib, "d", p, 20)
-        report("C1 c2c f64 N=1024 x16384 out-of-place", 5 * n * hm * math.log2(n), 2 * 16 * n * hm, ms, l, p, "d")
+        ex = e2e_host(lib, "d", lambda a, b: lib.plan_many_dft("d", [n], hm, a, None, 1, n, b, None, 1, n, -1, B.FFTW_ESTIMATE),
+                      16 * n * hm, 16 * n * hm) if e2e else None
+        report("C1 c2c f64 N=1024 x16384 out-of-place", 5 * n * hm * math.log2(n), 2 * 16 * n * hm, ms, l, p, "d", ex)
         lib.destroy_plan("d", p)
         p = lib.plan_many_dft("d", [n], hm, x.data_ptr(), None, 1, n, x.data_ptr(), None, 1, n, -1, flags)
         ms, l = timeit(lib, "d", p, 20, lambda: x.mul_(1 / 32.0))
@@ -82,7 +115,9 @@ def run_configs(lib, flags, peak, only="", echo=False):
         assert p
         ms, l = timeit(lib, "f", p, 5)
         nb = 4 * n * hm + 8 * (n // 2 + 1) * hm
-        report("C2 r2c f32 N=2^20 x256", 2.5 * n * hm * math.log2(n), nb, ms, l, p, "f")
+        ex = e2e_host(lib, "f", lambda a, b: lib.plan_many_dft_r2c("f", [n], hm, a, None, 1, n, b, None, 1, n // 2 + 1, B.FFTW_ESTIMATE),
+                      4 * n * hm, 8 * (n // 2 + 1) * hm) if e2e else None
+        report("C2 r2c f32 N=2^20 x256", 2.5 * n * hm * math.log2(n), nb, ms, l, p, "f", ex)
         lib.destroy_plan("f", p)
         p = lib.plan_many_dft_c2r("f", [n], hm, y.data_ptr(), None, 1, n // 2 + 1, x.data_ptr(), None, 1, n, flags)
         assert p
