@@ -214,9 +214,20 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
     int64_t R = howmany, alloc;
     size_t cs = csize(prec);
     unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
+    ptrdiff_t nswap[8];
     if (!comm || !comm->allgather || rnk < 2 || rnk > 8 || howmany < 1 || !in || !out) return NULL;
     if (block || tblock) return NULL;                         /* default block sizes only */
-    if (flags & (FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT)) return NULL;
+    if (flags & (FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT)) return NULL;
+    if (flags & FFTW_MPI_TRANSPOSED_IN) {
+        /* input laid out [local_n1][n0][...] (mpi/fftw3-mpi.h:212-215, mpi/dft-rank-geq2-transposed.c): the
+           multi-dimensional DFT does not care which of its dimensions is called the first, so this is the same plan
+           with the first two dimensions swapped -- natural-order output of the user's problem is the
+           TRANSPOSED_OUT layout of the swapped one and vice versa */
+        for (i = 0; i < rnk; ++i) nswap[i] = n[i];
+        nswap[0] = n[1]; nswap[1] = n[0];
+        n = nswap;
+        flags = (flags & ~FFTW_MPI_TRANSPOSED_IN) ^ FFTW_MPI_TRANSPOSED_OUT;
+    }
     if (sign != -1 && sign != 1) return NULL;
     P = comm->nranks; r = comm->rank;
     if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;

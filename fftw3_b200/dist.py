@@ -26,6 +26,7 @@ import torch.distributed as dist
 from . import binding as B
 
 FFTW_MPI_TRANSPOSED_OUT = 1 << 30          # same bit as mpi/fftw3-mpi.h:214
+FFTW_MPI_TRANSPOSED_IN = 1 << 29
 
 
 def _declare(lib):
@@ -172,7 +173,7 @@ class CommPlan:
     memory from cudaMalloc / fftw_b200_device_malloc), transformed in place unless `out` is given."""
 
     def __init__(self, lib, n, comm, local_ptr, out_ptr=None, howmany=1, prec="d", sign=B.FFTW_FORWARD,
-                 flags=B.FFTW_ESTIMATE, transposed_out=False):
+                 flags=B.FFTW_ESTIMATE, transposed_out=False, transposed_in=False):
         _declare(lib)
         _declare_mpi(lib)
         self.L = lib.lib
@@ -183,7 +184,7 @@ class CommPlan:
                                                                         *[C.byref(x) for x in v]))
         self.ln0, self.s0, self.ln1, self.s1 = [int(x.value) for x in v]
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_dft")
-        fl = int(flags) | (FFTW_MPI_TRANSPOSED_OUT if transposed_out else 0)
+        fl = int(flags) | (FFTW_MPI_TRANSPOSED_OUT if transposed_out else 0) | (FFTW_MPI_TRANSPOSED_IN if transposed_in else 0)
         self.plan = fn(len(n), nn, howmany, 0, 0, local_ptr, out_ptr if out_ptr is not None else local_ptr,
                        C.byref(comm), int(sign), fl)
 

@@ -37,7 +37,7 @@ class ThreadComm:
         return cs
 
 
-def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True):
+def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True, transposed_in=False):
     D._declare(lib)
     L = lib.lib
     cdt = np.complex64 if prec == "f" else np.complex128
@@ -65,10 +65,15 @@ def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True
             a = L.fftw_b200_device_malloc(max(alloc, 1) * isz)
             b = a if inplace else L.fftw_b200_device_malloc(max(alloc, 1) * isz)
             view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(alloc, 1) * isz,)).view(cdt)
-            if ln0:
+            if transposed_in:
+                # this rank holds columns [s1, s1 + ln1) of the global array as [ln1][n0][rest]
+                if ln1:
+                    piece = np.ascontiguousarray(np.moveaxis(full[:, s1:s1 + ln1], 1, 0))
+                    view(a)[:piece.size] = piece.reshape(-1)
+            elif ln0:
                 view(a)[:full[s0:s0 + ln0].size] = full[s0:s0 + ln0].reshape(-1)
             pl = D.CommPlan(lib, list(n), comm, a, None if inplace else b, howmany=howmany, prec=prec, sign=sign,
-                            transposed_out=transposed)
+                            transposed_out=transposed, transposed_in=transposed_in)
             assert pl.plan, "plan_many_dft returned NULL on rank %d" % r
             pl.execute()
             rest = int(np.prod(shape[2:])) if len(shape) > 2 else 1
@@ -111,6 +116,10 @@ def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True
     ((8, 6, 10), 2, {"prec": "f"}),                       # fftwf_b200_mpi_*
     ((8, 6, 10), 2, {"inplace": False}),
     ((17, 19, 3), 2, {}),                                 # non-smooth distributed dims
+    ((8, 6, 10), 2, {"transposed_in": True}),             # FFTW_MPI_TRANSPOSED_IN: input [local_n1][n0][n2]
+    ((12, 10, 7), 3, {"transposed_in": True, "transposed": True, "sign": 1}),
+    ((9, 10), 3, {"transposed_in": True, "inplace": False}),
+    ((6, 8, 5), 2, {"transposed_in": True, "howmany": 2}),
 ])
 def test_comm_interface_all_ranks_as_threads(emu_lib, n, P, kw):
     err = _run(emu_lib, n, P, **kw)
