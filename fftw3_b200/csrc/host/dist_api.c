@@ -53,6 +53,13 @@ static int64_t share(int64_t n, int p, int r)
     if (lo >= n) return 0;
     return (n - lo < b) ? n - lo : b;
 }
+/* share of rank r under an explicit block size (fftw_mpi's block / tblock arguments, mpi/block.c:52-70) */
+static int64_t shareb(int64_t n, int64_t b, int r)
+{
+    int64_t lo = b * r;
+    if (lo >= n) return 0;
+    return (n - lo < b) ? n - lo : b;
+}
 static size_t csize(int prec) { return prec == B2D_F32 ? 8 : 16; }
 
 /* ------------------------------------------------------------------ local sizes (mpi/api.c:248-352) */
@@ -215,8 +222,9 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
     size_t cs = csize(prec);
     unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
     ptrdiff_t nswap[8];
+    int64_t B0, B1;
     if (!comm || !comm->allgather || rnk < 2 || rnk > 8 || howmany < 1 || !in || !out) return NULL;
-    if (block || tblock) return NULL;                         /* default block sizes only */
+    if (block < 0 || tblock < 0) return NULL;
     if (flags & (FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT)) return NULL;
     if (flags & FFTW_MPI_TRANSPOSED_IN) {
         /* input laid out [local_n1][n0][...] (mpi/fftw3-mpi.h:212-215, mpi/dft-rank-geq2-transposed.c): the
@@ -227,6 +235,7 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
         nswap[0] = n[1]; nswap[1] = n[0];
         n = nswap;
         flags = (flags & ~FFTW_MPI_TRANSPOSED_IN) ^ FFTW_MPI_TRANSPOSED_OUT;
+        { ptrdiff_t t = block; block = tblock; tblock = t; }
     }
     if (sign != -1 && sign != 1) return NULL;
     P = comm->nranks; r = comm->rank;
@@ -239,8 +248,12 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
     p->prec = prec; p->rank = r; p->nranks = P; p->rnk = rnk; p->sign = sign;
     p->transposed_out = (flags & FFTW_MPI_TRANSPOSED_OUT) != 0;
     p->n0 = n[0]; p->n1 = n[1]; p->R = R;
-    p->b0 = blk(n[0], P); p->b1 = blk(n[1], P);
-    p->ln0 = share(n[0], P, r); p->ln1 = share(n[1], P, r);
+    /* block sizes: FFTW_MPI_DEFAULT_BLOCK (0) = ceil(n / P); a caller's own must still cover the dimension */
+    B0 = block > 0 ? block : blk(n[0], P);
+    B1 = tblock > 0 ? tblock : blk(n[1], P);
+    if (B0 * P < n[0] || B1 * P < n[1]) { free(p); return NULL; }
+    p->b0 = B0; p->b1 = B1;
+    p->ln0 = shareb(n[0], B0, r); p->ln1 = shareb(n[1], B1, r);
     p->s0 = p->b0 * r < n[0] ? p->b0 * r : n[0];
     p->s1 = p->b1 * r < n[1] ? p->b1 * r : n[1];
     p->in = in; p->out = out;
@@ -250,7 +263,8 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
     if (!ok) goto fail_collective;
 
     /* fused plans of dist.c: 3-D, double, one transform, in place, same pointer semantics */
-    if (rnk == 3 && howmany == 1 && prec == B2D_F64 && in == out && !getenv("FFTW3_B200_MPI_GENERAL")) {
+    if (rnk == 3 && howmany == 1 && prec == B2D_F64 && in == out && B0 == blk(n[0], P) && B1 == blk(n[1], P) &&
+        !getenv("FFTW3_B200_MPI_GENERAL")) {
         void *push[MAXP];
         for (d = 0; d < P; ++d) push[d] = (char *)p->peer_z[d] + cs * (size_t)(p->s0 * share(n[1], P, d) * n[2]);
         if (!p->transposed_out)
@@ -283,7 +297,7 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
             if (!p->local) ok = 0;
             /* scatter: my rows of column block d -> rank d's exchange buffer [n0][ln1(d)][R] at plane s0 */
             for (d = 0; d < P && ok; ++d) {
-                int64_t l1 = share(n[1], P, d);
+                int64_t l1 = shareb(n[1], p->b1, d);
                 if (!l1) continue;
                 problem(&q, prec, pflags | B2F_ESTIMATE, (char *)out + cs / 2 * (size_t)(p->b1 * d * inner),
                         (char *)p->peer_z[d] + cs / 2 * (size_t)(p->s0 * l1 * inner), -1);
@@ -309,7 +323,7 @@ static fftw_b200_mpi_plan mkplan(int prec, int rnk, const ptrdiff_t *n, ptrdiff_
                 if (!p->back[0]) ok = 0;
             } else for (d = 0; d < P && ok; ++d) {
                 /* rows of owner d -> its slab [ln0(d)][n1][R] at column s1 */
-                int64_t l0 = share(n[0], P, d);
+                int64_t l0 = shareb(n[0], p->b0, d);
                 if (!l0) continue;
                 problem(&q, prec, pflags | B2F_ESTIMATE, p->zbuf + cs / 2 * (size_t)(p->b0 * d * p->ln1 * inner),
                         (char *)p->peer_out[d] + cs / 2 * (size_t)(p->s1 * inner), -1);
@@ -373,7 +387,7 @@ static fftw_b200_mpi_plan mktranspose(int prec, ptrdiff_t n0, ptrdiff_t n1, ptrd
     int d, P, r, ok = 1, inplace = (in == out);
     size_t rs = prec == B2D_F32 ? 4 : 8;
     int64_t hm = howmany, alloc;
-    if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || howmany < 1 || !in || !out || block0 || block1) return NULL;
+    if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || howmany < 1 || !in || !out || block0 < 0 || block1 < 0) return NULL;
     P = comm->nranks; r = comm->rank;
     if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
     if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
@@ -381,8 +395,9 @@ static fftw_b200_mpi_plan mktranspose(int prec, ptrdiff_t n0, ptrdiff_t n1, ptrd
     if (!p) return NULL;
     p->kind = 2; p->prec = prec; p->rank = r; p->nranks = P;
     p->n0 = n0; p->n1 = n1; p->R = hm;
-    p->b0 = blk(n0, P); p->b1 = blk(n1, P);
-    p->ln0 = share(n0, P, r); p->ln1 = share(n1, P, r);
+    p->b0 = block0 > 0 ? block0 : blk(n0, P); p->b1 = block1 > 0 ? block1 : blk(n1, P);
+    if (p->b0 * P < n0 || p->b1 * P < n1) { free(p); return NULL; }
+    p->ln0 = shareb(n0, p->b0, r); p->ln1 = shareb(n1, p->b1, r);
     p->s0 = p->b0 * r < n0 ? p->b0 * r : n0; p->s1 = p->b1 * r < n1 ? p->b1 * r : n1;
     p->in = in; p->out = out;
     alloc = p->b1 * n0 * hm;
@@ -390,7 +405,7 @@ static fftw_b200_mpi_plan mktranspose(int prec, ptrdiff_t n0, ptrdiff_t n1, ptrd
     if (ok && p->ln0 > 0) {
         for (d = 0; d < P && ok; ++d) {
             /* my rows, column block d -> rank d's [ln1(d)][n0][hm] at column s0 */
-            int64_t l1 = share(n1, P, d);
+            int64_t l1 = shareb(n1, p->b1, d);
             char *dst = (char *)(inplace ? p->peer_z[d] : p->peer_out[d]) + rs * (size_t)(p->s0 * hm);
             if (!l1) continue;
             rproblem(&q, prec, flags, (char *)in + rs * (size_t)(p->b1 * d * hm), dst);

@@ -160,12 +160,12 @@ class CommPlan1D:
 class CommTranspose(CommPlan1D):
     """fftw_mpi_plan_many_transpose: n0 x n1 matrix of howmany-tuples of reals, rows block-distributed"""
 
-    def __init__(self, lib, n0, n1, comm, in_ptr, out_ptr, howmany=1, prec="d", flags=B.FFTW_ESTIMATE):
+    def __init__(self, lib, n0, n1, comm, in_ptr, out_ptr, howmany=1, prec="d", flags=B.FFTW_ESTIMATE, block0=0, block1=0):
         _declare(lib)
         _declare_mpi(lib)
         self.L = lib.lib
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_transpose")
-        self.plan = fn(n0, n1, howmany, 0, 0, in_ptr, out_ptr, C.byref(comm), int(flags))
+        self.plan = fn(n0, n1, howmany, block0, block1, in_ptr, out_ptr, C.byref(comm), int(flags))
 
 
 class CommPlan:
@@ -173,19 +173,19 @@ class CommPlan:
     memory from cudaMalloc / fftw_b200_device_malloc), transformed in place unless `out` is given."""
 
     def __init__(self, lib, n, comm, local_ptr, out_ptr=None, howmany=1, prec="d", sign=B.FFTW_FORWARD,
-                 flags=B.FFTW_ESTIMATE, transposed_out=False, transposed_in=False):
+                 flags=B.FFTW_ESTIMATE, transposed_out=False, transposed_in=False, block=0, tblock=0):
         _declare(lib)
         _declare_mpi(lib)
         self.L = lib.lib
         self.comm = comm
         nn = (C.c_ssize_t * len(n))(*n)
         v = [C.c_ssize_t() for _ in range(4)]
-        self.alloc = int(self.L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, 0, 0, C.byref(comm),
+        self.alloc = int(self.L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, block, tblock, C.byref(comm),
                                                                         *[C.byref(x) for x in v]))
         self.ln0, self.s0, self.ln1, self.s1 = [int(x.value) for x in v]
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_dft")
         fl = int(flags) | (FFTW_MPI_TRANSPOSED_OUT if transposed_out else 0) | (FFTW_MPI_TRANSPOSED_IN if transposed_in else 0)
-        self.plan = fn(len(n), nn, howmany, 0, 0, local_ptr, out_ptr if out_ptr is not None else local_ptr,
+        self.plan = fn(len(n), nn, howmany, block, tblock, local_ptr, out_ptr if out_ptr is not None else local_ptr,
                        C.byref(comm), int(sign), fl)
 
     def execute(self):

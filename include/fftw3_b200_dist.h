@@ -126,8 +126,9 @@ void fftw_b200_dist_destroy_plan(fftw_b200_dist_plan p);
  * Arrays are DEVICE memory obtained from cudaMalloc (or fftw_b200_device_malloc): `in` / `out` hold this
  * rank's slab [local_n0][n1]...[howmany] with room for the number of elements local_size returns;
  * FFTW_MPI_TRANSPOSED_OUT leaves [local_n1][n0]..., FFTW_MPI_TRANSPOSED_IN expects the input that way (the two
- * combine); in == out for an in-place transform.  Only the default
- * block size (FFTW_MPI_DEFAULT_BLOCK) is supported.  Planning and execution are collective.
+ * combine); in == out for an in-place transform.  block / tblock:
+ * FFTW_MPI_DEFAULT_BLOCK (0) = ceil(n / P), or the caller's own block sizes (block * P >= n0, tblock * P >= n1; the
+ * plan then takes the general path).  Planning and execution are collective.
  * ====================================================================================================== */
 #define FFTW_MPI_DEFAULT_BLOCK (0)
 #define FFTW_MPI_SCRAMBLED_IN (1U << 27)

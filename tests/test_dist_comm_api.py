@@ -37,7 +37,7 @@ class ThreadComm:
         return cs
 
 
-def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True, transposed_in=False):
+def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True, transposed_in=False, block=0, tblock=0):
     D._declare(lib)
     L = lib.lib
     cdt = np.complex64 if prec == "f" else np.complex128
@@ -58,7 +58,7 @@ def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True
             nn = (C.c_ssize_t * len(n))(*n)
             v = [C.c_ssize_t() for _ in range(4)]
             D._declare_mpi(lib)
-            alloc = int(L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, 0, 0, C.byref(comm),
+            alloc = int(L.fftw_b200_mpi_local_size_many_transposed(len(n), nn, howmany, block, tblock, C.byref(comm),
                                                                   *[C.byref(x) for x in v]))
             ln0, s0, ln1, s1 = [int(x.value) for x in v]
             isz = np.dtype(cdt).itemsize
@@ -73,7 +73,7 @@ def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True
             elif ln0:
                 view(a)[:full[s0:s0 + ln0].size] = full[s0:s0 + ln0].reshape(-1)
             pl = D.CommPlan(lib, list(n), comm, a, None if inplace else b, howmany=howmany, prec=prec, sign=sign,
-                            transposed_out=transposed, transposed_in=transposed_in)
+                            transposed_out=transposed, transposed_in=transposed_in, block=block, tblock=tblock)
             assert pl.plan, "plan_many_dft returned NULL on rank %d" % r
             pl.execute()
             rest = int(np.prod(shape[2:])) if len(shape) > 2 else 1
@@ -120,6 +120,9 @@ def _run(lib, n, P, howmany=1, prec="d", sign=-1, transposed=False, inplace=True
     ((12, 10, 7), 3, {"transposed_in": True, "transposed": True, "sign": 1}),
     ((9, 10), 3, {"transposed_in": True, "inplace": False}),
     ((6, 8, 5), 2, {"transposed_in": True, "howmany": 2}),
+    ((8, 6, 10), 2, {"block": 5, "tblock": 4}),           # the caller's own block sizes (mpi/block.c:52-70): 5 + 3 planes, 4 + 2 columns
+    ((12, 10), 3, {"block": 6, "tblock": 4, "transposed": True}),      # 6 + 6 + 0 rows
+    ((9, 7, 4), 3, {"block": 4, "transposed_in": True}),
 ])
 def test_comm_interface_all_ranks_as_threads(emu_lib, n, P, kw):
     err = _run(emu_lib, n, P, **kw)
@@ -219,10 +222,12 @@ def test_distributed_1d_six_step(emu_lib, n0, P, kw):
     assert O.rel_l2(got, ref) <= (3e-6 if prec == "f" else 2e-14), (n0, P, kw)
 
 
+@pytest.mark.parametrize("blocks", [(0, 0), (1, 1)])
 @pytest.mark.parametrize("n0,n1,P,hm,inplace,prec", [(12, 10, 2, 1, False, "d"), (7, 9, 3, 2, False, "d"), (8, 6, 2, 1, True, "d"),
                                                      (5, 16, 4, 3, True, "f"), (64, 48, 2, 1, False, "d")])
-def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec):
-    """fftw_mpi_plan_many_transpose (mpi/api.c:521-556): bit-exact"""
+def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec, blocks):
+    """fftw_mpi_plan_many_transpose (mpi/api.c:521-556): bit-exact; blocks = (1, 1): the caller's own block sizes,
+    one more than the default on both sides (so the last rank gets less, possibly nothing)"""
     lib = emu_lib
     D._declare(lib)
     L = lib.lib
@@ -231,7 +236,7 @@ def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec):
     full = np.arange(n0 * n1 * hm, dtype=rdt).reshape(n0, n1, hm)
 
     def rank_main(r, comm):
-        b0, b1 = -(-n0 // P), -(-n1 // P)
+        b0, b1 = -(-n0 // P) + blocks[0], -(-n1 // P) + blocks[1]
         ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
         ln1, s1 = max(0, min(b1, n1 - b1 * r)), min(b1 * r, n1)
         cnt = max(b0 * n1, b1 * n0) * hm
@@ -239,7 +244,8 @@ def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec):
         b = a if inplace else L.fftw_b200_device_malloc(max(cnt, 1) * isz)
         view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(cnt, 1) * isz,)).view(rdt)
         view(a)[:ln0 * n1 * hm] = full[s0:s0 + ln0].reshape(-1)
-        pl = D.CommTranspose(lib, n0, n1, comm, a, b, howmany=hm, prec=prec)
+        pl = D.CommTranspose(lib, n0, n1, comm, a, b, howmany=hm, prec=prec,
+                             block0=b0 if blocks[0] else 0, block1=b1 if blocks[1] else 0)
         assert pl.plan
         pl.execute()
         out = (s1, view(b)[:ln1 * n0 * hm].copy().reshape(ln1, n0, hm))
