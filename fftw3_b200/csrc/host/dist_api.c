@@ -479,7 +479,9 @@ ptrdiff_t fftw_b200_mpi_local_size_1d(ptrdiff_t n0, const fftw_b200_comm *comm, 
     sr = br * k < r ? br * k : r; sm = bm * k < m ? bm * k : m;
     if (local_ni) *local_ni = (ptrdiff_t)(lr * m);
     if (local_i_start) *local_i_start = (ptrdiff_t)(sr * m);
-    if (flags & FFTW_MPI_SCRAMBLED_OUT) {
+    if (flags & (FFTW_MPI_SCRAMBLED_OUT | FFTW_MPI_SCRAMBLED_IN)) {
+        /* scrambled output stays [k1 in my block][k2]; a scrambled-input transform ends with the rows j1 of the
+           r x m view on their owners: the same distribution as the input */
         if (local_no) *local_no = (ptrdiff_t)(lr * m);
         if (local_o_start) *local_o_start = (ptrdiff_t)(sr * m);
     } else {
@@ -494,12 +496,13 @@ static fftw_b200_mpi_plan mkplan1d(int prec, ptrdiff_t n0, void *in, void *out, 
 {
     fftw_b200_mpi_plan p;
     b2_problem q;
-    int d, P, k, ok = 1, scrambled = (flags & FFTW_MPI_SCRAMBLED_OUT) != 0;
+    int d, P, k, ok = 1, scrambled = (flags & FFTW_MPI_SCRAMBLED_OUT) != 0, scr_in = (flags & FFTW_MPI_SCRAMBLED_IN) != 0;
     size_t cs = csize(prec);
     unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
     int64_t r, m, br, bm, lr, lm, sr, sm;
     if (!comm || !comm->allgather || n0 < 4 || !in || !out || (sign != -1 && sign != 1)) return NULL;
-    if (flags & (FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_TRANSPOSED_OUT)) return NULL;
+    if (flags & (FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_TRANSPOSED_OUT)) return NULL;
+    if (scr_in && scrambled) return NULL;
     P = comm->nranks; k = comm->rank;
     if (P < 1 || P > MAXP || k < 0 || k >= P) return NULL;
     if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
@@ -515,6 +518,49 @@ static fftw_b200_mpi_plan mkplan1d(int prec, ptrdiff_t n0, void *in, void *out, 
     p->n0 = r; p->n1 = m; p->R = 1; p->ln0 = lr; p->ln1 = lm; p->s0 = sr; p->s1 = sm; p->b0 = br; p->b1 = bm;
     p->in = in; p->out = out;
     ok = setup_peers(p, comm, out, (size_t)(r * bm > 0 ? r * bm : 1) * cs, (size_t)(br * m > 0 ? br * m : 1) * cs);
+    if (ok && scr_in) {
+        /* FFTW_MPI_SCRAMBLED_IN: the input is what a SCRAMBLED_OUT transform leaves -- element X[k1 + r k2] at
+           [k1 in my block][k2].  With j = j1 m + j2:  w^(jk) = w_r^(j1 k1) w_n^(j2 k1) w_m^(j2 k2), so
+             B'  FFT_m along my rows (over k2 -> j2) with the twiddle exp(-+2 pi i j2 k1 / n) in its store
+             T1  columns of block d -> rank d's Z1 = [k1 (all r)][j2 in its block]
+             A'  FFT_r down the columns of Z1 (over k1 -> j1)
+             T2  rows j1 of block d -> rank d's OUTPUT [j1 in its block][j2 (all m)]: natural order
+           two transposes instead of three. */
+        p->kind = 3;
+        if (lr > 0) {
+            problem(&q, prec, pflags, in, p->z2alloc, sign);
+            dim(&q.sz, m, 2, 2);
+            dim(&q.vecsz, lr, 2 * m, 2 * m);
+            q.tw_big_n = n0; q.tw_off = sr;
+            p->z = b2_mkplan(&q);
+            if (!p->z) ok = 0;
+            for (d = 0; d < P && ok; ++d) {
+                int64_t lmd = share(m, P, d), smd = bm * d < m ? bm * d : m;
+                if (!lmd) continue;
+                problem(&q, prec, pflags | B2F_ESTIMATE, p->z2alloc + cs * (size_t)smd, (char *)p->peer_z[d] + cs * (size_t)(sr * lmd), -1);
+                dim(&q.vecsz, lr, 2 * m, 2 * lmd);
+                dim(&q.vecsz, lmd, 2, 2);
+                p->scatter[d] = b2_mkplan(&q);
+                if (!p->scatter[d]) ok = 0;
+            }
+        }
+        if (ok && lm > 0) {
+            problem(&q, prec, pflags, p->zbuf, p->zbuf, sign);
+            dim(&q.sz, r, 2 * lm, 2 * lm);
+            dim(&q.vecsz, lm, 2, 2);
+            p->local = b2_mkplan(&q);
+            if (!p->local) ok = 0;
+            for (d = 0; d < P && ok; ++d) {
+                int64_t lrd = share(r, P, d), srd = br * d < r ? br * d : r;
+                if (!lrd) continue;
+                problem(&q, prec, pflags | B2F_ESTIMATE, p->zbuf + cs * (size_t)(srd * lm), (char *)p->peer_out[d] + cs * (size_t)sm, -1);
+                dim(&q.vecsz, lrd, 2 * lm, 2 * m);
+                dim(&q.vecsz, lm, 2, 2);
+                p->back[d] = b2_mkplan(&q);
+                if (!p->back[d]) ok = 0;
+            }
+        }
+    } else
     if (ok) {
         for (d = 0; d < P && ok && lr > 0; ++d) {
             /* T1: my rows, columns of block d -> rank d's Z1 [r][lm(d)] at row sr */
@@ -597,6 +643,16 @@ void fftw_b200_mpi_execute(fftw_b200_mpi_plan p)
         barrier(p);
         run(p->back[0]);
         barrier(p);                                     /* nobody overwrites an exchange buffer still being copied back */
+        if (!b2_async_mode) b2d_sync();
+        return;
+    }
+    if (p->kind == 3) {
+        run(p->z);                                                                             /* B' (+ twiddle) */
+        for (d = 0; d < p->nranks; ++d) run(p->scatter[(p->rank + 1 + d) % p->nranks]);      /* T1 */
+        barrier(p);
+        run(p->local);                                                                         /* A' */
+        for (d = 0; d < p->nranks; ++d) run(p->back[(p->rank + 1 + d) % p->nranks]);          /* T2 -> outputs */
+        barrier(p);
         if (!b2_async_mode) b2d_sync();
         return;
     }

@@ -141,12 +141,14 @@ def local_size_1d(lib, n0, comm, sign=B.FFTW_FORWARD, flags=0):
 class CommPlan1D:
     """fftw_mpi_plan_dft_1d through the communicator interface (six-step over the ranks)"""
 
-    def __init__(self, lib, n0, comm, in_ptr, out_ptr, prec="d", sign=B.FFTW_FORWARD, flags=B.FFTW_ESTIMATE, scrambled_out=False):
+    def __init__(self, lib, n0, comm, in_ptr, out_ptr, prec="d", sign=B.FFTW_FORWARD, flags=B.FFTW_ESTIMATE, scrambled_out=False,
+                 scrambled_in=False):
         _declare(lib)
         _declare_mpi(lib)
         self.L = lib.lib
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_dft_1d")
-        self.plan = fn(n0, in_ptr, out_ptr, C.byref(comm), int(sign), int(flags) | ((1 << 28) if scrambled_out else 0))
+        self.plan = fn(n0, in_ptr, out_ptr, C.byref(comm), int(sign),
+                       int(flags) | ((1 << 28) if scrambled_out else 0) | ((1 << 27) if scrambled_in else 0))
 
     def execute(self):
         self.L.fftw_b200_mpi_execute(self.plan)

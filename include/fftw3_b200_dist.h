@@ -187,7 +187,8 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdif
  * mpi/api.c:248-352 local_size_1d).  Input: this rank's local_ni consecutive points starting at local_i_start;
  * output: local_no points starting at local_o_start (the two distributions differ: rows of the r x m view on
  * input, rows of the m x r view on output).  FFTW_MPI_SCRAMBLED_OUT skips the last transpose (output element
- * X[k1 + r k2] stays at [k1][k2] in this rank's k1 block); SCRAMBLED_IN is not supported (NULL).  n0 must be
+ * X[k1 + r k2] stays at [k1][k2] in this rank's k1 block); FFTW_MPI_SCRAMBLED_IN takes its input in that layout and
+ * leaves natural order distributed like the input (two transposes; n0 / r must fit one pass).  n0 must be
  * composite with a smooth factor <= the one-pass limit, else 0 / NULL (as the reference, n0 must be composite). */
 ptrdiff_t fftw_b200_mpi_local_size_1d(ptrdiff_t n0, const fftw_b200_comm *comm, int sign, unsigned flags,
                                       ptrdiff_t *local_ni, ptrdiff_t *local_i_start,

@@ -222,6 +222,49 @@ def test_distributed_1d_six_step(emu_lib, n0, P, kw):
     assert O.rel_l2(got, ref) <= (3e-6 if prec == "f" else 2e-14), (n0, P, kw)
 
 
+@pytest.mark.parametrize("n0,P,prec,inplace", [(4096, 2, "d", False), (1000, 3, "d", True), (6 * 35, 4, "d", False), (2048, 2, "f", True)])
+def test_distributed_1d_scrambled_out_then_scrambled_in(emu_lib, n0, P, prec, inplace):
+    """FFTW_MPI_SCRAMBLED_OUT forward followed by FFTW_MPI_SCRAMBLED_IN backward (mpi/fftw3-mpi.h:209-211,
+    mpi/dft-rank1.c:224-340): the pair skips the transposes that would only put the spectrum in natural order; the
+    forward result is checked against the oracle through its [k1][k2] layout, the round trip returns n0 * x in
+    natural order."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    cdt = np.complex64 if prec == "f" else np.complex128
+    isz = np.dtype(cdt).itemsize
+    rng = np.random.default_rng(9)
+    x = (rng.uniform(-0.5, 0.5, n0) + 1j * rng.uniform(-0.5, 0.5, n0)).astype(cdt)
+
+    def rank_main(r, comm):
+        alloc, lni, si, lno, so = D.local_size_1d(lib, n0, comm, -1, 1 << 28)
+        alloc2, lni2, si2, lno2, so2 = D.local_size_1d(lib, n0, comm, +1, 1 << 27)
+        assert (lni2, si2) == (lno, so)                       # the scrambled layout is the same on both sides
+        cnt = max(alloc, alloc2, 1)
+        a = L.fftw_b200_device_malloc(cnt * isz)
+        b = a if inplace else L.fftw_b200_device_malloc(cnt * isz)
+        view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(cnt * isz,)).view(cdt)
+        view(a)[:lni] = x[si:si + lni]
+        fwd = D.CommPlan1D(lib, n0, comm, a, b, prec=prec, sign=-1, scrambled_out=True)
+        bwd = D.CommPlan1D(lib, n0, comm, b, a, prec=prec, sign=+1, scrambled_in=True)
+        assert fwd.plan and bwd.plan
+        fwd.execute()
+        spec = (so, view(b)[:lno].copy())
+        bwd.execute()
+        back = (so2, view(a)[:lno2].copy())
+        fwd.destroy(); bwd.destroy()
+        L.fftw_b200_device_free(a)
+        if not inplace:
+            L.fftw_b200_device_free(b)
+        return spec, back
+
+    res = _threads(P, rank_main)
+    back = np.zeros(n0, cdt)
+    for _, (so2, arr) in res:
+        back[so2:so2 + len(arr)] = arr
+    assert O.rel_l2(back / n0, x) <= (3e-6 if prec == "f" else 2e-14), (n0, P)
+
+
 @pytest.mark.parametrize("blocks", [(0, 0), (1, 1)])
 @pytest.mark.parametrize("n0,n1,P,hm,inplace,prec", [(12, 10, 2, 1, False, "d"), (7, 9, 3, 2, False, "d"), (8, 6, 2, 1, True, "d"),
                                                      (5, 16, 4, 3, True, "f"), (64, 48, 2, 1, False, "d")])
