@@ -128,8 +128,8 @@ def test_guru_wisdom_callbacks_and_introspection(L):
     L.dfftw_destroy_plan_(C.byref(plan))
     # wisdom through the Fortran character callbacks
     chars = []
-    WR = C.CFUNCTYPE(None, C.c_char_p, P)
-    wr = WR(lambda c, d: chars.append(c[:1]))
+    WR = C.CFUNCTYPE(None, C.POINTER(C.c_char), P)      # ONE character by reference (not a C string: c_char_p would strlen it)
+    wr = WR(lambda c, d: chars.append(c[0]))
     L.dfftw_export_wisdom_(wr, None)
     text = b"".join(chars)
     assert text.startswith(b"(fftw3_b200-") and b"b200_fft_pass" in text
