@@ -621,6 +621,76 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_1d(ptrdiff_t n0, fftwf_complex *in, f
                                               int sign, unsigned flags)
 { return mkplan1d(B2D_F32, n0, in, out, comm, sign, flags); }
 
+/* ------------------------------------------------------------------ real data and r2r, 3-D
+   fftw_mpi_plan_dft_r2c_3d / _c2r_3d / fftw_mpi_plan_r2r_3d (mpi/api.c:650-760, 770-886) behind the communicator
+   interface: the plans of dist.c (double precision, default blocks), this file adds the buffer exchange through the
+   callback and the device-side barriers between their stages.  Layout as fftw_mpi: real slab
+   [local_n0][n1][2 (n2/2+1)] (padded rows, may alias the complex slab [local_n0][n1][n2/2+1]); local sizes come from
+   fftw_b200_mpi_local_size_3d(n0, n1, n2/2+1) in complex elements. */
+static fftw_b200_mpi_plan mkreal3d(int what, ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, void *in, void *out,
+                                   const fftw_b200_comm *comm, const int *kinds, unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    int d, P, r, ok;
+    int64_t h = n2 / 2 + 1, b0, b1;
+    size_t zbytes;
+    void *slab, *push[MAXP];
+    unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
+    if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || n2 <= 0 || !in || !out || pflags != flags) return NULL;
+    P = comm->nranks; r = comm->rank;
+    if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    b0 = blk(n0, P); b1 = blk(n1, P);
+    p->kind = 4 + what; p->prec = B2D_F64; p->rank = r; p->nranks = P; p->rnk = 3;
+    p->n0 = n0; p->n1 = n1; p->R = what == 2 ? n2 : h; p->b0 = b0; p->b1 = b1;
+    p->ln0 = share(n0, P, r); p->ln1 = share(n1, P, r);
+    p->s0 = b0 * r < n0 ? b0 * r : n0; p->s1 = b1 * r < n1 ? b1 * r : n1;
+    p->in = in; p->out = out;
+    /* the array the peers write into: the complex slab (r2c: the output, c2r: the input), r2r: the slab itself */
+    slab = what == 1 ? in : out;
+    zbytes = what == 2 ? sizeof(double) * (size_t)(n0 * b1 * n2) : 16 * (size_t)(P * b0 * b1 * h);
+    ok = setup_peers(p, comm, slab, zbytes ? zbytes : 16, 0);
+    if (ok) {
+        if (what == 2) {
+            if (in != out) {
+                /* out of place: copy the slab, then transform the copy in place */
+                b2_problem q;
+                rproblem(&q, B2D_F64, pflags, in, out);
+                if (p->ln0 > 0) { dim(&q.vecsz, p->ln0 * n1 * n2, 1, 1); p->local = b2_mkplan(&q); if (!p->local) ok = 0; }
+            }
+            if (ok) p->fused = fftw_b200_dist_plan_r2r_3d(n0, n1, n2, r, P, (double *)out, (double *)p->zbuf, p->peer_out,
+                                                          p->peer_z, kinds, pflags);
+        } else {
+            for (d = 0; d < P; ++d) push[d] = (char *)p->peer_z[d] + 16 * (size_t)(r * b0 * b1 * h);
+            p->fused = what == 0
+                ? fftw_b200_dist_plan_dft_r2c_3d(n0, n1, n2, r, P, (double *)in, (fftw_complex *)out, (fftw_complex *)p->zbuf,
+                                                 push, p->peer_out, pflags)
+                : fftw_b200_dist_plan_dft_c2r_3d(n0, n1, n2, r, P, (fftw_complex *)in, (double *)out, (fftw_complex *)p->zbuf,
+                                                 push, p->peer_out, pflags);
+        }
+        if (!p->fused) ok = 0;
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, fftw_complex *out,
+                                                 const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal3d(0, n0, n1, n2, in, out, comm, NULL, flags); }
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex *in, double *out,
+                                                 const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal3d(1, n0, n1, n2, in, out, comm, NULL, flags); }
+fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, double *out,
+                                             const fftw_b200_comm *comm, fftw_r2r_kind kind0, fftw_r2r_kind kind1,
+                                             fftw_r2r_kind kind2, unsigned flags)
+{
+    int kinds[3];
+    kinds[0] = (int)kind0; kinds[1] = (int)kind1; kinds[2] = (int)kind2;
+    return mkreal3d(2, n0, n1, n2, in, out, comm, kinds, flags);
+}
+
 /* ------------------------------------------------------------------ execution */
 static void run(b2_plan *pl)
 {
@@ -643,6 +713,22 @@ void fftw_b200_mpi_execute(fftw_b200_mpi_plan p)
         barrier(p);
         run(p->back[0]);
         barrier(p);                                     /* nobody overwrites an exchange buffer still being copied back */
+        if (!b2_async_mode) b2d_sync();
+        return;
+    }
+    if (p->kind >= 4) {
+        if (p->kind == 6) {
+            /* r2r: a barrier before every stage (peers read each other's slabs and exchange buffers) */
+            int st;
+            run(p->local);
+            for (st = 0; st < 3; ++st) { barrier(p); fftw_b200_dist_execute_stage(p->fused, st); }
+        } else {
+            fftw_b200_dist_execute_stage(p->fused, 0);
+            barrier(p);                                 /* every row block has landed in my exchange buffer */
+            fftw_b200_dist_execute_stage(p->fused, 1);
+            barrier(p);                                 /* every rank's rows have landed in my complex slab */
+            if (p->kind == 5) fftw_b200_dist_execute_stage(p->fused, 2);
+        }
         if (!b2_async_mode) b2d_sync();
         return;
     }

@@ -125,6 +125,10 @@ def _declare_mpi(lib):
         f = getattr(L, pfx + "plan_many_transpose")
         f.restype = P
         f.argtypes = [S, S, S, S, S, P, P, CP, U]
+    for name, extra in (("plan_dft_r2c_3d", []), ("plan_dft_c2r_3d", []), ("plan_r2r_3d", [I, I, I])):
+        f = getattr(L, "fftw_b200_mpi_" + name)
+        f.restype = P
+        f.argtypes = [S, S, S, P, P, C.POINTER(CommStruct)] + extra + [U]
     L.fftw_b200_mpi_execute.argtypes = [P]
     L.fftw_b200_mpi_destroy_plan.argtypes = [P]
     L._mpi_declared = True
@@ -168,6 +172,21 @@ class CommTranspose(CommPlan1D):
         self.L = lib.lib
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_transpose")
         self.plan = fn(n0, n1, howmany, block0, block1, in_ptr, out_ptr, C.byref(comm), int(flags))
+
+
+class CommPlanReal3D(CommPlan1D):
+    """fftw_mpi_plan_dft_r2c_3d / _c2r_3d / fftw_mpi_plan_r2r_3d through the communicator interface (double)"""
+
+    def __init__(self, lib, n, comm, in_ptr, out_ptr, what="r2c", kinds=None, flags=B.FFTW_ESTIMATE):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        if what == "r2r":
+            ks = [B.R2R_KINDS[k] if isinstance(k, str) else int(k) for k in kinds]
+            self.plan = self.L.fftw_b200_mpi_plan_r2r_3d(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), ks[0], ks[1], ks[2], int(flags))
+        else:
+            fn = self.L.fftw_b200_mpi_plan_dft_r2c_3d if what == "r2c" else self.L.fftw_b200_mpi_plan_dft_c2r_3d
+            self.plan = fn(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), int(flags))
 
 
 class CommPlan:

@@ -183,6 +183,18 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_
                                               const fftw_b200_comm *comm, int sign, unsigned flags);
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in,
                                               fftwf_complex *out, const fftw_b200_comm *comm, int sign, unsigned flags);
+/* Real data and r2r in 3-D (fftw_mpi_plan_dft_r2c_3d / _c2r_3d / fftw_mpi_plan_r2r_3d, mpi/api.c:650-760, 770-886),
+ * double precision, default blocks.  Real slab [local_n0][n1][2 (n2/2+1)] doubles (padded rows; it may alias the
+ * complex slab [local_n0][n1][n2/2+1] for an in-place transform); allocate with
+ * fftw_b200_mpi_local_size_3d(n0, n1, n2/2+1, ...) complex elements.  c2r overwrites its input (as fftw_mpi's does).
+ * r2r: [local_n0][n1][n2] doubles, kindK along dimension K; out != in copies first. */
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, fftw_complex *out,
+                                                 const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex *in, double *out,
+                                                 const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, double *out,
+                                             const fftw_b200_comm *comm, fftw_r2r_kind kind0, fftw_r2r_kind kind1,
+                                             fftw_r2r_kind kind2, unsigned flags);
 /* Distributed 1-D transform of n0 = r * m points (six-step with three global transposes; mpi/dft-rank1.c:81-148,
  * mpi/api.c:248-352 local_size_1d).  Input: this rank's local_ni consecutive points starting at local_i_start;
  * output: local_no points starting at local_o_start (the two distributions differ: rows of the r x m view on

@@ -303,3 +303,93 @@ def test_distributed_transpose(emu_lib, n0, n1, P, hm, inplace, prec, blocks):
     for s1, arr in res:
         got[s1:s1 + arr.shape[0]] = arr
     assert np.array_equal(got, full.transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("shape,P,inplace", [((8, 6, 10), 2, False), ((8, 6, 10), 2, True), ((12, 10, 7), 3, False),
+                                              ((6, 5, 4), 4, True), ((17, 19, 6), 2, False)])
+def test_real_data_3d_through_the_communicator_interface(emu_lib, shape, P, inplace):
+    """fftw_mpi_plan_dft_r2c_3d / _c2r_3d shapes (mpi/api.c:650-760): padded real slabs, r2c against numpy's rfftn
+    of the whole array, c2r back to n0 n1 n2 x; uneven, idle and non-smooth blocks."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    n0, n1, n2 = shape
+    h = n2 // 2 + 1
+    rng = np.random.default_rng(13)
+    full = rng.uniform(-0.5, 0.5, shape)
+    ref = np.fft.rfftn(full)
+
+    def rank_main(r, comm):
+        nn = (C.c_ssize_t * 3)(n0, n1, h)
+        v = [C.c_ssize_t() for _ in range(4)]
+        D._declare_mpi(lib)
+        alloc = int(L.fftw_b200_mpi_local_size_many_transposed(3, nn, 1, 0, 0, C.byref(comm), *[C.byref(x) for x in v]))
+        ln0, s0 = int(v[0].value), int(v[1].value)
+        cplx = L.fftw_b200_device_malloc(max(alloc, 1) * 16)
+        real = cplx if inplace else L.fftw_b200_device_malloc(max(alloc, 1) * 16)
+        rview = np.ctypeslib.as_array(C.cast(real, C.POINTER(C.c_double)), shape=(max(alloc, 1) * 2,))
+        cview = np.ctypeslib.as_array(C.cast(cplx, C.POINTER(C.c_double)), shape=(max(alloc, 1) * 2,)).view(np.complex128)
+        pad = rview[:ln0 * n1 * 2 * h].reshape(ln0, n1, 2 * h)
+        pad[:, :, :n2] = full[s0:s0 + ln0]
+        fwd = D.CommPlanReal3D(lib, shape, comm, real, cplx, "r2c")
+        bwd = D.CommPlanReal3D(lib, shape, comm, cplx, real, "c2r")
+        assert fwd.plan and bwd.plan
+        pad[:, :, :n2] = full[s0:s0 + ln0]
+        fwd.execute()
+        spec = cview[:ln0 * n1 * h].copy().reshape(ln0, n1, h)
+        bwd.execute()
+        back = rview[:ln0 * n1 * 2 * h].reshape(ln0, n1, 2 * h)[:, :, :n2].copy()
+        fwd.destroy(); bwd.destroy()
+        L.fftw_b200_device_free(cplx)
+        if not inplace:
+            L.fftw_b200_device_free(real)
+        return s0, spec, back
+
+    res = _threads(P, rank_main)
+    got = np.zeros((n0, n1, h), np.complex128)
+    back = np.zeros(shape)
+    for s0, spec, b in res:
+        got[s0:s0 + spec.shape[0]] = spec
+        back[s0:s0 + b.shape[0]] = b
+    assert O.rel_l2(got, ref) <= 2e-14, (shape, P)
+    assert O.rel_l2(back / (n0 * n1 * n2), full) <= 2e-14, (shape, P)
+
+
+@pytest.mark.parametrize("shape,P,kinds,inplace", [((8, 6, 10), 2, ("REDFT10", "RODFT01", "R2HC"), True),
+                                                    ((9, 10, 4), 3, ("DHT", "REDFT00", "RODFT11"), False),
+                                                    ((6, 5, 4), 4, ("REDFT01", "REDFT10", "HC2R"), True)])
+def test_r2r_3d_through_the_communicator_interface(emu_lib, shape, P, kinds, inplace):
+    """fftw_mpi_plan_r2r_3d shape (mpi/api.c:770-886) against the oracle's separable r2r"""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    n0, n1, n2 = shape
+    rng = np.random.default_rng(17)
+    full = rng.uniform(-0.5, 0.5, shape)
+    ref = O.r2r(full, list(kinds))
+
+    def rank_main(r, comm):
+        b0 = -(-n0 // P)
+        ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
+        cnt = max(b0 * n1 * n2, 1)
+        a = L.fftw_b200_device_malloc(cnt * 8)
+        b = a if inplace else L.fftw_b200_device_malloc(cnt * 8)
+        view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(cnt,))
+        view(a)[:ln0 * n1 * n2] = full[s0:s0 + ln0].reshape(-1)
+        pl = D.CommPlanReal3D(lib, shape, comm, a, b, "r2r", kinds=kinds)
+        assert pl.plan
+        pl.execute()
+        out = view(b)[:ln0 * n1 * n2].copy().reshape(ln0, n1, n2)
+        if not inplace:
+            assert np.array_equal(view(a)[:ln0 * n1 * n2], full[s0:s0 + ln0].reshape(-1))
+        pl.destroy()
+        L.fftw_b200_device_free(a)
+        if not inplace:
+            L.fftw_b200_device_free(b)
+        return s0, out
+
+    res = _threads(P, rank_main)
+    got = np.zeros(shape)
+    for s0, arr in res:
+        got[s0:s0 + arr.shape[0]] = arr
+    assert O.rel_l2(got, ref) <= 2e-14, (shape, P, kinds)
