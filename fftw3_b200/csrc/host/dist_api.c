@@ -676,6 +676,93 @@ static fftw_b200_mpi_plan mkreal3d(int what, ptrdiff_t n0, ptrdiff_t n1, ptrdiff
     return p;
 }
 
+/* 2-D real data (fftw_mpi_plan_dft_r2c_2d / _c2r_2d): real slab [local_n0][2 (n1/2+1)] (padded rows), complex slab
+   [local_n0][h], h = n1/2 + 1.  r2c = local r2c of the rows, then the distributed c2c along n0 over the n0 x h
+   complex matrix (scatter column blocks | FFT_n0 | push rows back: the general path above with h playing n1 and no
+   local pass); c2r = the same backward, then the local c2r of the rows.  Natural layouts only (the TRANSPOSED
+   flags return NULL).  The complex slab is overwritten by c2r, as in fftw_mpi. */
+static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in, void *out, const fftw_b200_comm *comm,
+                                   unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    b2_problem q;
+    int d, P, r, ok;
+    int64_t h = n1 / 2 + 1, alloc;
+    const int sign = c2r ? 1 : -1;
+    const size_t cs = 16;
+    double *real = (double *)(c2r ? out : in);
+    char *cplx = (char *)(c2r ? in : out);
+    unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
+    if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || !in || !out) return NULL;
+    if (pflags != flags) return NULL;
+    P = comm->nranks; r = comm->rank;
+    if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    p->kind = c2r ? 8 : 7; p->prec = B2D_F64; p->rank = r; p->nranks = P; p->rnk = 2; p->sign = sign;
+    p->n0 = n0; p->n1 = h; p->R = 1;
+    p->b0 = blk(n0, P); p->b1 = blk(h, P);
+    p->ln0 = share(n0, P, r); p->ln1 = share(h, P, r);
+    p->s0 = p->b0 * r < n0 ? p->b0 * r : n0;
+    p->s1 = p->b1 * r < h ? p->b1 * r : h;
+    p->in = in; p->out = out;
+    alloc = p->b0 * h;
+    if (p->b1 * n0 > alloc) alloc = p->b1 * n0;
+    ok = setup_peers(p, comm, cplx, (size_t)(alloc > 0 ? alloc : 1) * cs, 0);
+    if (ok && p->ln0 > 0) {
+        /* rows: padded real rows <-> this rank's complex rows [ln0][h] */
+        memset(&q, 0, sizeof q);
+        q.prec = B2D_F64; q.kind = c2r ? B2_C2R : B2_R2C; q.flags = pflags;
+        b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
+        dim(&q.sz, n1, c2r ? 2 : 1, c2r ? 1 : 2);
+        dim(&q.vecsz, p->ln0, 2 * h, 2 * h);
+        if (c2r) { q.in0 = cplx; q.in1 = cplx + 8; q.out0 = real; }
+        else { q.in0 = real; q.out0 = cplx; q.out1 = cplx + 8; }
+        p->local = b2_mkplan(&q);
+        if (!p->local) ok = 0;
+    }
+    if (ok) {
+        /* scatter: my rows of column block d -> rank d's exchange buffer [n0][lh(d)] at row s0 */
+        for (d = 0; d < P && ok && p->ln0 > 0; ++d) {
+            int64_t l1 = share(h, P, d);
+            if (!l1) continue;
+            problem(&q, B2D_F64, pflags | B2F_ESTIMATE, cplx + cs * (size_t)(p->b1 * d), (char *)p->peer_z[d] + cs * (size_t)(p->s0 * l1), -1);
+            dim(&q.vecsz, p->ln0, 2 * h, 2 * l1);
+            dim(&q.vecsz, l1, 2, 2);
+            p->scatter[d] = b2_mkplan(&q);
+            if (!p->scatter[d]) ok = 0;
+        }
+        if (ok && p->ln1 > 0) {
+            problem(&q, B2D_F64, pflags, p->zbuf, p->zbuf, sign);
+            dim(&q.sz, n0, 2 * p->ln1, 2 * p->ln1);
+            dim(&q.vecsz, p->ln1, 2, 2);
+            p->z = b2_mkplan(&q);
+            if (!p->z) ok = 0;
+            for (d = 0; d < P && ok; ++d) {
+                /* rows of owner d -> its complex slab [ln0(d)][h] at column s1 */
+                int64_t l0 = share(n0, P, d);
+                if (!l0) continue;
+                problem(&q, B2D_F64, pflags | B2F_ESTIMATE, p->zbuf + cs * (size_t)(p->b0 * d * p->ln1),
+                        (char *)p->peer_out[d] + cs * (size_t)p->s1, -1);
+                dim(&q.vecsz, l0, 2 * p->ln1, 2 * h);
+                dim(&q.vecsz, p->ln1, 2, 2);
+                p->back[d] = b2_mkplan(&q);
+                if (!p->back[d]) ok = 0;
+            }
+        }
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, fftw_complex *out,
+                                                 const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal2d(0, n0, n1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_2d(ptrdiff_t n0, ptrdiff_t n1, fftw_complex *in, double *out,
+                                                 const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal2d(1, n0, n1, in, out, comm, flags); }
+
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, fftw_complex *out,
                                                  const fftw_b200_comm *comm, unsigned flags)
 { return mkreal3d(0, n0, n1, n2, in, out, comm, NULL, flags); }
@@ -713,6 +800,18 @@ void fftw_b200_mpi_execute(fftw_b200_mpi_plan p)
         barrier(p);
         run(p->back[0]);
         barrier(p);                                     /* nobody overwrites an exchange buffer still being copied back */
+        if (!b2_async_mode) b2d_sync();
+        return;
+    }
+    if (p->kind == 7 || p->kind == 8) {
+        /* 2-D real data: rows locally, columns through the exchange (c2r: the other way round) */
+        if (p->kind == 7) run(p->local);
+        for (d = 0; d < p->nranks; ++d) run(p->scatter[(p->rank + 1 + d) % p->nranks]);
+        barrier(p);
+        run(p->z);
+        for (d = 0; d < p->nranks; ++d) run(p->back[(p->rank + 1 + d) % p->nranks]);
+        barrier(p);
+        if (p->kind == 8) run(p->local);
         if (!b2_async_mode) b2d_sync();
         return;
     }

@@ -125,6 +125,10 @@ def _declare_mpi(lib):
         f = getattr(L, pfx + "plan_many_transpose")
         f.restype = P
         f.argtypes = [S, S, S, S, S, P, P, CP, U]
+    for name in ("plan_dft_r2c_2d", "plan_dft_c2r_2d"):
+        f = getattr(L, "fftw_b200_mpi_" + name)
+        f.restype = P
+        f.argtypes = [S, S, P, P, C.POINTER(CommStruct), U]
     for name, extra in (("plan_dft_r2c_3d", []), ("plan_dft_c2r_3d", []), ("plan_r2r_3d", [I, I, I])):
         f = getattr(L, "fftw_b200_mpi_" + name)
         f.restype = P
@@ -184,6 +188,9 @@ class CommPlanReal3D(CommPlan1D):
         if what == "r2r":
             ks = [B.R2R_KINDS[k] if isinstance(k, str) else int(k) for k in kinds]
             self.plan = self.L.fftw_b200_mpi_plan_r2r_3d(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), ks[0], ks[1], ks[2], int(flags))
+        elif len(n) == 2:
+            fn = self.L.fftw_b200_mpi_plan_dft_r2c_2d if what == "r2c" else self.L.fftw_b200_mpi_plan_dft_c2r_2d
+            self.plan = fn(n[0], n[1], in_ptr, out_ptr, C.byref(comm), int(flags))
         else:
             fn = self.L.fftw_b200_mpi_plan_dft_r2c_3d if what == "r2c" else self.L.fftw_b200_mpi_plan_dft_c2r_3d
             self.plan = fn(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), int(flags))

@@ -190,6 +190,13 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdif
  * r2r: [local_n0][n1][n2] doubles, kindK along dimension K; out != in copies first. */
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, fftw_complex *out,
                                                  const fftw_b200_comm *comm, unsigned flags);
+/* 2-D real data (fftw_mpi_plan_dft_r2c_2d / _c2r_2d): real slab [local_n0][2 (n1/2+1)], complex slab
+ * [local_n0][n1/2+1]; the halved dimension is the one exchanged, as in fftw_mpi.  Allocate with
+ * fftw_b200_mpi_local_size_2d(n0, n1/2+1, ...) complex elements.  Natural layouts only. */
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, fftw_complex *out,
+                                                 const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_2d(ptrdiff_t n0, ptrdiff_t n1, fftw_complex *in, double *out,
+                                                 const fftw_b200_comm *comm, unsigned flags);
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftw_complex *in, double *out,
                                                  const fftw_b200_comm *comm, unsigned flags);
 fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, double *out,

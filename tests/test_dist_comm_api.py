@@ -393,3 +393,52 @@ def test_r2r_3d_through_the_communicator_interface(emu_lib, shape, P, kinds, inp
     for s0, arr in res:
         got[s0:s0 + arr.shape[0]] = arr
     assert O.rel_l2(got, ref) <= 2e-14, (shape, P, kinds)
+
+
+@pytest.mark.parametrize("shape,P,inplace", [((8, 10), 2, False), ((8, 10), 2, True), ((12, 9), 3, False), ((6, 4), 4, True),
+                                              ((17, 22), 2, False)])
+def test_real_data_2d_through_the_communicator_interface(emu_lib, shape, P, inplace):
+    """fftw_mpi_plan_dft_r2c_2d / _c2r_2d shapes: the halved dimension (n1/2 + 1 complex columns) is the one that
+    is exchanged; r2c against numpy's rfft2 of the whole array, c2r back to n0 n1 x."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    n0, n1 = shape
+    h = n1 // 2 + 1
+    rng = np.random.default_rng(19)
+    full = rng.uniform(-0.5, 0.5, shape)
+    ref = np.fft.rfft2(full)
+
+    def rank_main(r, comm):
+        nn = (C.c_ssize_t * 2)(n0, h)
+        v = [C.c_ssize_t() for _ in range(4)]
+        D._declare_mpi(lib)
+        alloc = int(L.fftw_b200_mpi_local_size_many_transposed(2, nn, 1, 0, 0, C.byref(comm), *[C.byref(x) for x in v]))
+        ln0, s0 = int(v[0].value), int(v[1].value)
+        cplx = L.fftw_b200_device_malloc(max(alloc, 1) * 16)
+        real = cplx if inplace else L.fftw_b200_device_malloc(max(alloc, 1) * 16)
+        rview = np.ctypeslib.as_array(C.cast(real, C.POINTER(C.c_double)), shape=(max(alloc, 1) * 2,))
+        cview = np.ctypeslib.as_array(C.cast(cplx, C.POINTER(C.c_double)), shape=(max(alloc, 1) * 2,)).view(np.complex128)
+        pad = rview[:ln0 * 2 * h].reshape(ln0, 2 * h)
+        fwd = D.CommPlanReal3D(lib, shape, comm, real, cplx, "r2c")
+        bwd = D.CommPlanReal3D(lib, shape, comm, cplx, real, "c2r")
+        assert fwd.plan and bwd.plan
+        pad[:, :n1] = full[s0:s0 + ln0]
+        fwd.execute()
+        spec = cview[:ln0 * h].copy().reshape(ln0, h)
+        bwd.execute()
+        back = rview[:ln0 * 2 * h].reshape(ln0, 2 * h)[:, :n1].copy()
+        fwd.destroy(); bwd.destroy()
+        L.fftw_b200_device_free(cplx)
+        if not inplace:
+            L.fftw_b200_device_free(real)
+        return s0, spec, back
+
+    res = _threads(P, rank_main)
+    got = np.zeros((n0, h), np.complex128)
+    back = np.zeros(shape)
+    for s0, spec, b in res:
+        got[s0:s0 + spec.shape[0]] = spec
+        back[s0:s0 + b.shape[0]] = b
+    assert O.rel_l2(got, ref) <= 2e-14, (shape, P)
+    assert O.rel_l2(back / (n0 * n1), full) <= 2e-14, (shape, P)
