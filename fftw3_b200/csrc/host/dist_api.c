@@ -778,6 +778,43 @@ fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff
     return mkreal3d(2, n0, n1, n2, in, out, comm, kinds, flags);
 }
 
+/* ------------------------------------------------------------------ wisdom across ranks (mpi/wisdom-api.c:24-103)
+   fftw_mpi_gather_wisdom: rank 0 ends up with the union of every rank's wisdom; fftw_mpi_broadcast_wisdom: every
+   rank imports rank 0's.  One length all-gather + one padded-text all-gather through the communicator callback. */
+static void exchange_wisdom(const fftw_b200_comm *comm, int gather, char *(*export_str)(void), int (*import_str)(const char *))
+{
+    char *mine, *all = NULL, *padded = NULL;
+    unsigned long long len, *lens = NULL, maxlen = 0;
+    int d, P;
+    if (!comm || !comm->allgather || comm->nranks < 2) return;
+    P = comm->nranks;
+    mine = export_str();
+    len = mine ? (unsigned long long)strlen(mine) + 1 : 1;
+    lens = (unsigned long long *)calloc((size_t)P, sizeof *lens);
+    if (lens && !comm->allgather(comm->ctx, &len, lens, sizeof len)) {
+        for (d = 0; d < P; ++d) if (lens[d] > maxlen) maxlen = lens[d];
+        padded = (char *)calloc((size_t)maxlen, 1);
+        all = (char *)malloc((size_t)maxlen * (size_t)P);
+        if (padded && all) {
+            if (mine) memcpy(padded, mine, (size_t)len);
+            if (!comm->allgather(comm->ctx, padded, all, (size_t)maxlen)) {
+                if (gather) { if (comm->rank == 0) for (d = 1; d < P; ++d) import_str(all + (size_t)d * maxlen); }
+                else if (comm->rank != 0) import_str(all);
+            }
+        }
+    }
+    free(lens); free(padded); free(all); free(mine);
+}
+
+void fftw_b200_mpi_gather_wisdom(const fftw_b200_comm *comm)
+{ exchange_wisdom(comm, 1, fftw_export_wisdom_to_string, fftw_import_wisdom_from_string); }
+void fftw_b200_mpi_broadcast_wisdom(const fftw_b200_comm *comm)
+{ exchange_wisdom(comm, 0, fftw_export_wisdom_to_string, fftw_import_wisdom_from_string); }
+void fftwf_b200_mpi_gather_wisdom(const fftw_b200_comm *comm)
+{ exchange_wisdom(comm, 1, fftwf_export_wisdom_to_string, fftwf_import_wisdom_from_string); }
+void fftwf_b200_mpi_broadcast_wisdom(const fftw_b200_comm *comm)
+{ exchange_wisdom(comm, 0, fftwf_export_wisdom_to_string, fftwf_import_wisdom_from_string); }
+
 /* ------------------------------------------------------------------ execution */
 static void run(b2_plan *pl)
 {

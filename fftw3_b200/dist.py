@@ -133,6 +133,10 @@ def _declare_mpi(lib):
         f = getattr(L, "fftw_b200_mpi_" + name)
         f.restype = P
         f.argtypes = [S, S, S, P, P, C.POINTER(CommStruct)] + extra + [U]
+    for name in ("fftw_b200_mpi_gather_wisdom", "fftw_b200_mpi_broadcast_wisdom", "fftwf_b200_mpi_gather_wisdom",
+                 "fftwf_b200_mpi_broadcast_wisdom"):
+        getattr(L, name).restype = None
+        getattr(L, name).argtypes = [C.POINTER(CommStruct)]
     L.fftw_b200_mpi_execute.argtypes = [P]
     L.fftw_b200_mpi_destroy_plan.argtypes = [P]
     L._mpi_declared = True

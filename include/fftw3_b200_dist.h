@@ -183,6 +183,12 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_
                                               const fftw_b200_comm *comm, int sign, unsigned flags);
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in,
                                               fftwf_complex *out, const fftw_b200_comm *comm, int sign, unsigned flags);
+/* Wisdom across ranks (fftw_mpi_gather_wisdom / fftw_mpi_broadcast_wisdom, mpi/wisdom-api.c): after gather rank 0
+ * holds the union of every rank's wisdom; after broadcast every rank has imported rank 0's.  Collective. */
+void fftw_b200_mpi_gather_wisdom(const fftw_b200_comm *comm);
+void fftw_b200_mpi_broadcast_wisdom(const fftw_b200_comm *comm);
+void fftwf_b200_mpi_gather_wisdom(const fftw_b200_comm *comm);
+void fftwf_b200_mpi_broadcast_wisdom(const fftw_b200_comm *comm);
 /* Real data and r2r in 3-D (fftw_mpi_plan_dft_r2c_3d / _c2r_3d / fftw_mpi_plan_r2r_3d, mpi/api.c:650-760, 770-886),
  * double precision, default blocks.  Real slab [local_n0][n1][2 (n2/2+1)] doubles (padded rows; it may alias the
  * complex slab [local_n0][n1][n2/2+1] for an in-place transform); allocate with

@@ -3,6 +3,7 @@
 device layer is the unit-test double (tests/emu).  Mirrors how the reference
 tests its MPI code: several ranks on one machine, gather, compare
 (mpi/mpi-bench.c:66-120, mpi/Makefile.am:52-72)."""
+import ctypes as C
 import os
 import socket
 import sys
@@ -133,3 +134,65 @@ def test_batched_1d_shards_without_collective(emu_lib, world, n, howmany):
         seen += count
     assert seen == howmany
     assert O.rel_l2(got, O.dft(full, rank=1)) < 1e-14
+
+
+def _wisdom_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fftw3_b200 import binding as B
+        from fftw3_b200 import dist as D
+        lib = B.Lib(os.path.join(ROOT, "tests", "_emu", "libfftw3_b200_emu.so"))
+        D._declare(lib)
+        D._declare_mpi(lib)
+        comm = D.torch_comm()
+
+        def plans(n, flags):
+            x = np.zeros((4, n), dtype=np.complex128)
+            p = lib.plan_many_dft("d", [n], 4, x.ctypes.data, None, 1, n, x.ctypes.data, None, 1, n, -1, flags)
+            ok = bool(p)
+            if p:
+                lib.destroy_plan("d", p)
+            return ok
+
+        only = B.FFTW_MEASURE | B.FFTW_WISDOM_ONLY
+        res = {}
+        # rank 0 measures a size nobody else knows, then broadcasts
+        if rank == 0:
+            assert plans(1024, B.FFTW_MEASURE)
+        res["before_bcast"] = plans(1024, only)
+        lib.lib.fftw_b200_mpi_broadcast_wisdom(C.byref(comm))
+        res["after_bcast"] = plans(1024, only)
+        # the last rank measures another size, then everything is gathered on rank 0
+        if rank == world - 1:
+            assert plans(512, B.FFTW_MEASURE)
+        res["before_gather"] = plans(512, only)
+        lib.lib.fftw_b200_mpi_gather_wisdom(C.byref(comm))
+        res["after_gather"] = plans(512, only)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_wisdom_broadcast_and_gather_over_the_communicator(emu_lib):
+    """fftw_mpi_broadcast_wisdom / fftw_mpi_gather_wisdom (mpi/wisdom-api.c): FFTW_WISDOM_ONLY plans fail on the ranks
+    that have not measured a size and succeed once the wisdom has travelled (3 processes, gloo all-gather as the
+    communicator callback)."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wisdom_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert got[r]["before_bcast"] == (r == 0), got
+        assert got[r]["after_bcast"], got
+        assert got[r]["before_gather"] == (r == world - 1), got
+        assert got[r]["after_gather"] == (r in (0, world - 1)), got
