@@ -778,6 +778,221 @@ fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff
     return mkreal3d(2, n0, n1, n2, in, out, comm, kinds, flags);
 }
 
+/* ------------------------------------------------------------------ general r2r and real-data plans
+   fftw_mpi_plan_many_r2r (mpi/api.c:770-886) for any rank >= 2 and any howmany, both precisions: local r2r over
+   dimensions 1 .. rnk-1, column blocks pushed into the owners' exchange buffers, r2r along n0 there, rows pushed back
+   -- the sequence of the complex general path above (kind 0), on reals.  kinds[i] along dimension i. */
+static fftw_b200_mpi_plan mkr2r(int prec, int rnk, const ptrdiff_t *n, ptrdiff_t howmany, void *in, void *out,
+                                const fftw_b200_comm *comm, const int *kinds, unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    b2_problem q;
+    int i, d, P, r, ok = 1;
+    int64_t R = howmany, alloc, st;
+    size_t rs = prec == B2D_F32 ? 4 : 8;
+    if (!comm || !comm->allgather || rnk < 2 || rnk > 8 || howmany < 1 || !in || !out || !kinds) return NULL;
+    if (flags & (FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT)) return NULL;
+    P = comm->nranks; r = comm->rank;
+    if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
+    for (i = 0; i < rnk; ++i) if (n[i] <= 0 || kinds[i] < 0 || kinds[i] > 10) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    for (i = 2; i < rnk; ++i) R *= n[i];
+    p->prec = prec; p->rank = r; p->nranks = P; p->rnk = rnk;
+    p->n0 = n[0]; p->n1 = n[1]; p->R = R;
+    p->b0 = blk(n[0], P); p->b1 = blk(n[1], P);
+    p->ln0 = share(n[0], P, r); p->ln1 = share(n[1], P, r);
+    p->s0 = p->b0 * r < n[0] ? p->b0 * r : n[0];
+    p->s1 = p->b1 * r < n[1] ? p->b1 * r : n[1];
+    p->in = in; p->out = out;
+    alloc = p->b0 * n[1] * R;
+    if (p->b1 * n[0] * R > alloc) alloc = p->b1 * n[0] * R;
+    ok = setup_peers(p, comm, out, (size_t)(alloc > 0 ? alloc : 1) * rs, 0);
+    if (ok && p->ln0 > 0) {
+        /* local r2r over dims 1 .. rnk-1 of [ln0][n1]...[howmany], in -> out */
+        rproblem(&q, prec, flags, in, out);
+        q.flags = flags;
+        st = howmany;
+        for (i = rnk - 1; i >= 1; --i) { q.sz.d[i - 1].n = n[i]; q.sz.d[i - 1].is = q.sz.d[i - 1].os = st; st *= n[i]; q.r2r_kind[i - 1] = kinds[i]; }
+        q.sz.rnk = rnk - 1;
+        dim(&q.vecsz, p->ln0, n[1] * R, n[1] * R);
+        if (howmany > 1) dim(&q.vecsz, howmany, 1, 1);
+        p->local = b2_mkplan(&q);
+        if (!p->local) ok = 0;
+        for (d = 0; d < P && ok; ++d) {
+            int64_t l1 = share(n[1], P, d);
+            if (!l1) continue;
+            rproblem(&q, prec, flags, (char *)out + rs * (size_t)(p->b1 * d * R), (char *)p->peer_z[d] + rs * (size_t)(p->s0 * l1 * R));
+            dim(&q.vecsz, p->ln0, n[1] * R, l1 * R);
+            dim(&q.vecsz, l1 * R, 1, 1);
+            p->scatter[d] = b2_mkplan(&q);
+            if (!p->scatter[d]) ok = 0;
+        }
+    }
+    if (ok && p->ln1 > 0) {
+        rproblem(&q, prec, flags, p->zbuf, p->zbuf);
+        q.flags = flags;
+        dim(&q.sz, n[0], p->ln1 * R, p->ln1 * R);
+        q.r2r_kind[0] = kinds[0];
+        dim(&q.vecsz, p->ln1 * R, 1, 1);
+        p->z = b2_mkplan(&q);
+        if (!p->z) ok = 0;
+        for (d = 0; d < P && ok; ++d) {
+            int64_t l0 = share(n[0], P, d);
+            if (!l0) continue;
+            rproblem(&q, prec, flags, p->zbuf + rs * (size_t)(p->b0 * d * p->ln1 * R), (char *)p->peer_out[d] + rs * (size_t)(p->s1 * R));
+            dim(&q.vecsz, l0, p->ln1 * R, n[1] * R);
+            dim(&q.vecsz, p->ln1 * R, 1, 1);
+            p->back[d] = b2_mkplan(&q);
+            if (!p->back[d]) ok = 0;
+        }
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_r2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                               double *in, double *out, const fftw_b200_comm *comm,
+                                               const fftw_r2r_kind *kind, unsigned flags)
+{
+    int k[8], i;
+    if (iblock || oblock || rnk < 2 || rnk > 8 || !kind) return NULL;
+    for (i = 0; i < rnk; ++i) k[i] = (int)kind[i];
+    return mkr2r(B2D_F64, rnk, n, howmany, in, out, comm, k, flags);
+}
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_r2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                float *in, float *out, const fftw_b200_comm *comm,
+                                                const fftwf_r2r_kind *kind, unsigned flags)
+{
+    int k[8], i;
+    if (iblock || oblock || rnk < 2 || rnk > 8 || !kind) return NULL;
+    for (i = 0; i < rnk; ++i) k[i] = (int)kind[i];
+    return mkr2r(B2D_F32, rnk, n, howmany, in, out, comm, k, flags);
+}
+fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, double *out, const fftw_b200_comm *comm,
+                                             fftw_r2r_kind kind0, fftw_r2r_kind kind1, unsigned flags)
+{
+    ptrdiff_t n[2]; int k[2];
+    n[0] = n0; n[1] = n1; k[0] = (int)kind0; k[1] = (int)kind1;
+    return mkr2r(B2D_F64, 2, n, 1, in, out, comm, k, flags);
+}
+
+/* fftw_mpi_plan_many_dft_r2c / _c2r (mpi/api.c:650-760) for rank >= 3, any howmany, both precisions: r2c = local r2c
+   over dimensions 1 .. rnk-1 (last one halved: h = n_last/2 + 1), then the distributed c2c along n0 exactly as in the
+   complex general path, with R = n2 ... n_(rnk-2) h howmany complex numbers per (i0, i1); c2r = the same backward, then
+   the local c2r.  Real slab [local_n0][n1]...[2 h][howmany] (padded), complex slab [local_n0][n1]...[h][howmany]; the
+   complex slab is overwritten by c2r.  Rank 2 (the halved dimension itself is exchanged): mkreal2d above. */
+static fftw_b200_mpi_plan mkrealnd(int prec, int c2r, int rnk, const ptrdiff_t *n, ptrdiff_t howmany, void *in, void *out,
+                                   const fftw_b200_comm *comm, unsigned flags)
+{
+    fftw_b200_mpi_plan p;
+    b2_problem q;
+    int i, d, P, r, ok = 1;
+    const int sign = c2r ? 1 : -1;
+    int64_t h, R = howmany, alloc, inner, str, stc;
+    size_t cs = csize(prec), rs = cs / 2;
+    char *real = (char *)(c2r ? out : in), *cplx = (char *)(c2r ? in : out);
+    if (!comm || !comm->allgather || rnk < 3 || rnk > 8 || howmany < 1 || !in || !out) return NULL;
+    if (flags & (FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT)) return NULL;
+    P = comm->nranks; r = comm->rank;
+    if (P < 1 || P > MAXP || r < 0 || r >= P) return NULL;
+    for (i = 0; i < rnk; ++i) if (n[i] <= 0) return NULL;
+    if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
+    p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
+    if (!p) return NULL;
+    h = n[rnk - 1] / 2 + 1;
+    for (i = 2; i < rnk - 1; ++i) R *= n[i];
+    R *= h;
+    inner = 2 * R;                       /* reals per (i0, i1) row, both in the complex and in the padded real slab */
+    p->kind = c2r ? 8 : 0; p->prec = prec; p->rank = r; p->nranks = P; p->rnk = rnk; p->sign = sign;
+    p->n0 = n[0]; p->n1 = n[1]; p->R = R;
+    p->b0 = blk(n[0], P); p->b1 = blk(n[1], P);
+    p->ln0 = share(n[0], P, r); p->ln1 = share(n[1], P, r);
+    p->s0 = p->b0 * r < n[0] ? p->b0 * r : n[0];
+    p->s1 = p->b1 * r < n[1] ? p->b1 * r : n[1];
+    p->in = in; p->out = out;
+    alloc = p->b0 * n[1] * R;
+    if (p->b1 * n[0] * R > alloc) alloc = p->b1 * n[0] * R;
+    ok = setup_peers(p, comm, cplx, (size_t)(alloc > 0 ? alloc : 1) * cs, 0);
+    if (ok && p->ln0 > 0) {
+        /* local r2c / c2r over dims 1 .. rnk-1; strides in reals: real side (padded last dim 2h), complex side */
+        memset(&q, 0, sizeof q);
+        q.prec = prec; q.kind = c2r ? B2_C2R : B2_R2C; q.flags = flags;
+        b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
+        str = howmany; stc = 2 * howmany;
+        for (i = rnk - 1; i >= 1; --i) {
+            q.sz.d[i - 1].n = n[i];
+            q.sz.d[i - 1].is = c2r ? stc : str;
+            q.sz.d[i - 1].os = c2r ? str : stc;
+            if (i == rnk - 1) { str *= 2 * h; stc *= h; } else { str *= n[i]; stc *= n[i]; }
+        }
+        q.sz.rnk = rnk - 1;
+        dim(&q.vecsz, p->ln0, n[1] * inner, n[1] * inner);
+        if (howmany > 1) dim(&q.vecsz, howmany, c2r ? 2 : 1, c2r ? 1 : 2);
+        if (c2r) { q.in0 = cplx; q.in1 = cplx + rs; q.out0 = real; }
+        else { q.in0 = real; q.out0 = cplx; q.out1 = cplx + rs; }
+        p->local = b2_mkplan(&q);
+        if (!p->local) ok = 0;
+        for (d = 0; d < P && ok; ++d) {
+            int64_t l1 = share(n[1], P, d);
+            if (!l1) continue;
+            problem(&q, prec, flags | B2F_ESTIMATE, cplx + rs * (size_t)(p->b1 * d * inner),
+                    (char *)p->peer_z[d] + rs * (size_t)(p->s0 * l1 * inner), -1);
+            dim(&q.vecsz, p->ln0, n[1] * inner, l1 * inner);
+            dim(&q.vecsz, l1 * R, 2, 2);
+            p->scatter[d] = b2_mkplan(&q);
+            if (!p->scatter[d]) ok = 0;
+        }
+    }
+    if (ok && p->ln1 > 0) {
+        problem(&q, prec, flags, p->zbuf, p->zbuf, sign);
+        dim(&q.sz, n[0], p->ln1 * inner, p->ln1 * inner);
+        dim(&q.vecsz, p->ln1 * R, 2, 2);
+        p->z = b2_mkplan(&q);
+        if (!p->z) ok = 0;
+        for (d = 0; d < P && ok; ++d) {
+            int64_t l0 = share(n[0], P, d);
+            if (!l0) continue;
+            problem(&q, prec, flags | B2F_ESTIMATE, p->zbuf + rs * (size_t)(p->b0 * d * p->ln1 * inner),
+                    (char *)p->peer_out[d] + rs * (size_t)(p->s1 * inner), -1);
+            dim(&q.vecsz, l0, p->ln1 * inner, n[1] * inner);
+            dim(&q.vecsz, p->ln1 * R, 2, 2);
+            p->back[d] = b2_mkplan(&q);
+            if (!p->back[d]) ok = 0;
+        }
+    }
+    if (!agree(comm, ok)) { fftw_b200_mpi_destroy_plan(p); return NULL; }
+    return p;
+}
+
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                   double *in, fftw_complex *out, const fftw_b200_comm *comm, unsigned flags)
+{
+    if (iblock || oblock) return NULL;
+    if (rnk == 2 && howmany == 1) return mkreal2d(0, n[0], n[1], in, out, comm, flags);
+    return mkrealnd(B2D_F64, 0, rnk, n, howmany, in, out, comm, flags);
+}
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                   fftw_complex *in, double *out, const fftw_b200_comm *comm, unsigned flags)
+{
+    if (iblock || oblock) return NULL;
+    if (rnk == 2 && howmany == 1) return mkreal2d(1, n[0], n[1], in, out, comm, flags);
+    return mkrealnd(B2D_F64, 1, rnk, n, howmany, in, out, comm, flags);
+}
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                    float *in, fftwf_complex *out, const fftw_b200_comm *comm, unsigned flags)
+{
+    if (iblock || oblock) return NULL;
+    return mkrealnd(B2D_F32, 0, rnk, n, howmany, in, out, comm, flags);
+}
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                    fftwf_complex *in, float *out, const fftw_b200_comm *comm, unsigned flags)
+{
+    if (iblock || oblock) return NULL;
+    return mkrealnd(B2D_F32, 1, rnk, n, howmany, in, out, comm, flags);
+}
+
 /* ------------------------------------------------------------------ wisdom across ranks (mpi/wisdom-api.c:24-103)
    fftw_mpi_gather_wisdom: rank 0 ends up with the union of every rank's wisdom; fftw_mpi_broadcast_wisdom: every
    rank imports rank 0's.  One length all-gather + one padded-text all-gather through the communicator callback. */

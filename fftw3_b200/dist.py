@@ -125,6 +125,17 @@ def _declare_mpi(lib):
         f = getattr(L, pfx + "plan_many_transpose")
         f.restype = P
         f.argtypes = [S, S, S, S, S, P, P, CP, U]
+    for pfx in ("fftw_b200_mpi_", "fftwf_b200_mpi_"):
+        f = getattr(L, pfx + "plan_many_r2r")
+        f.restype = P
+        f.argtypes = [I, SP, S, S, S, P, P, C.POINTER(CommStruct), C.POINTER(I), U]
+    for pfx in ("fftw_b200_mpi_", "fftwf_b200_mpi_"):
+        for nm in ("plan_many_dft_r2c", "plan_many_dft_c2r"):
+            f = getattr(L, pfx + nm)
+            f.restype = P
+            f.argtypes = [I, SP, S, S, S, P, P, C.POINTER(CommStruct), U]
+    L.fftw_b200_mpi_plan_r2r_2d.restype = P
+    L.fftw_b200_mpi_plan_r2r_2d.argtypes = [S, S, P, P, C.POINTER(CommStruct), I, I, U]
     for name in ("plan_dft_r2c_2d", "plan_dft_c2r_2d"):
         f = getattr(L, "fftw_b200_mpi_" + name)
         f.restype = P
@@ -180,6 +191,31 @@ class CommTranspose(CommPlan1D):
         self.L = lib.lib
         fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_transpose")
         self.plan = fn(n0, n1, howmany, block0, block1, in_ptr, out_ptr, C.byref(comm), int(flags))
+
+
+class CommPlanManyR2R(CommPlan1D):
+    """fftw_mpi_plan_many_r2r through the communicator interface: any rank >= 2, howmany interleaved tuples"""
+
+    def __init__(self, lib, n, comm, in_ptr, out_ptr, kinds, howmany=1, prec="d", flags=B.FFTW_ESTIMATE):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        nn = (C.c_ssize_t * len(n))(*n)
+        ks = (C.c_int * len(n))(*[B.R2R_KINDS[k] if isinstance(k, str) else int(k) for k in kinds])
+        fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_r2r")
+        self.plan = fn(len(n), nn, howmany, 0, 0, in_ptr, out_ptr, C.byref(comm), ks, int(flags))
+
+
+class CommPlanManyReal(CommPlan1D):
+    """fftw_mpi_plan_many_dft_r2c / _c2r through the communicator interface"""
+
+    def __init__(self, lib, n, comm, in_ptr, out_ptr, what="r2c", howmany=1, prec="d", flags=B.FFTW_ESTIMATE):
+        _declare(lib)
+        _declare_mpi(lib)
+        self.L = lib.lib
+        nn = (C.c_ssize_t * len(n))(*n)
+        fn = getattr(self.L, ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_plan_many_dft_" + what)
+        self.plan = fn(len(n), nn, howmany, 0, 0, in_ptr, out_ptr, C.byref(comm), int(flags))
 
 
 class CommPlanReal3D(CommPlan1D):

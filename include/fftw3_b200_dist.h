@@ -183,6 +183,27 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_
                                               const fftw_b200_comm *comm, int sign, unsigned flags);
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in,
                                               fftwf_complex *out, const fftw_b200_comm *comm, int sign, unsigned flags);
+/* Real data of any rank >= 3 and any howmany, both precisions (fftw_mpi_plan_many_dft_r2c / _c2r, mpi/api.c:650-760;
+ * rank 2 with howmany 1 takes the 2-D plan above): real slab [local_n0][n1]...[2 (n_last/2+1)][howmany] (padded),
+ * complex slab [local_n0][n1]...[n_last/2+1][howmany]; default blocks, natural layouts; c2r overwrites its input. */
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                   double *in, fftw_complex *out, const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                   fftw_complex *in, double *out, const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                    float *in, fftwf_complex *out, const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                    fftwf_complex *in, float *out, const fftw_b200_comm *comm, unsigned flags);
+/* r2r of any rank >= 2 and any howmany (fftw_mpi_plan_many_r2r / fftw_mpi_plan_r2r_2d, mpi/api.c:770-886): slab
+ * [local_n0][n1]...[howmany] reals, kind[i] along dimension i; default blocks; in == out or out of place. */
+fftw_b200_mpi_plan fftw_b200_mpi_plan_many_r2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                               double *in, double *out, const fftw_b200_comm *comm,
+                                               const fftw_r2r_kind *kind, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_r2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
+                                                float *in, float *out, const fftw_b200_comm *comm,
+                                                const fftwf_r2r_kind *kind, unsigned flags);
+fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, double *out, const fftw_b200_comm *comm,
+                                             fftw_r2r_kind kind0, fftw_r2r_kind kind1, unsigned flags);
 /* Wisdom across ranks (fftw_mpi_gather_wisdom / fftw_mpi_broadcast_wisdom, mpi/wisdom-api.c): after gather rank 0
  * holds the union of every rank's wisdom; after broadcast every rank has imported rank 0's.  Collective. */
 void fftw_b200_mpi_gather_wisdom(const fftw_b200_comm *comm);

@@ -442,3 +442,112 @@ def test_real_data_2d_through_the_communicator_interface(emu_lib, shape, P, inpl
         back[s0:s0 + b.shape[0]] = b
     assert O.rel_l2(got, ref) <= 2e-14, (shape, P)
     assert O.rel_l2(back / (n0 * n1), full) <= 2e-14, (shape, P)
+
+
+@pytest.mark.parametrize("shape,P,kinds,kw", [
+    ((12, 10), 2, ("REDFT10", "RODFT01"), {}),
+    ((9, 8), 3, ("R2HC", "DHT"), {"inplace": False}),
+    ((8, 6, 5), 2, ("RODFT00", "REDFT11", "HC2R"), {"howmany": 2}),
+    ((4, 6, 5, 3), 2, ("REDFT01", "REDFT10", "DHT", "RODFT10"), {}),
+    ((6, 5), 4, ("REDFT00", "RODFT11"), {"prec": "f"}),
+])
+def test_many_r2r_through_the_communicator_interface(emu_lib, shape, P, kinds, kw):
+    """fftw_mpi_plan_many_r2r shape (mpi/api.c:770-886): any rank >= 2, howmany interleaved tuples, both precisions,
+    against the oracle's separable r2r."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    howmany, prec, inplace = kw.get("howmany", 1), kw.get("prec", "d"), kw.get("inplace", True)
+    rdt = np.float32 if prec == "f" else np.float64
+    isz = np.dtype(rdt).itemsize
+    n0, n1 = shape[0], shape[1]
+    rest = int(np.prod(shape[2:])) * howmany if len(shape) > 2 else howmany
+    rng = np.random.default_rng(23)
+    full = rng.uniform(-0.5, 0.5, shape + ((howmany,) if howmany > 1 else ())).astype(rdt)
+    x64 = full.astype(np.float64)
+    ref = O.r2r(np.moveaxis(x64, -1, 0), list(kinds), rank=len(shape)) if howmany > 1 else O.r2r(x64, list(kinds))
+    if howmany > 1:
+        ref = np.moveaxis(ref, 0, -1)
+
+    def rank_main(r, comm):
+        b0, b1 = -(-n0 // P), -(-n1 // P)
+        ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
+        cnt = max(b0 * n1, b1 * n0) * rest
+        a = L.fftw_b200_device_malloc(max(cnt, 1) * isz)
+        b = a if inplace else L.fftw_b200_device_malloc(max(cnt, 1) * isz)
+        view = lambda ptr: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_ubyte)), shape=(max(cnt, 1) * isz,)).view(rdt)
+        view(a)[:ln0 * n1 * rest] = full[s0:s0 + ln0].reshape(-1)
+        pl = D.CommPlanManyR2R(lib, list(shape), comm, a, b, kinds, howmany=howmany, prec=prec)
+        assert pl.plan
+        pl.execute()
+        out = view(b)[:ln0 * n1 * rest].copy().reshape((ln0,) + full.shape[1:])
+        pl.destroy()
+        L.fftw_b200_device_free(a)
+        if not inplace:
+            L.fftw_b200_device_free(b)
+        return s0, out
+
+    res = _threads(P, rank_main)
+    got = np.zeros(full.shape, np.float64)
+    for s0, arr in res:
+        got[s0:s0 + arr.shape[0]] = arr
+    assert O.rel_l2(got, ref) <= (5e-6 if prec == "f" else 3e-14), (shape, P, kinds, kw)
+
+
+@pytest.mark.parametrize("shape,P,kw", [
+    ((8, 6, 10), 2, {"howmany": 2}),
+    ((6, 5, 4, 7), 3, {}),
+    ((8, 6, 9), 2, {"prec": "f", "inplace": True}),
+    ((5, 4, 6), 4, {"howmany": 3, "inplace": True}),
+])
+def test_many_real_data_through_the_communicator_interface(emu_lib, shape, P, kw):
+    """fftw_mpi_plan_many_dft_r2c / _c2r shapes (mpi/api.c:650-760): rank >= 3, howmany interleaved tuples, both
+    precisions; r2c against numpy's rfftn, c2r back to N x."""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    howmany, prec, inplace = kw.get("howmany", 1), kw.get("prec", "d"), kw.get("inplace", False)
+    rdt, cdt = (np.float32, np.complex64) if prec == "f" else (np.float64, np.complex128)
+    n0, n1, nl = shape[0], shape[1], shape[-1]
+    h = nl // 2 + 1
+    mid = shape[2:-1]
+    rng = np.random.default_rng(29)
+    full = rng.uniform(-0.5, 0.5, shape + (howmany,)).astype(rdt)
+    ref = np.fft.rfftn(full.astype(np.float64), axes=tuple(range(len(shape))))
+    Rc = int(np.prod(mid)) * h * howmany                      # complex numbers per (i0, i1)
+
+    def rank_main(r, comm):
+        b0, b1 = -(-n0 // P), -(-n1 // P)
+        ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
+        cnt = max(b0 * n1, b1 * n0) * Rc                      # complex elements
+        csz = np.dtype(cdt).itemsize
+        cplx = L.fftw_b200_device_malloc(max(cnt, 1) * csz)
+        real = cplx if inplace else L.fftw_b200_device_malloc(max(cnt, 1) * csz)
+        rview = np.ctypeslib.as_array(C.cast(real, C.POINTER(C.c_ubyte)), shape=(max(cnt, 1) * csz,)).view(rdt)
+        cview = np.ctypeslib.as_array(C.cast(cplx, C.POINTER(C.c_ubyte)), shape=(max(cnt, 1) * csz,)).view(cdt)
+        pshape = (ln0, n1) + mid + (2 * h, howmany)
+        pad = rview[:int(np.prod(pshape))].reshape(pshape)
+        fwd = D.CommPlanManyReal(lib, list(shape), comm, real, cplx, "r2c", howmany=howmany, prec=prec)
+        bwd = D.CommPlanManyReal(lib, list(shape), comm, cplx, real, "c2r", howmany=howmany, prec=prec)
+        assert fwd.plan and bwd.plan
+        pad[..., :nl, :] = full[s0:s0 + ln0]
+        fwd.execute()
+        cshape = (ln0, n1) + mid + (h, howmany)
+        spec = cview[:int(np.prod(cshape))].copy().reshape(cshape)
+        bwd.execute()
+        back = rview[:int(np.prod(pshape))].reshape(pshape)[..., :nl, :].copy()
+        fwd.destroy(); bwd.destroy()
+        L.fftw_b200_device_free(cplx)
+        if not inplace:
+            L.fftw_b200_device_free(real)
+        return s0, spec, back
+
+    res = _threads(P, rank_main)
+    got = np.zeros(ref.shape, np.complex128)
+    back = np.zeros(full.shape)
+    for s0, spec, b in res:
+        got[s0:s0 + spec.shape[0]] = spec
+        back[s0:s0 + b.shape[0]] = b
+    tol = 5e-6 if prec == "f" else 3e-14
+    assert O.rel_l2(got, ref) <= tol, (shape, P, kw)
+    assert O.rel_l2(back / float(np.prod(shape)), full.astype(np.float64)) <= tol, (shape, P, kw)
