@@ -1073,6 +1073,8 @@ void fftw_b200_mpi_execute(fftw_b200_mpi_plan p)
             int st;
             run(p->local);
             for (st = 0; st < 3; ++st) { barrier(p); fftw_b200_dist_execute_stage(p->fused, st); }
+            barrier(p);                                 /* the peers have finished reading my exchange buffer: the
+                                                           caller may destroy the plan (found with AddressSanitizer) */
         } else {
             fftw_b200_dist_execute_stage(p->fused, 0);
             barrier(p);                                 /* every row block has landed in my exchange buffer */
