@@ -681,7 +681,7 @@ static fftw_b200_mpi_plan mkreal3d(int what, ptrdiff_t n0, ptrdiff_t n1, ptrdiff
    complex matrix (scatter column blocks | FFT_n0 | push rows back: the general path above with h playing n1 and no
    local pass); c2r = the same backward, then the local c2r of the rows.  Natural layouts only (the TRANSPOSED
    flags return NULL).  The complex slab is overwritten by c2r, as in fftw_mpi. */
-static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in, void *out, const fftw_b200_comm *comm,
+static fftw_b200_mpi_plan mkreal2d(int prec, int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in, void *out, const fftw_b200_comm *comm,
                                    unsigned flags)
 {
     fftw_b200_mpi_plan p;
@@ -689,8 +689,8 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
     int d, P, r, ok;
     int64_t h = n1 / 2 + 1, alloc;
     const int sign = c2r ? 1 : -1;
-    const size_t cs = 16;
-    double *real = (double *)(c2r ? out : in);
+    const size_t cs = csize(prec);
+    char *real = (char *)(c2r ? out : in);
     char *cplx = (char *)(c2r ? in : out);
     unsigned pflags = flags & ~(FFTW_MPI_TRANSPOSED_OUT | FFTW_MPI_TRANSPOSED_IN | FFTW_MPI_SCRAMBLED_IN | FFTW_MPI_SCRAMBLED_OUT);
     if (!comm || !comm->allgather || n0 <= 0 || n1 <= 0 || !in || !out) return NULL;
@@ -700,7 +700,7 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
     if (b2d_pointer_is_device(in) != 1 || b2d_pointer_is_device(out) != 1) return NULL;
     p = (fftw_b200_mpi_plan)calloc(1, sizeof *p);
     if (!p) return NULL;
-    p->kind = c2r ? 8 : 7; p->prec = B2D_F64; p->rank = r; p->nranks = P; p->rnk = 2; p->sign = sign;
+    p->kind = c2r ? 8 : 7; p->prec = prec; p->rank = r; p->nranks = P; p->rnk = 2; p->sign = sign;
     p->n0 = n0; p->n1 = h; p->R = 1;
     p->b0 = blk(n0, P); p->b1 = blk(h, P);
     p->ln0 = share(n0, P, r); p->ln1 = share(h, P, r);
@@ -713,12 +713,12 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
     if (ok && p->ln0 > 0) {
         /* rows: padded real rows <-> this rank's complex rows [ln0][h] */
         memset(&q, 0, sizeof q);
-        q.prec = B2D_F64; q.kind = c2r ? B2_C2R : B2_R2C; q.flags = pflags;
+        q.prec = prec; q.kind = c2r ? B2_C2R : B2_R2C; q.flags = pflags;
         b2_tensor_init(&q.sz, 0); b2_tensor_init(&q.vecsz, 0);
         dim(&q.sz, n1, c2r ? 2 : 1, c2r ? 1 : 2);
         dim(&q.vecsz, p->ln0, 2 * h, 2 * h);
-        if (c2r) { q.in0 = cplx; q.in1 = cplx + 8; q.out0 = real; }
-        else { q.in0 = real; q.out0 = cplx; q.out1 = cplx + 8; }
+        if (c2r) { q.in0 = cplx; q.in1 = cplx + cs / 2; q.out0 = real; }
+        else { q.in0 = real; q.out0 = cplx; q.out1 = cplx + cs / 2; }
         p->local = b2_mkplan(&q);
         if (!p->local) ok = 0;
     }
@@ -727,14 +727,14 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
         for (d = 0; d < P && ok && p->ln0 > 0; ++d) {
             int64_t l1 = share(h, P, d);
             if (!l1) continue;
-            problem(&q, B2D_F64, pflags | B2F_ESTIMATE, cplx + cs * (size_t)(p->b1 * d), (char *)p->peer_z[d] + cs * (size_t)(p->s0 * l1), -1);
+            problem(&q, prec, pflags | B2F_ESTIMATE, cplx + cs * (size_t)(p->b1 * d), (char *)p->peer_z[d] + cs * (size_t)(p->s0 * l1), -1);
             dim(&q.vecsz, p->ln0, 2 * h, 2 * l1);
             dim(&q.vecsz, l1, 2, 2);
             p->scatter[d] = b2_mkplan(&q);
             if (!p->scatter[d]) ok = 0;
         }
         if (ok && p->ln1 > 0) {
-            problem(&q, B2D_F64, pflags, p->zbuf, p->zbuf, sign);
+            problem(&q, prec, pflags, p->zbuf, p->zbuf, sign);
             dim(&q.sz, n0, 2 * p->ln1, 2 * p->ln1);
             dim(&q.vecsz, p->ln1, 2, 2);
             p->z = b2_mkplan(&q);
@@ -743,7 +743,7 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
                 /* rows of owner d -> its complex slab [ln0(d)][h] at column s1 */
                 int64_t l0 = share(n0, P, d);
                 if (!l0) continue;
-                problem(&q, B2D_F64, pflags | B2F_ESTIMATE, p->zbuf + cs * (size_t)(p->b0 * d * p->ln1),
+                problem(&q, prec, pflags | B2F_ESTIMATE, p->zbuf + cs * (size_t)(p->b0 * d * p->ln1),
                         (char *)p->peer_out[d] + cs * (size_t)p->s1, -1);
                 dim(&q.vecsz, l0, 2 * p->ln1, 2 * h);
                 dim(&q.vecsz, p->ln1, 2, 2);
@@ -758,10 +758,10 @@ static fftw_b200_mpi_plan mkreal2d(int c2r, ptrdiff_t n0, ptrdiff_t n1, void *in
 
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, fftw_complex *out,
                                                  const fftw_b200_comm *comm, unsigned flags)
-{ return mkreal2d(0, n0, n1, in, out, comm, flags); }
+{ return mkreal2d(B2D_F64, 0, n0, n1, in, out, comm, flags); }
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_c2r_2d(ptrdiff_t n0, ptrdiff_t n1, fftw_complex *in, double *out,
                                                  const fftw_b200_comm *comm, unsigned flags)
-{ return mkreal2d(1, n0, n1, in, out, comm, flags); }
+{ return mkreal2d(B2D_F64, 1, n0, n1, in, out, comm, flags); }
 
 fftw_b200_mpi_plan fftw_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, double *in, fftw_complex *out,
                                                  const fftw_b200_comm *comm, unsigned flags)
@@ -970,27 +970,58 @@ fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, 
                                                    double *in, fftw_complex *out, const fftw_b200_comm *comm, unsigned flags)
 {
     if (iblock || oblock) return NULL;
-    if (rnk == 2 && howmany == 1) return mkreal2d(0, n[0], n[1], in, out, comm, flags);
+    if (rnk == 2 && howmany == 1) return mkreal2d(B2D_F64, 0, n[0], n[1], in, out, comm, flags);
     return mkrealnd(B2D_F64, 0, rnk, n, howmany, in, out, comm, flags);
 }
 fftw_b200_mpi_plan fftw_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
                                                    fftw_complex *in, double *out, const fftw_b200_comm *comm, unsigned flags)
 {
     if (iblock || oblock) return NULL;
-    if (rnk == 2 && howmany == 1) return mkreal2d(1, n[0], n[1], in, out, comm, flags);
+    if (rnk == 2 && howmany == 1) return mkreal2d(B2D_F64, 1, n[0], n[1], in, out, comm, flags);
     return mkrealnd(B2D_F64, 1, rnk, n, howmany, in, out, comm, flags);
 }
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_r2c(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
                                                     float *in, fftwf_complex *out, const fftw_b200_comm *comm, unsigned flags)
 {
     if (iblock || oblock) return NULL;
+    if (rnk == 2 && howmany == 1) return mkreal2d(B2D_F32, 0, n[0], n[1], in, out, comm, flags);
     return mkrealnd(B2D_F32, 0, rnk, n, howmany, in, out, comm, flags);
 }
 fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_dft_c2r(int rnk, const ptrdiff_t *n, ptrdiff_t howmany, ptrdiff_t iblock, ptrdiff_t oblock,
                                                     fftwf_complex *in, float *out, const fftw_b200_comm *comm, unsigned flags)
 {
     if (iblock || oblock) return NULL;
+    if (rnk == 2 && howmany == 1) return mkreal2d(B2D_F32, 1, n[0], n[1], in, out, comm, flags);
     return mkrealnd(B2D_F32, 1, rnk, n, howmany, in, out, comm, flags);
+}
+
+/* single-precision basic forms: through the general plans (the fused 3-D plans of dist.c are double precision) */
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_r2c_2d(ptrdiff_t n0, ptrdiff_t n1, float *in, fftwf_complex *out,
+                                                  const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal2d(B2D_F32, 0, n0, n1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_c2r_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_complex *in, float *out,
+                                                  const fftw_b200_comm *comm, unsigned flags)
+{ return mkreal2d(B2D_F32, 1, n0, n1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, float *in, fftwf_complex *out,
+                                                  const fftw_b200_comm *comm, unsigned flags)
+{ ptrdiff_t n[3]; n[0] = n0; n[1] = n1; n[2] = n2; return mkrealnd(B2D_F32, 0, 3, n, 1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in, float *out,
+                                                  const fftw_b200_comm *comm, unsigned flags)
+{ ptrdiff_t n[3]; n[0] = n0; n[1] = n1; n[2] = n2; return mkrealnd(B2D_F32, 1, 3, n, 1, in, out, comm, flags); }
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_r2r_2d(ptrdiff_t n0, ptrdiff_t n1, float *in, float *out, const fftw_b200_comm *comm,
+                                              fftwf_r2r_kind kind0, fftwf_r2r_kind kind1, unsigned flags)
+{
+    ptrdiff_t n[2]; int k[2];
+    n[0] = n0; n[1] = n1; k[0] = (int)kind0; k[1] = (int)kind1;
+    return mkr2r(B2D_F32, 2, n, 1, in, out, comm, k, flags);
+}
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, float *in, float *out,
+                                              const fftw_b200_comm *comm, fftwf_r2r_kind kind0, fftwf_r2r_kind kind1,
+                                              fftwf_r2r_kind kind2, unsigned flags)
+{
+    ptrdiff_t n[3]; int k[3];
+    n[0] = n0; n[1] = n1; n[2] = n2; k[0] = (int)kind0; k[1] = (int)kind1; k[2] = (int)kind2;
+    return mkr2r(B2D_F32, 3, n, 1, in, out, comm, k, flags);
 }
 
 /* ------------------------------------------------------------------ wisdom across ranks (mpi/wisdom-api.c:24-103)

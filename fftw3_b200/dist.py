@@ -136,10 +136,17 @@ def _declare_mpi(lib):
             f.argtypes = [I, SP, S, S, S, P, P, C.POINTER(CommStruct), U]
     L.fftw_b200_mpi_plan_r2r_2d.restype = P
     L.fftw_b200_mpi_plan_r2r_2d.argtypes = [S, S, P, P, C.POINTER(CommStruct), I, I, U]
-    for name in ("plan_dft_r2c_2d", "plan_dft_c2r_2d"):
-        f = getattr(L, "fftw_b200_mpi_" + name)
+    for pfx in ("fftw_b200_mpi_", "fftwf_b200_mpi_"):
+        for name in ("plan_dft_r2c_2d", "plan_dft_c2r_2d"):
+            f = getattr(L, pfx + name)
+            f.restype = P
+            f.argtypes = [S, S, P, P, C.POINTER(CommStruct), U]
+    for name, extra in (("plan_dft_r2c_3d", []), ("plan_dft_c2r_3d", []), ("plan_r2r_3d", [I, I, I])):
+        f = getattr(L, "fftwf_b200_mpi_" + name)
         f.restype = P
-        f.argtypes = [S, S, P, P, C.POINTER(CommStruct), U]
+        f.argtypes = [S, S, S, P, P, C.POINTER(CommStruct)] + extra + [U]
+    L.fftwf_b200_mpi_plan_r2r_2d.restype = P
+    L.fftwf_b200_mpi_plan_r2r_2d.argtypes = [S, S, P, P, C.POINTER(CommStruct), I, I, U]
     for name, extra in (("plan_dft_r2c_3d", []), ("plan_dft_c2r_3d", []), ("plan_r2r_3d", [I, I, I])):
         f = getattr(L, "fftw_b200_mpi_" + name)
         f.restype = P
@@ -221,19 +228,21 @@ class CommPlanManyReal(CommPlan1D):
 class CommPlanReal3D(CommPlan1D):
     """fftw_mpi_plan_dft_r2c_3d / _c2r_3d / fftw_mpi_plan_r2r_3d through the communicator interface (double)"""
 
-    def __init__(self, lib, n, comm, in_ptr, out_ptr, what="r2c", kinds=None, flags=B.FFTW_ESTIMATE):
+    def __init__(self, lib, n, comm, in_ptr, out_ptr, what="r2c", kinds=None, flags=B.FFTW_ESTIMATE, prec="d"):
         _declare(lib)
         _declare_mpi(lib)
         self.L = lib.lib
+        pfx = ("fftwf_" if prec == "f" else "fftw_") + "b200_mpi_"
         if what == "r2r":
             ks = [B.R2R_KINDS[k] if isinstance(k, str) else int(k) for k in kinds]
-            self.plan = self.L.fftw_b200_mpi_plan_r2r_3d(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), ks[0], ks[1], ks[2], int(flags))
+            if len(n) == 2:
+                self.plan = getattr(self.L, pfx + "plan_r2r_2d")(n[0], n[1], in_ptr, out_ptr, C.byref(comm), ks[0], ks[1], int(flags))
+            else:
+                self.plan = getattr(self.L, pfx + "plan_r2r_3d")(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), ks[0], ks[1], ks[2], int(flags))
         elif len(n) == 2:
-            fn = self.L.fftw_b200_mpi_plan_dft_r2c_2d if what == "r2c" else self.L.fftw_b200_mpi_plan_dft_c2r_2d
-            self.plan = fn(n[0], n[1], in_ptr, out_ptr, C.byref(comm), int(flags))
+            self.plan = getattr(self.L, pfx + "plan_dft_%s_2d" % what)(n[0], n[1], in_ptr, out_ptr, C.byref(comm), int(flags))
         else:
-            fn = self.L.fftw_b200_mpi_plan_dft_r2c_3d if what == "r2c" else self.L.fftw_b200_mpi_plan_dft_c2r_3d
-            self.plan = fn(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), int(flags))
+            self.plan = getattr(self.L, pfx + "plan_dft_%s_3d" % what)(n[0], n[1], n[2], in_ptr, out_ptr, C.byref(comm), int(flags))
 
 
 class CommPlan:

@@ -204,6 +204,20 @@ fftw_b200_mpi_plan fftwf_b200_mpi_plan_many_r2r(int rnk, const ptrdiff_t *n, ptr
                                                 const fftwf_r2r_kind *kind, unsigned flags);
 fftw_b200_mpi_plan fftw_b200_mpi_plan_r2r_2d(ptrdiff_t n0, ptrdiff_t n1, double *in, double *out, const fftw_b200_comm *comm,
                                              fftw_r2r_kind kind0, fftw_r2r_kind kind1, unsigned flags);
+/* single precision: the basic real-data and r2r forms (through the general plans) */
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_r2c_2d(ptrdiff_t n0, ptrdiff_t n1, float *in, fftwf_complex *out,
+                                                  const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_c2r_2d(ptrdiff_t n0, ptrdiff_t n1, fftwf_complex *in, float *out,
+                                                  const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_r2c_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, float *in, fftwf_complex *out,
+                                                  const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_dft_c2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, fftwf_complex *in, float *out,
+                                                  const fftw_b200_comm *comm, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_r2r_2d(ptrdiff_t n0, ptrdiff_t n1, float *in, float *out, const fftw_b200_comm *comm,
+                                              fftwf_r2r_kind kind0, fftwf_r2r_kind kind1, unsigned flags);
+fftw_b200_mpi_plan fftwf_b200_mpi_plan_r2r_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, float *in, float *out,
+                                              const fftw_b200_comm *comm, fftwf_r2r_kind kind0, fftwf_r2r_kind kind1,
+                                              fftwf_r2r_kind kind2, unsigned flags);
 /* Wisdom across ranks (fftw_mpi_gather_wisdom / fftw_mpi_broadcast_wisdom, mpi/wisdom-api.c): after gather rank 0
  * holds the union of every rank's wisdom; after broadcast every rank has imported rank 0's.  Collective. */
 void fftw_b200_mpi_gather_wisdom(const fftw_b200_comm *comm);

@@ -551,3 +551,70 @@ def test_many_real_data_through_the_communicator_interface(emu_lib, shape, P, kw
     tol = 5e-6 if prec == "f" else 3e-14
     assert O.rel_l2(got, ref) <= tol, (shape, P, kw)
     assert O.rel_l2(back / float(np.prod(shape)), full.astype(np.float64)) <= tol, (shape, P, kw)
+
+
+@pytest.mark.parametrize("shape,P", [((8, 10), 2), ((6, 5, 8), 3)])
+def test_single_precision_basic_real_and_r2r_forms(emu_lib, shape, P):
+    """fftwf_b200_mpi_plan_dft_r2c_2d/_3d, _c2r_2d/_3d, _r2r_2d/_3d: the single-precision basic forms"""
+    lib = emu_lib
+    D._declare(lib)
+    L = lib.lib
+    nl = shape[-1]
+    h = nl // 2 + 1
+    n0, n1 = shape[0], shape[1]
+    mid = shape[2:-1]
+    rng = np.random.default_rng(31)
+    full = rng.uniform(-0.5, 0.5, shape).astype(np.float32)
+    ref = np.fft.rfftn(full.astype(np.float64))
+    kinds = ("REDFT10", "RODFT01", "DHT")[:len(shape)]
+    ref_r2r = O.r2r(full.astype(np.float64), list(kinds))
+    # rank 2: the halved dimension is exchanged (rows of h complex); rank 3: n1 is exchanged
+    cols = h if len(shape) == 2 else n1
+    Rc = 1 if len(shape) == 2 else int(np.prod(mid)) * h
+
+    def rank_main(r, comm):
+        b0, b1 = -(-n0 // P), -(-cols // P)
+        ln0, s0 = max(0, min(b0, n0 - b0 * r)), min(b0 * r, n0)
+        cnt = max(b0 * cols, b1 * n0) * Rc
+        cplx = L.fftw_b200_device_malloc(max(cnt, 1) * 8)
+        real = L.fftw_b200_device_malloc(max(cnt, 1) * 8)
+        rview = np.ctypeslib.as_array(C.cast(real, C.POINTER(C.c_float)), shape=(max(cnt, 1) * 2,))
+        cview = np.ctypeslib.as_array(C.cast(cplx, C.POINTER(C.c_float)), shape=(max(cnt, 1) * 2,)).view(np.complex64)
+        pshape = (ln0,) + shape[1:-1] + (2 * h,)
+        pad = rview[:int(np.prod(pshape))].reshape(pshape)
+        fwd = D.CommPlanReal3D(lib, shape, comm, real, cplx, "r2c", prec="f")
+        bwd = D.CommPlanReal3D(lib, shape, comm, cplx, real, "c2r", prec="f")
+        assert fwd.plan and bwd.plan
+        pad[..., :nl] = full[s0:s0 + ln0]
+        fwd.execute()
+        cshape = (ln0,) + shape[1:-1] + (h,)
+        spec = cview[:int(np.prod(cshape))].copy().reshape(cshape)
+        bwd.execute()
+        back = rview[:int(np.prod(pshape))].reshape(pshape)[..., :nl].copy()
+        fwd.destroy(); bwd.destroy()
+        # r2r in place on a slab of the natural shape
+        rr = L.fftw_b200_device_malloc(max(-(-n0 // P) * n1, -(-n1 // P) * n0, 1) * int(np.prod(shape[2:])) * 4 if len(shape) > 2
+                                       else max(-(-n0 // P) * n1, -(-n1 // P) * n0, 1) * 4)
+        nel = ln0 * int(np.prod(shape[1:]))
+        v2 = np.ctypeslib.as_array(C.cast(rr, C.POINTER(C.c_float)), shape=(max(nel, 1),))
+        v2[:nel] = full[s0:s0 + ln0].reshape(-1)
+        pr = D.CommPlanReal3D(lib, shape, comm, rr, rr, "r2r", kinds=kinds, prec="f")
+        assert pr.plan
+        pr.execute()
+        r2r_out = v2[:nel].copy().reshape((ln0,) + shape[1:])
+        pr.destroy()
+        for ptr in (cplx, real, rr):
+            L.fftw_b200_device_free(ptr)
+        return s0, spec, back, r2r_out
+
+    res = _threads(P, rank_main)
+    got = np.zeros(ref.shape, np.complex128)
+    back = np.zeros(shape)
+    got_r2r = np.zeros(shape)
+    for s0, spec, b, rr in res:
+        got[s0:s0 + spec.shape[0]] = spec
+        back[s0:s0 + b.shape[0]] = b
+        got_r2r[s0:s0 + rr.shape[0]] = rr
+    assert O.rel_l2(got, ref) <= 5e-6
+    assert O.rel_l2(back / float(np.prod(shape)), full.astype(np.float64)) <= 5e-6
+    assert O.rel_l2(got_r2r, ref_r2r) <= 5e-6
