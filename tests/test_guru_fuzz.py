@@ -225,3 +225,17 @@ def test_random_guru_c2c_single_precision(host_lib, seed):
         mask = np.ones(osz, dtype=bool)
         mask[oidx.reshape(-1)] = False
         assert np.all(b[mask] == np.complex64(9 + 9j))
+
+
+@pytest.mark.parametrize("seed", range(0, 120, 4))
+def test_random_guru_problems_through_the_host_pipeline(emu_lib, seed, monkeypatch):
+    """The same seeded guru problems with every batched host-array problem forced through the chunk pipeline of
+    csrc/host/exec.c (FFTW3_B200_PIPE_MIN_KB=1): whatever layout the fuzz draws, cutting the outermost batch dimension
+    must either be refused (chunks would interleave) or give the same result."""
+    monkeypatch.setenv("FFTW3_B200_PIPE_MIN_KB", "1")
+    test_random_guru_c2c(emu_lib, seed)
+    if seed < 60:
+        test_random_guru_r2r(emu_lib, seed)
+    if seed < 40:
+        test_random_guru_r2c_c2r(emu_lib, seed)
+        test_random_guru_c2c_single_precision(emu_lib, seed)
